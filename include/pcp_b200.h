@@ -1,0 +1,179 @@
+/*
+ * pcp_b200.h - C ABI of libpcp_b200.so: the B200 (sm_100a) point->BEV front end.
+ *
+ * This is the drop-in boundary for the reference's hot path (quan-dao/practical-collab-perception,
+ * an OpenPCDet fork).  Each entry point names the reference code it replaces (paths relative to the
+ * reference root).  The reference reaches this arithmetic through torch / torch_scatter /
+ * roiaware_pool3d_cuda calls inside three Python call sites; a maintainer binds this library with
+ * ctypes - no torch types cross the boundary.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the parameter name ends in _host;
+ *    the library never allocates, frees or retains caller memory;
+ *  - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no entry point
+ *    synchronises the device or the stream; results that size later tensors (`counts`) are read back
+ *    by the caller (one 32-byte D2H copy);
+ *  - scratch lives in a caller-provided workspace of pcp_workspace_bytes() bytes; the workspace filled
+ *    by pcp_voxelize() is consumed by pcp_pfn(), pcp_segment_reduce() and pcp_bev_scatter_ws(), which
+ *    must be given the same (n_points, max_frames, nx, ny) so that they find the same layout;
+ *  - return value: 0 = ok, < 0 = invalid argument (PCP_E_*), > 0 = a cudaError_t from a launch.
+ *    pcp_last_error_string() describes the last failure on the calling thread.  Never exit()s
+ *    (contrast pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:350-354);
+ *  - stateless and re-entrant: no globals, no static device buffers; safe for one process per GPU or
+ *    several streams in one process; every call is CUDA-graph capturable.
+ */
+#ifndef PCP_B200_H_
+#define PCP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCP_ABI_VERSION 1
+
+#define PCP_E_INVALID   (-1)   /* null pointer, negative size, unsupported shape */
+#define PCP_E_WORKSPACE (-2)   /* workspace smaller than pcp_workspace_bytes() */
+#define PCP_E_UNSUPPORTED (-3) /* configuration outside what the kernels implement */
+
+/* indices into the int32 `counts[PCP_COUNTS_LEN]` block written by pcp_voxelize() */
+#define PCP_COUNTS_LEN        8
+#define PCP_COUNT_PILLARS     0   /* P  = number of non-empty pillars                      */
+#define PCP_COUNT_KEPT        1   /* N' = points that survived the range cull              */
+#define PCP_COUNT_FRAMES      2   /* max frame index among pillars + 1 (0 if P == 0)        */
+#define PCP_COUNT_BAD_FRAME   3   /* points whose frame index was < 0 or >= max_frames      */
+#define PCP_COUNT_MAX_PER_PILLAR 4 /* largest number of points in one pillar               */
+
+/* Constants DynamicPillarVFE.__init__ derives: pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py:77-89.
+ * x/y/z_offset are computed by the HOST exactly as the reference does (voxel/2 + range_min, :80-82) and
+ * passed as fp32, because their rounding depends on the caller's scalar types. */
+typedef struct pcp_grid {
+  float range_min_x, range_min_y;  /* point_cloud_range[0], [1]            */
+  float voxel_x, voxel_y;          /* voxel_size[0], [1]                   */
+  float x_offset, y_offset, z_offset;
+  int32_t nx, ny;                  /* grid_size[0], grid_size[1]; nz == 1  */
+} pcp_grid;
+
+/* Feature assembly + PFN stack description: dynamic_pillar_vfe.py:53-75,118-126. */
+typedef struct pcp_pfn_desc {
+  int32_t c_raw;             /* NUM_RAW_POINT_FEATURES: columns 1..c_raw of a point row          */
+  int32_t use_absolute_xyz;  /* USE_ABSLOTE_XYZ: 1 -> features start at column 1, 0 -> column 4 */
+  int32_t with_distance;     /* WITH_DISTANCE: append ||xyz||                                  */
+  int32_t num_layers;        /* 1 or 2 PFNLayerV2                                                */
+  int32_t hidden;            /* layer-0 output width when num_layers == 2 (NUM_FILTERS[0]/2 = 32)*/
+  int32_t c_out;             /* NUM_FILTERS[-1] (64)                                             */
+} pcp_pfn_desc;
+
+int  pcp_abi_version(void);
+const char* pcp_last_error_string(void);
+
+/* Bytes of scratch for a batch of n_points rows over max_frames frames on an nx x ny grid. */
+size_t pcp_workspace_bytes(int64_t n_points, int32_t max_frames, int32_t nx, int32_t ny);
+
+/* Number of float32 elements of the packed PFN parameter block pcp_pack_pfn_params() writes. */
+size_t pcp_pfn_param_floats(const pcp_pfn_desc* desc);
+
+/*
+ * Fold BatchNorm1d(eval) into per-channel scale/shift and lay the PFN weights out for pcp_pfn().
+ * Replaces the per-forward nn.Linear / nn.BatchNorm1d parameter reads of PFNLayerV2
+ * (dynamic_pillar_vfe.py:24-39).  alpha = gamma / sqrt(var + eps), beta = bias - mean * alpha
+ * (ATen's eval-mode batch_norm transform).  For use_norm == 0 pass bn_* = NULL and lin_bias != NULL.
+ * w0: (w0_out, c_in) row-major, w1: (c_out, 2 * hidden) row-major or NULL when num_layers == 1.
+ */
+int pcp_pack_pfn_params(const pcp_pfn_desc* desc,
+                        const float* w0, const float* lin_bias0,
+                        const float* bn0_weight, const float* bn0_bias, const float* bn0_mean, const float* bn0_var,
+                        const float* w1, const float* lin_bias1,
+                        const float* bn1_weight, const float* bn1_bias, const float* bn1_mean, const float* bn1_var,
+                        float eps, float* packed_out, void* stream);
+
+/*
+ * Quantise + cull + linearise + compact.  Replaces dynamic_pillar_vfe.py:98-108 (floor((xy-min)/voxel),
+ * range mask, merge_coords, torch.unique(return_inverse, return_counts)) and :137-143 (voxel_coords).
+ *   points            (n_points, row_stride) fp32, column 0 = frame index, 1..3 = x,y,z
+ *   point_pillar_out  (n_points) int32: pillar rank of each input row, -1 for culled rows.  The
+ *                     reference's unq_inv is this array with the -1 entries removed.  May be NULL.
+ *   voxel_coords_out  (pillar_capacity, 4) int32 rows (frame, 0, y, x), ascending linear key, first P valid
+ *   pillar_count_out  (pillar_capacity) int32 points per pillar (unq_cnt).  May be NULL.
+ *   counts_out        int32[PCP_COUNTS_LEN]
+ * Points whose frame index is outside [0, max_frames) are dropped and counted in PCP_COUNT_BAD_FRAME.
+ * Non-finite x or y are culled (the reference's float->int cast of NaN is undefined behaviour).
+ */
+int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
+                 const pcp_grid* grid, void* workspace, size_t workspace_bytes,
+                 int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
+                 int64_t pillar_capacity, int32_t* counts_out, void* stream);
+
+/*
+ * Pillar feature network.  Replaces dynamic_pillar_vfe.py:110-129 (scatter_mean, f_cluster, f_center,
+ * concat) and PFNLayerV2.forward :35-46 for every layer, fused: no per-point intermediate reaches HBM.
+ *   pillar_features_out (pillar_capacity, c_out) fp32, first P rows valid.
+ *   pillar_mean_out     (pillar_capacity, 3) fp32 per-pillar mean xyz (points_mean, :110).  May be NULL.
+ */
+int pcp_pfn(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames, const pcp_grid* grid,
+            const pcp_pfn_desc* desc, const float* packed_params,
+            const void* workspace, size_t workspace_bytes,
+            float* pillar_features_out, float* pillar_mean_out, int64_t pillar_capacity, void* stream);
+
+/*
+ * Segmented reduction of arbitrary per-point values over the pillars found by pcp_voxelize():
+ * torch_scatter.scatter_mean / scatter_max (call sites dynamic_pillar_vfe.py:40,110).
+ *   values (n_points, value_stride) fp32 indexed by ORIGINAL row number, first `channels` columns reduced
+ *   mode   0 = mean (sum in ascending row order / count), 1 = max
+ *   out    (pillar_capacity, channels)
+ */
+int pcp_segment_reduce(const float* values, int64_t value_stride, int32_t channels, int32_t mode,
+                       int64_t n_points, int32_t max_frames, int32_t nx, int32_t ny,
+                       const void* workspace, size_t workspace_bytes,
+                       float* out, int64_t pillar_capacity, void* stream);
+
+/*
+ * Dense BEV canvas from the workspace left by pcp_voxelize() (fast path: no search, no memset; every
+ * canvas element is written exactly once).  Replaces PointPillarScatter.forward,
+ * pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-37.
+ *   canvas_out (num_frames, channels, ny, nx) fp32.
+ */
+int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels, int32_t num_frames,
+                       int64_t n_points, int32_t max_frames, const pcp_grid* grid,
+                       const void* workspace, size_t workspace_bytes,
+                       float* canvas_out, void* stream);
+
+/*
+ * Dense BEV canvas from arbitrary (pillar_features, voxel_coords) - the generic PointPillarScatter for
+ * callers that did not run pcp_voxelize().  cell_map_scratch: (num_frames * ny * nx) int32 scratch.
+ * Rows with coordinates outside the canvas are ignored; duplicate coordinates: the highest row wins
+ * (the CPU reference's sequential index_put order).
+ */
+int pcp_bev_scatter(const float* pillar_features, const int32_t* voxel_coords, int64_t num_pillars,
+                    int32_t channels, int32_t num_frames, int32_t nx, int32_t ny,
+                    int32_t* cell_map_scratch, float* canvas_out, void* stream);
+
+/* max(voxel_coords[:,0]) + 1 into *num_frames_out (device int32): pointpillar_scatter.py:17. */
+int pcp_num_frames(const int32_t* voxel_coords, int64_t num_pillars, int32_t* num_frames_out, void* stream);
+
+/*
+ * MoDAR point synthesis for all agents of one frame in one launch.  Replaces
+ * pcdet/datasets/v2x_sim/v2x_sim_dataset_ego.py:203-232 (== workspace/visualize_collab.py:118-142,253-262):
+ * points_in_boxes_gpu (roiaware_pool3d_kernel.cu:16-36,313-336) + unique + scatter(mean) * scale +
+ * modar[:, :3] += offset, then apply_se3_ (nuscenes_temporal_utils.py:66-70), then the row packing.
+ *   boxes        (total_boxes, 9) fp32: box7 | score | label, agents concatenated
+ *   box_offsets  int32[num_agents + 1] prefix offsets into boxes
+ *   foreground   (total_fg, 13) fp32: pt5 | sweep | inst | cls3 | flow3; may be NULL (no propagation)
+ *   fg_offsets   int32[num_agents + 1]
+ *   se3          (num_agents, 12) fp64: rows 0..2 of target_se3_agent, row-major
+ *   scale        flow multiplier: 2.0 * latency / sweep interval; 2.0 in the reference (:213); 0 = EXCHANGE_NOW
+ *   rows_out     (total_boxes, out_stride) fp32; with_batch_col != 0 prepends the frame index column
+ *                (collate_batch layout), i.e. 14 columns instead of 13
+ *   box_idx_out  (total_fg) int32 per-agent box index of each foreground point, -1 = none.  May be NULL.
+ */
+int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreground, const int32_t* fg_offsets,
+              const double* se3, int32_t num_agents, float scale, float max_sweep_idx,
+              int32_t with_batch_col, float batch_idx, float* rows_out, int64_t out_stride,
+              int32_t* box_idx_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PCP_B200_H_ */

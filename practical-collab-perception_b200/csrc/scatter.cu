@@ -1,0 +1,160 @@
+// scatter.cu - dense BEV canvas (reference: pointpillar_scatter.py:14-37).
+//
+// The reference zero-fills a canvas per frame, boolean-masks the pillars of that frame, index-assigns the
+// transposed features and finally torch.stack()s the frames (a second full copy).  Here every canvas
+// element is written exactly ONCE - zero or feature - by a kernel that is a pure streaming write:
+// a CTA owns a (8 rows x 128 columns) patch of one frame, looks the pillar rank of its 1024 cells up
+// once, and for every group of 4 channels gathers 16-byte pieces of the pillar rows, transposes them in
+// registers and issues 128-bit streaming stores, 512 contiguous bytes per warp per (channel, row).
+#include "common.cuh"
+
+namespace pcp {
+
+constexpr int kTileX = 128;   // columns per CTA (32 lanes x 4)
+constexpr int kTileY = 8;     // rows per CTA (one warp per row)
+
+__device__ __forceinline__ void st_stream_f4(float* p, float a, float b, float c, float d) {
+  // canvas lines are never re-read by this library: keep them from displacing pillar rows in L2
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// kXMajor = true : rank map is the voxelize workspace, laid out like the reference's linear key
+//                  (frame, cx, cy) -> b*nx*ny + cx*ny + cy
+// kXMajor = false: rank map is canvas-ordered (frame, y, x) (generic path)
+template <bool kXMajor>
+__global__ void __launch_bounds__(kTileY * 32)
+canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
+              float* __restrict__ canvas) {
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int y = blockIdx.y * kTileY + wy;
+  const int x0 = blockIdx.x * kTileX + lane * 4;
+  if (y >= ny || x0 >= nx) return;
+  const int64_t nxy = (int64_t)nx * ny;
+  int r[4];
+  if (kXMajor) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = (x0 + i < nx) ? __ldg(rank_map + b * nxy + (int64_t)(x0 + i) * ny + y) : -1;
+  } else {
+    const int32_t* m = rank_map + b * nxy + (int64_t)y * nx + x0;
+    if (x0 + 3 < nx && ((reinterpret_cast<uintptr_t>(m) & 15) == 0)) {
+      const int4 t = __ldg(reinterpret_cast<const int4*>(m));
+      r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (x0 + i < nx) ? __ldg(m + i) : -1;
+    }
+  }
+  float* dst = canvas + ((int64_t)b * channels) * nxy + (int64_t)y * nx + x0;
+  const bool vec = (x0 + 3 < nx) && ((nx & 3) == 0) && ((reinterpret_cast<uintptr_t>(canvas) & 15) == 0);
+  const bool any = (r[0] >= 0) | (r[1] >= 0) | (r[2] >= 0) | (r[3] >= 0);
+  if (vec && (channels & 3) == 0) {
+    if (!__any_sync(0xffffffffu, any)) {
+      // whole 512-byte row piece is empty for every channel: pure zero stream
+#pragma unroll 8
+      for (int c = 0; c < channels; ++c) st_stream_f4(dst + (int64_t)c * nxy, 0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+#pragma unroll 2
+    for (int c = 0; c < channels; c += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        v[i] = (r[i] >= 0) ? __ldg(reinterpret_cast<const float4*>(pf + (int64_t)r[i] * channels + c))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      st_stream_f4(dst + (int64_t)(c + 0) * nxy, v[0].x, v[1].x, v[2].x, v[3].x);
+      st_stream_f4(dst + (int64_t)(c + 1) * nxy, v[0].y, v[1].y, v[2].y, v[3].y);
+      st_stream_f4(dst + (int64_t)(c + 2) * nxy, v[0].z, v[1].z, v[2].z, v[3].z);
+      st_stream_f4(dst + (int64_t)(c + 3) * nxy, v[0].w, v[1].w, v[2].w, v[3].w);
+    }
+  } else {
+    for (int c = 0; c < channels; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x0 + i < nx) dst[(int64_t)c * nxy + i] = (r[i] >= 0) ? __ldg(pf + (int64_t)r[i] * channels + c) : 0.f;
+  }
+}
+
+// generic path: canvas-ordered rank map from arbitrary voxel_coords rows (frame, z, y, x)
+__global__ void __launch_bounds__(256)
+coords_to_map_kernel(const int32_t* __restrict__ coords, int64_t P, int frames, int nx, int ny,
+                     int32_t* __restrict__ map) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P) return;
+  const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + r);
+  // reference: indices = z + y * nx + x (pointpillar_scatter.py:27); nz == 1 so z is 0
+  const int64_t idx = (int64_t)c.y + (int64_t)c.z * nx + c.w;
+  if (c.x < 0 || c.x >= frames || idx < 0 || idx >= (int64_t)nx * ny) return;
+  // duplicate coordinates: the highest row wins, as the CPU reference's sequential index_put does
+  atomicMax(&map[(int64_t)c.x * nx * ny + idx], (int32_t)r);
+}
+
+__global__ void __launch_bounds__(256)
+num_frames_kernel(const int32_t* __restrict__ coords, int64_t P, int32_t* __restrict__ out) {
+  int m = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P; r += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, __ldg(coords + 4 * r) + 1);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+}  // namespace pcp
+
+using namespace pcp;
+
+static dim3 canvas_grid(int nx, int ny, int frames) {
+  return dim3((unsigned)((nx + kTileX - 1) / kTileX), (unsigned)((ny + kTileY - 1) / kTileY), (unsigned)frames);
+}
+
+extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels, int32_t num_frames,
+                                  int64_t n_points, int32_t max_frames, const pcp_grid* grid,
+                                  const void* workspace, size_t workspace_bytes, float* canvas_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(grid && workspace && canvas_out, PCP_E_INVALID, "pcp_bev_scatter_ws: null argument");
+  PCP_REQUIRE(channels > 0 && num_frames >= 0 && num_frames <= max_frames && num_frames <= 65535, PCP_E_INVALID,
+              "pcp_bev_scatter_ws: bad channels/num_frames");
+  const WsLayout L = ws_layout(n_points, max_frames, grid->nx, grid->ny);
+  PCP_REQUIRE(workspace_bytes >= L.total, PCP_E_WORKSPACE, "pcp_bev_scatter_ws: workspace too small");
+  if (num_frames == 0) return 0;
+  PCP_REQUIRE(pillar_features, PCP_E_INVALID, "pcp_bev_scatter_ws: null pillar_features");
+  const WsView W = ws_view(const_cast<void*>(workspace), L);
+  canvas_kernel<true><<<canvas_grid(grid->nx, grid->ny, num_frames), kTileY * 32, 0, stream>>>(
+      pillar_features, W.cell, channels, grid->nx, grid->ny, canvas_out);
+  PCP_LAUNCH_CHECK("canvas_kernel<ws>");
+  return 0;
+}
+
+extern "C" int pcp_bev_scatter(const float* pillar_features, const int32_t* voxel_coords, int64_t num_pillars,
+                               int32_t channels, int32_t num_frames, int32_t nx, int32_t ny,
+                               int32_t* cell_map_scratch, float* canvas_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(cell_map_scratch && canvas_out, PCP_E_INVALID, "pcp_bev_scatter: null argument");
+  PCP_REQUIRE(channels > 0 && nx > 0 && ny > 0 && num_frames >= 0 && num_frames <= 65535 && num_pillars >= 0,
+              PCP_E_INVALID, "pcp_bev_scatter: bad shape");
+  PCP_REQUIRE(num_pillars == 0 || (pillar_features && voxel_coords), PCP_E_INVALID, "pcp_bev_scatter: null input");
+  PCP_REQUIRE((reinterpret_cast<uintptr_t>(voxel_coords) & 15) == 0, PCP_E_INVALID, "pcp_bev_scatter: voxel_coords not 16-byte aligned");
+  if (num_frames == 0) return 0;
+  PCP_CUDA(cudaMemsetAsync(cell_map_scratch, 0xff, sizeof(int32_t) * (size_t)num_frames * nx * ny, stream));
+  if (num_pillars > 0) {
+    coords_to_map_kernel<<<(unsigned)((num_pillars + 255) / 256), 256, 0, stream>>>(voxel_coords, num_pillars, num_frames,
+                                                                                  nx, ny, cell_map_scratch);
+    PCP_LAUNCH_CHECK("coords_to_map_kernel");
+  }
+  canvas_kernel<false><<<canvas_grid(nx, ny, num_frames), kTileY * 32, 0, stream>>>(pillar_features, cell_map_scratch,
+                                                                                     channels, nx, ny, canvas_out);
+  PCP_LAUNCH_CHECK("canvas_kernel<map>");
+  return 0;
+}
+
+extern "C" int pcp_num_frames(const int32_t* voxel_coords, int64_t num_pillars, int32_t* num_frames_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(num_frames_out && num_pillars >= 0 && (num_pillars == 0 || voxel_coords), PCP_E_INVALID,
+              "pcp_num_frames: bad argument");
+  PCP_CUDA(cudaMemsetAsync(num_frames_out, 0, sizeof(int32_t), stream));
+  if (num_pillars > 0) {
+    num_frames_kernel<<<148, 256, 0, stream>>>(voxel_coords, num_pillars, num_frames_out);
+    PCP_LAUNCH_CHECK("num_frames_kernel");
+  }
+  return 0;
+}

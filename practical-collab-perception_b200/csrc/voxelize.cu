@@ -1,0 +1,364 @@
+// voxelize.cu - quantise + cull + linearise + compact (reference: dynamic_pillar_vfe.py:98-108,137-143).
+//
+// B200-first design: the linear key space B*nx*ny is dense and small (2 M cells for 8 frames of
+// 512 x 512), so instead of the reference's sort-based torch.unique the pillars are found with a
+// dense per-cell histogram that lives in L2:
+//   1. quantise_count : one thread per point, bit-exact fp32 quantisation, atomicAdd on the cell's
+//                       counter returns the point's arrival slot inside its cell;
+//   2. scan_cells     : ONE pass decoupled look-back scan over the cells produces, for every
+//                       non-empty cell, its pillar rank (ascending key order == torch.unique order),
+//                       the first sorted position of its points, voxel_coords and the counts;
+//   3. place          : counting-sort scatter of the row numbers + the point->pillar map (unq_inv);
+//   4. sort_segments  : row numbers inside each pillar are put in ascending order so that every
+//                       later per-pillar sum runs in the reference CPU path's order (deterministic).
+// No kernel synchronises with the host; the only data-dependent size (P) is read back by the caller.
+#include "common.cuh"
+
+namespace pcp {
+
+// ------------------------------------------------------------------------------------------------
+// 1. quantise + count
+// ------------------------------------------------------------------------------------------------
+template <bool kVec4>
+__global__ void __launch_bounds__(256)
+quantise_count_kernel(const float* __restrict__ points, int64_t stride, int64_t n, int32_t frames,
+                      pcp_grid g, int32_t* __restrict__ cell, int32_t* __restrict__ key,
+                      int32_t* __restrict__ within, int32_t* __restrict__ hdr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* row = points + i * stride;
+  float bf, x, y;
+  if (kVec4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+    bf = v.x; x = v.y; y = v.z;
+  } else {
+    bf = __ldg(row); x = __ldg(row + 1); y = __ldg(row + 2);
+  }
+  const float qx = quantise(x, g.range_min_x, g.voxel_x);
+  const float qy = quantise(y, g.range_min_y, g.voxel_y);
+  // reference: (coords >= 0) & (coords < grid) on the int-cast floor (dynamic_pillar_vfe.py:99);
+  // qx, qy are integral floats, the float compare is the same predicate and is false for NaN.
+  bool keep = (qx >= 0.f) && (qx < (float)g.nx) && (qy >= 0.f) && (qy < (float)g.ny);
+  int32_t k = -1, w = 0;
+  if (keep) {
+    // points[:, 0].int() truncates toward zero (:104)
+    if (!(bf > -1.f) || !(bf < (float)frames)) {
+      atomicAdd(&hdr[PCP_COUNT_BAD_FRAME], 1);
+    } else {
+      const int32_t b = (int32_t)bf;
+      k = b * (g.nx * g.ny) + (int32_t)qx * g.ny + (int32_t)qy;
+      w = atomicAdd(&cell[k], 1);
+    }
+  }
+  key[i] = k;
+  within[i] = w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. single-pass scan over the cells (decoupled look-back)
+//    packed 64-bit partial: [63:62] status, [61:32] sum of counts (points), [31:0] sum of flags (pillars)
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long kStatusAgg = 1ull << 62;
+constexpr unsigned long long kStatusPrefix = 2ull << 62;
+constexpr unsigned long long kPayloadMask = (1ull << 62) - 1;
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = kScanTileCells / kScanThreads;  // 8
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t ny,
+                  unsigned long long* __restrict__ state, int32_t* __restrict__ hdr,
+                  int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
+                  int32_t* __restrict__ pillar_count, int32_t* __restrict__ big_list, int64_t scan_tiles) {
+  __shared__ int s_tile;
+  __shared__ unsigned long long s_warp[kScanThreads / 32];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_red[2][kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&hdr[kHdrScanTicket], 1);
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t base = tile * kScanTileCells + (int64_t)tid * kScanItems;
+
+  int32_t c[kScanItems];
+  if (base + kScanItems <= cells) {
+    const int4 a = *reinterpret_cast<const int4*>(cell + base);
+    const int4 b = *reinterpret_cast<const int4*>(cell + base + 4);
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) c[j] = (base + j < cells) ? cell[base + j] : 0;
+  }
+  unsigned long long mine = 0;
+  int cmax = 0, last_nonempty = -1;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    mine += ((unsigned long long)(uint32_t)c[j] << 32) | (c[j] > 0 ? 1ull : 0ull);
+    cmax = max(cmax, c[j]);
+    if (c[j] > 0) last_nonempty = j;
+  }
+  // block exclusive scan of `mine`
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  // per-tile reductions for the header (max points per pillar, last frame that owns a pillar)
+  const int64_t nxy = (int64_t)nx * ny;
+  int fr = last_nonempty >= 0 ? (int)((base + last_nonempty) / nxy) + 1 : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
+    fr = max(fr, __shfl_xor_sync(0xffffffffu, fr, d));
+  }
+  if (lane == 0) { s_red[0][warp] = cmax; s_red[1][warp] = fr; }
+  __syncthreads();
+  unsigned long long warp_excl = 0, tile_total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    if (w < warp) warp_excl += s_warp[w];
+    tile_total += s_warp[w];
+  }
+  if (warp == 0) {
+    unsigned long long running = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&state[0], kStatusPrefix | tile_total);
+    } else {
+      if (lane == 0) atomicExch(&state[tile], kStatusAgg | tile_total);
+      int64_t j = tile - 1;
+      while (true) {
+        const int64_t idx = j - lane;
+        unsigned long long v = kStatusPrefix;  // virtual predecessor of tile 0: prefix 0
+        if (idx >= 0) {
+          v = ld_volatile_u64(&state[idx]);
+          while ((v >> 62) == 0) v = ld_volatile_u64(&state[idx]);
+        }
+        const unsigned pref = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first = pref ? (__ffs(pref) - 1) : 32;
+        unsigned long long contrib = (lane <= first) ? (v & kPayloadMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        running += contrib;
+        if (pref) break;
+        j -= 32;
+      }
+      if (lane == 0) atomicExch(&state[tile], kStatusPrefix | ((running + tile_total) & kPayloadMask));
+    }
+    if (lane == 0) {
+      s_prefix = running;
+      int m = 0, f = 0;
+#pragma unroll
+      for (int w = 0; w < kScanThreads / 32; ++w) { m = max(m, s_red[0][w]); f = max(f, s_red[1][w]); }
+      if (m > 0) {
+        atomicMax(&hdr[PCP_COUNT_MAX_PER_PILLAR], m);
+        atomicMax(&hdr[PCP_COUNT_FRAMES], f);
+      }
+      if (tile == scan_tiles - 1) {
+        const unsigned long long tot = running + tile_total;
+        const int32_t P = (int32_t)(tot & 0xffffffffull);
+        const int32_t Nk = (int32_t)((tot >> 32) & 0x3fffffffull);
+        hdr[PCP_COUNT_PILLARS] = P;
+        hdr[PCP_COUNT_KEPT] = Nk;
+        seg_off[P] = Nk;
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long excl = s_prefix + warp_excl + (incl - mine);
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    const int64_t idx = base + j;
+    if (idx < cells) {
+      if (c[j] > 0) {
+        const int32_t r = (int32_t)(excl & 0xffffffffull);
+        const int32_t off = (int32_t)((excl >> 32) & 0x3fffffffull);
+        seg_off[r] = off;
+        const int32_t b = (int32_t)(idx / nxy);
+        const int32_t rem = (int32_t)(idx - (int64_t)b * nxy);
+        const int32_t cx = rem / ny, cy = rem - cx * ny;
+        // (frame, z = 0, y, x): dynamic_pillar_vfe.py:138-143 after the [0, 3, 2, 1] reorder
+        *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4(b, 0, cy, cx);
+        if (pillar_count) pillar_count[r] = c[j];
+        cell[idx] = r;
+        if (c[j] > kSmallSeg) big_list[atomicAdd(&hdr[kHdrBigCount], 1)] = r;
+        excl += ((unsigned long long)(uint32_t)c[j] << 32) | 1ull;
+      } else {
+        cell[idx] = -1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. counting-sort scatter + point -> pillar map
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within,
+             const int32_t* __restrict__ cell, const int32_t* __restrict__ seg_off, int64_t n,
+             int32_t* __restrict__ sorted_idx, int32_t* __restrict__ point_pillar,
+             const int32_t* __restrict__ hdr, int32_t* __restrict__ counts_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && counts_out) {
+#pragma unroll
+    for (int j = 0; j < PCP_COUNTS_LEN; ++j) counts_out[j] = hdr[j];
+  }
+  if (i >= n) return;
+  const int32_t k = key[i];
+  int32_t r = -1;
+  if (k >= 0) {
+    r = __ldg(cell + k);
+    sorted_idx[__ldg(seg_off + r) + within[i]] = (int32_t)i;
+  }
+  if (point_pillar) point_pillar[i] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. ascending row order inside every pillar
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(int32_t& a, int32_t& b) {
+  const int32_t lo = min(a, b), hi = max(a, b);
+  a = lo; b = hi;
+}
+
+// one thread per pillar for n <= 8 (19-comparator network), one warp per pillar for 9..32
+__global__ void __launch_bounds__(256)
+sort_small_segments_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
+                           const int32_t* __restrict__ hdr) {
+  const int32_t P = hdr[PCP_COUNT_PILLARS];
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if ((r - lane) >= P) return;  // whole warp out of range
+  int32_t off = 0, n = 0;
+  if (r < P) { off = seg_off[r]; n = seg_off[r + 1] - off; }
+  if (n >= 2 && n <= 8) {
+    int32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
+    // optimal 8-input sorting network (19 compare-exchanges)
+    cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
+    cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
+    cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
+    cswap(v[1], v[5]); cswap(v[2], v[6]);
+    cswap(v[1], v[4]); cswap(v[3], v[6]);
+    cswap(v[2], v[4]); cswap(v[3], v[5]);
+    cswap(v[3], v[4]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < n) sorted_idx[off + j] = v[j];
+  }
+  unsigned mid = __ballot_sync(0xffffffffu, n > 8 && n <= kSmallSeg);
+  while (mid) {
+    const int l = __ffs(mid) - 1;
+    mid &= mid - 1;
+    const int32_t o = __shfl_sync(0xffffffffu, off, l);
+    const int32_t m = __shfl_sync(0xffffffffu, n, l);
+    const int32_t v = (lane < m) ? sorted_idx[o + lane] : 0x7fffffff;
+    int rank = 0;
+    for (int i = 0; i < m; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
+    __syncwarp();
+    if (lane < m) sorted_idx[o + rank] = v;
+  }
+}
+
+// one CTA per pillar with more than kSmallSeg points: bitonic sort in shared memory (<= kBigSegMax).
+// Larger pillars keep their arrival order (documented: sums over them stay within tolerance but are
+// not order-canonical).
+__global__ void __launch_bounds__(256)
+sort_big_segments_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
+                         const int32_t* __restrict__ big_list, const int32_t* __restrict__ hdr) {
+  __shared__ int32_t s[kBigSegMax];
+  const int nbig = hdr[kHdrBigCount];
+  for (int e = blockIdx.x; e < nbig; e += gridDim.x) {
+    const int32_t r = big_list[e];
+    const int32_t off = seg_off[r], n = seg_off[r + 1] - off;
+    if (n > kBigSegMax) continue;
+    int m = 64;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+          const int p = i ^ j;
+          if (p > i) {
+            const int32_t a = s[i], b = s[p];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { s[i] = b; s[p] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted_idx[off + i] = s[i];
+    __syncthreads();
+  }
+}
+
+}  // namespace pcp
+
+using namespace pcp;
+
+extern "C" size_t pcp_workspace_bytes(int64_t n_points, int32_t max_frames, int32_t nx, int32_t ny) {
+  if (n_points < 0 || max_frames <= 0 || nx <= 0 || ny <= 0) return 0;
+  return ws_layout(n_points, max_frames, nx, ny).total;
+}
+
+extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
+                            const pcp_grid* grid, void* workspace, size_t workspace_bytes,
+                            int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
+                            int64_t pillar_capacity, int32_t* counts_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(grid && workspace && voxel_coords_out && counts_out, PCP_E_INVALID, "pcp_voxelize: null argument");
+  PCP_REQUIRE(n_points >= 0 && n_points < (1ll << 30), PCP_E_INVALID, "pcp_voxelize: n_points out of range");
+  PCP_REQUIRE(n_points == 0 || points, PCP_E_INVALID, "pcp_voxelize: null points");
+  PCP_REQUIRE(row_stride >= 3, PCP_E_INVALID, "pcp_voxelize: row_stride < 3");
+  PCP_REQUIRE(max_frames > 0 && grid->nx > 0 && grid->ny > 0, PCP_E_INVALID, "pcp_voxelize: bad grid");
+  PCP_REQUIRE((int64_t)max_frames * grid->nx * grid->ny < (1ll << 31), PCP_E_UNSUPPORTED,
+              "pcp_voxelize: frames*nx*ny must fit int32 (the reference's merge_coords is int32 too)");
+  const WsLayout L = ws_layout(n_points, max_frames, grid->nx, grid->ny);
+  PCP_REQUIRE(workspace_bytes >= L.total, PCP_E_WORKSPACE, "pcp_voxelize: workspace %zu < %zu bytes",
+              workspace_bytes, L.total);
+  PCP_REQUIRE(pillar_capacity >= L.cap, PCP_E_INVALID, "pcp_voxelize: pillar_capacity %lld < min(N, cells) = %lld",
+              (long long)pillar_capacity, (long long)L.cap);
+  PCP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PCP_E_INVALID, "pcp_voxelize: workspace not 256-byte aligned");
+  PCP_REQUIRE((reinterpret_cast<uintptr_t>(voxel_coords_out) & 15) == 0, PCP_E_INVALID, "pcp_voxelize: voxel_coords_out not 16-byte aligned");
+  const WsView W = ws_view(workspace, L);
+
+  PCP_CUDA(cudaMemsetAsync(workspace, 0, L.clear_bytes, stream));
+  if (n_points > 0) {
+    const bool vec4 = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    const unsigned blocks = (unsigned)((n_points + 255) / 256);
+    if (vec4)
+      quantise_count_kernel<true><<<blocks, 256, 0, stream>>>(points, row_stride, n_points, max_frames, *grid,
+                                                              W.cell, W.key, W.within, W.hdr);
+    else
+      quantise_count_kernel<false><<<blocks, 256, 0, stream>>>(points, row_stride, n_points, max_frames, *grid,
+                                                               W.cell, W.key, W.within, W.hdr);
+    PCP_LAUNCH_CHECK("quantise_count_kernel");
+  }
+  scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
+      W.cell, L.cells, grid->nx, grid->ny, W.scan_state, W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
+      W.big_list, L.scan_tiles);
+  PCP_LAUNCH_CHECK("scan_cells_kernel");
+  {
+    const unsigned blocks = (unsigned)((n_points + 255) / 256);
+    place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.seg_off, n_points, W.sorted_idx,
+                                                          point_pillar_out, W.hdr, counts_out);
+    PCP_LAUNCH_CHECK("place_kernel");
+  }
+  if (n_points > 0) {
+    const unsigned blocks = (unsigned)((L.cap + 255) / 256);
+    sort_small_segments_kernel<<<blocks, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.hdr);
+    PCP_LAUNCH_CHECK("sort_small_segments_kernel");
+    sort_big_segments_kernel<<<296, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.big_list, W.hdr);
+    PCP_LAUNCH_CHECK("sort_big_segments_kernel");
+  }
+  return 0;
+}

@@ -1,0 +1,235 @@
+"""Host side of the point->BEV front end: owns device buffers and enqueues the C-ABI calls.
+
+PyTorch is used for device memory and streams only; every arithmetic step runs in libpcp_b200.so.
+``FrontEnd`` is the object both the drop-in modules (modules.py) and bench.py drive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PcpGrid, PcpPfnDesc
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: pcp_b200 has no CPU path")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class GridSpec:
+    """Constants DynamicPillarVFE.__init__ derives (dynamic_pillar_vfe.py:77-89), evaluated with the
+    caller's own scalar types exactly as the reference does, then rounded to fp32 for the kernels."""
+    voxel_size: Sequence[float]
+    point_cloud_range: Sequence[float]
+    grid_size: Sequence[int]
+
+    def __post_init__(self):
+        vs, rng = self.voxel_size, self.point_cloud_range
+        self.voxel_x, self.voxel_y, self.voxel_z = vs[0], vs[1], vs[2]
+        self.x_offset = self.voxel_x / 2 + rng[0]          # :80
+        self.y_offset = self.voxel_y / 2 + rng[1]          # :81
+        self.z_offset = self.voxel_z / 2 + rng[2]          # :82
+        self.nx, self.ny, self.nz = (int(g) for g in self.grid_size)
+        # torch.tensor(voxel_size).cuda() / torch.tensor(point_cloud_range).cuda() are fp32 tensors (:88-89)
+        f32 = lambda v: float(np.float32(v))
+        self.c = PcpGrid(f32(rng[0]), f32(rng[1]), f32(vs[0]), f32(vs[1]),
+                         f32(self.x_offset), f32(self.y_offset), f32(self.z_offset), self.nx, self.ny)
+
+
+class Workspace:
+    """Caller-owned scratch for one batch; remembers which problem filled it."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.n_points = 0
+        self.max_frames = 0
+        self.generation = 0
+
+    def ensure(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class FrontEnd:
+    """voxelize -> PFN -> BEV scatter on one GPU.  No host synchronisation inside any method except
+    ``read_counts`` (the single D2H read of P the data-dependent output shape needs)."""
+
+    def __init__(self, grid: GridSpec, c_raw: int, use_absolute_xyz: bool = True, with_distance: bool = False,
+                 num_filters: Sequence[int] = (64, 64)):
+        self.lib = _lib.load()
+        self.grid = grid
+        nf = list(num_filters)
+        if len(nf) not in (1, 2) or nf[-1] != 64 or (len(nf) == 2 and nf[0] != 64):
+            raise NotImplementedError(
+                f"NUM_FILTERS={nf}: the fused sm_100a PFN kernel implements [64] and [64, 64] "
+                "(every DynPillarVFE config the reference ships uses [64, 64])")
+        self.desc = PcpPfnDesc(int(c_raw), int(bool(use_absolute_xyz)), int(bool(with_distance)), len(nf),
+                               nf[0] // 2 if len(nf) == 2 else 0, nf[-1])
+        self.c_out = nf[-1]
+        self.c_in = int(c_raw) + (6 if use_absolute_xyz else 3) + (1 if with_distance else 0)
+        self.n_param_floats = int(self.lib.pcp_pfn_param_floats(C.byref(self.desc)))
+        if self.n_param_floats == 0:
+            raise RuntimeError("pcp_pfn_param_floats returned 0")
+        self.ws = Workspace()
+        self.packed: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ parameters
+    def pack_params(self, w0, bn0, w1=None, bn1=None, lin_bias0=None, lin_bias1=None, eps: float = 1e-3):
+        """bn = (weight, bias, running_mean, running_var) or None.  Runs pcp_pack_pfn_params on the GPU."""
+        dev = w0.device
+        _require_cuda(w0, "w0")
+        self.packed = torch.empty(self.n_param_floats, dtype=torch.float32, device=dev)
+        keep = []
+
+        def f(t):
+            if t is None:
+                return None
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return _ptr(t)
+
+        b0 = [f(t) for t in bn0] if bn0 is not None else [None] * 4
+        b1 = [f(t) for t in bn1] if bn1 is not None else [None] * 4
+        rc = self.lib.pcp_pack_pfn_params(C.byref(self.desc), f(w0), f(lin_bias0), *b0, f(w1), f(lin_bias1), *b1,
+                                          C.c_float(eps), _ptr(self.packed), _stream())
+        _lib.check(rc, "pcp_pack_pfn_params")
+        self._keep = keep  # keep sources alive until the stream has consumed them
+        return self.packed
+
+    # ------------------------------------------------------------------ stages
+    def capacity(self, n_points: int, max_frames: int) -> int:
+        return max(1, min(int(n_points), int(max_frames) * self.grid.nx * self.grid.ny))
+
+    def voxelize(self, points: torch.Tensor, max_frames: int, out: Optional[Dict[str, torch.Tensor]] = None,
+                 want_point_pillar: bool = True, want_counts_per_pillar: bool = False) -> Dict[str, torch.Tensor]:
+        _require_cuda(points, "points")
+        if points.dtype != torch.float32 or points.dim() != 2 or points.stride(1) != 1:
+            raise RuntimeError("points must be a 2-D fp32 tensor with unit column stride")
+        n, stride = points.shape[0], points.stride(0)
+        dev = points.device
+        cap = self.capacity(n, max_frames)
+        nbytes = int(self.lib.pcp_workspace_bytes(n, max_frames, self.grid.nx, self.grid.ny))
+        ws = self.ws.ensure(nbytes, dev)
+        out = {} if out is None else out
+
+        def buf(name, shape, dtype):
+            t = out.get(name)
+            if t is None or t.shape[0] < shape[0] or t.device != dev:
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                out[name] = t
+            return t
+
+        coords = buf("voxel_coords_buf", (cap, 4), torch.int32)
+        counts = buf("counts", (_lib.PCP_COUNTS_LEN,), torch.int32)
+        pp = buf("point_pillar", (max(n, 1),), torch.int32) if want_point_pillar else None
+        pc = buf("pillar_count_buf", (cap,), torch.int32) if want_counts_per_pillar else None
+        rc = self.lib.pcp_voxelize(_ptr(points), stride, n, int(max_frames), C.byref(self.grid.c), _ptr(ws), ws.numel(),
+                                   _ptr(pp), _ptr(coords), _ptr(pc), coords.shape[0], _ptr(counts), _stream())
+        _lib.check(rc, "pcp_voxelize")
+        self.ws.n_points, self.ws.max_frames = n, int(max_frames)
+        self.ws.generation += 1
+        out["capacity"] = cap
+        return out
+
+    def pfn(self, points: torch.Tensor, out: Dict[str, torch.Tensor], want_mean: bool = False) -> Dict[str, torch.Tensor]:
+        if self.packed is None:
+            raise RuntimeError("pack_params() must be called before pfn()")
+        n, stride = points.shape[0], points.stride(0)
+        cap = out["voxel_coords_buf"].shape[0]
+        pf = out.get("pillar_features_buf")
+        if pf is None or pf.shape[0] < cap:
+            pf = torch.empty((cap, self.c_out), dtype=torch.float32, device=points.device)
+            out["pillar_features_buf"] = pf
+        mean = None
+        if want_mean:
+            mean = out.get("pillar_mean_buf")
+            if mean is None or mean.shape[0] < cap:
+                mean = torch.empty((cap, 3), dtype=torch.float32, device=points.device)
+                out["pillar_mean_buf"] = mean
+        ws = self.ws.buf
+        rc = self.lib.pcp_pfn(_ptr(points), stride, n, self.ws.max_frames, C.byref(self.grid.c), C.byref(self.desc),
+                              _ptr(self.packed), _ptr(ws), ws.numel(), _ptr(pf), _ptr(mean), cap, _stream())
+        _lib.check(rc, "pcp_pfn")
+        return out
+
+    def scatter_ws(self, pillar_features: torch.Tensor, num_frames: int,
+                   canvas: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Dense canvas from the workspace the last voxelize() left (no search, no memset)."""
+        g = self.grid
+        c = pillar_features.shape[1]
+        if canvas is None:
+            canvas = torch.empty((num_frames, c, g.ny, g.nx), dtype=torch.float32, device=pillar_features.device)
+        ws = self.ws.buf
+        rc = self.lib.pcp_bev_scatter_ws(_ptr(pillar_features), c, int(num_frames), self.ws.n_points, self.ws.max_frames,
+                                         C.byref(g.c), _ptr(ws), ws.numel(), _ptr(canvas), _stream())
+        _lib.check(rc, "pcp_bev_scatter_ws")
+        return canvas
+
+    def segment_reduce(self, values: torch.Tensor, mode: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """scatter_mean / scatter_max of per-point ``values`` (indexed by original row) over the pillars of
+        the last voxelize().  Returns the (capacity, C) buffer; the first P rows are valid."""
+        _require_cuda(values, "values")
+        assert values.dim() == 2 and values.stride(1) == 1 and values.dtype == torch.float32
+        assert values.shape[0] == self.ws.n_points
+        cap = self.capacity(self.ws.n_points, self.ws.max_frames)
+        c = values.shape[1]
+        if out is None:
+            out = torch.empty((cap, c), dtype=torch.float32, device=values.device)
+        ws = self.ws.buf
+        rc = self.lib.pcp_segment_reduce(_ptr(values), values.stride(0), c, {"mean": 0, "max": 1}[mode],
+                                         self.ws.n_points, self.ws.max_frames, self.grid.nx, self.grid.ny,
+                                         _ptr(ws), ws.numel(), _ptr(out), cap, _stream())
+        _lib.check(rc, "pcp_segment_reduce")
+        return out
+
+    # ------------------------------------------------------------------ whole chain
+    def forward_device(self, points: torch.Tensor, max_frames: int, out: Optional[Dict[str, torch.Tensor]] = None,
+                       canvas: Optional[torch.Tensor] = None, want_point_pillar: bool = False):
+        """voxelize -> PFN -> canvas for ``max_frames`` frames, all enqueued, nothing read back.
+        The canvas covers all ``max_frames`` frames (the reference sizes it from the last non-empty frame,
+        pointpillar_scatter.py:17; the modules do that after reading the counts)."""
+        out = self.voxelize(points, max_frames, out, want_point_pillar=want_point_pillar)
+        self.pfn(points, out)
+        out["spatial_features"] = self.scatter_ws(out["pillar_features_buf"], max_frames, canvas)
+        return out
+
+    @staticmethod
+    def read_counts(out: Dict[str, torch.Tensor]) -> np.ndarray:
+        """The one D2H read of the path: 32 bytes (P, N', frames, bad-frame count, max points per pillar)."""
+        return out["counts"].cpu().numpy()
+
+
+def generic_scatter(pillar_features: torch.Tensor, voxel_coords: torch.Tensor, nx: int, ny: int,
+                    num_frames: Optional[int] = None) -> torch.Tensor:
+    """PointPillarScatter for arbitrary (pillar_features, voxel_coords) (pointpillar_scatter.py:14-37)."""
+    lib = _lib.load()
+    _require_cuda(pillar_features, "pillar_features")
+    _require_cuda(voxel_coords, "voxel_coords")
+    pf = pillar_features.float().contiguous()
+    vc = voxel_coords.to(torch.int32).contiguous()
+    p = vc.shape[0]
+    if num_frames is None:
+        nf = torch.zeros(1, dtype=torch.int32, device=vc.device)
+        _lib.check(lib.pcp_num_frames(_ptr(vc), p, _ptr(nf), _stream()), "pcp_num_frames")
+        num_frames = int(nf.item())             # the reference syncs here too (pointpillar_scatter.py:17)
+    c = pf.shape[1]
+    cell_map = torch.empty((max(num_frames, 1) * ny * nx,), dtype=torch.int32, device=vc.device)
+    canvas = torch.empty((num_frames, c, ny, nx), dtype=torch.float32, device=vc.device)
+    rc = lib.pcp_bev_scatter(_ptr(pf), _ptr(vc), p, c, num_frames, nx, ny, _ptr(cell_map), _ptr(canvas), _stream())
+    _lib.check(rc, "pcp_bev_scatter")
+    return canvas
