@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py - frames/s of the point->BEV front end (voxelize + PFN + BEV scatter) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic frames that is already resident in HBM:
+the V2X-Sim EARLY-FUSION shape (BASELINE.json configs[2]: ~300 k points per frame, 0.2 m pillars,
+512 x 512 canvas, C_raw 5 -> PFN 11->32, 64->64), 8 frames per GPU (configs[3]: 64 frames over 8 GPUs).
+Frames are independent, so GPUs are weak-scaled with no collective on the hot path.
+Rank 0 prints ONE JSON line (contract in the task statement): value = whole-job frames/s from CUDA events
+(max over ranks), `e2e` = the same through the drop-in modules with pinned HOST input (H2D inside the
+timed region), `roofline` for the dominant kernel, `cpu_baseline` = the oracle port of the reference timed
+on this box's host cores.  `--impl reference` times that CPU port alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 8
+POINTS_PER_FRAME = 300_000
+C_RAW = 5
+CONFIG_ID = 3
+METRIC = "frames/s (voxelize+PFN+BEV scatter)"
+UNIT = "frames/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml)."""
+
+    def __init__(self, index: int, period_s: float = 0.05):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self.index, self.period = index, period_s
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = get(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's DynamicPillarVFE + PointPillarScatter
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_frames_per_s(steps: int, warmup: int, frame_seed: int = 0):
+    """Times the CPU restatement of the reference path (oracle/, same ATen ops incl. torch.unique(dim=0))
+    on ONE early-fusion frame per step, all host threads."""
+    from oracle import pillar_oracle as po
+    from pcp_b200 import synthetic as syn
+    from tests.helpers import layers_from_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    grid = syn.grid_size_of(rng, syn.V2X_VOXEL)
+    cfg = po.VFEConfig(C_RAW, syn.V2X_VOXEL, rng, grid)
+    layers = layers_from_state_dict(syn.pfn_state_dict(C_RAW + 6))
+    pts = syn.batch_of_frames(1, POINTS_PER_FRAME, CONFIG_ID, first_frame=frame_seed)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            po.front_end(pts, cfg, layers, unique_dim0=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    mean = sum(times) / len(times)
+    return 1.0 / mean, mean, cores, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fps, sec, cores, threads = cpu_reference_frames_per_s(max(args.steps, 1), max(min(args.warmup, 2), 1))
+    sample = f"1 frame of {POINTS_PER_FRAME} points per step (1/{FRAMES_PER_GPU} of one GPU's batch)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"v2x early fusion (BASELINE configs[2]): {POINTS_PER_FRAME} pts/frame x {FRAMES_PER_GPU} frames/GPU, "
+                        f"0.2 m pillars, 512x512 canvas, C_raw {C_RAW}, PFN 11->32,64->64",
+            "frames_per_gpu": FRAMES_PER_GPU, "points_per_frame": POINTS_PER_FRAME, "global_frames": FRAMES_PER_GPU * n_gpus,
+            "parallelism": f"frames sharded over {n_gpus} GPU(s), no hot-path collective",
+            "l2": "per-step working set ~0.95 GB >> 126 MB L2 (537 MB canvas streamed every step); 2 input batches alternate"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import pcp_b200
+    from pcp_b200 import _lib, synthetic as syn
+    from pcp_b200.frontend import FrontEnd, GridSpec
+    from tests.helpers import model_cfgs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    vox = syn.V2X_VOXEL
+    grid = syn.grid_size_of(rng, vox)
+    gs = GridSpec(vox, rng, grid)
+    sd = syn.pfn_state_dict(C_RAW + 6)
+
+    # two alternating batches of this rank's frames (global frame numbers: weak scaling)
+    B = FRAMES_PER_GPU
+    host_batches = [syn.batch_of_frames(B, POINTS_PER_FRAME, CONFIG_ID, first_frame=rank * B + alt * 1000).pin_memory()
+                    for alt in range(2)]
+    dev_batches = [h.to(dev) for h in host_batches]
+    n_points = dev_batches[0].shape[0]
+
+    fe = FrontEnd(gs, C_RAW)
+    bn = lambda i: [sd[f"pfn_layers.{i}.norm.{k}"].to(dev) for k in ("weight", "bias", "running_mean", "running_var")]
+    fe.pack_params(sd["pfn_layers.0.linear.weight"].to(dev), bn(0), sd["pfn_layers.1.linear.weight"].to(dev), bn(1))
+    out, canvas = {}, torch.empty((B, 64, gs.ny, gs.nx), dtype=torch.float32, device=dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    stage_ev = [[ev() for _ in range(4)] for _ in range(args.steps)]
+
+    def step(i, record=None):
+        pts = dev_batches[i & 1]
+        if record:
+            record[0].record()
+        fe.voxelize(pts, B, out, want_point_pillar=False)
+        if record:
+            record[1].record()
+        fe.pfn(pts, out)
+        if record:
+            record[2].record()
+        fe.scatter_ws(out["pillar_features_buf"], B, canvas)
+        if record:
+            record[3].record()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    with ClockSampler(physical_gpu_index(local_rank)) as clk:
+        t_start, t_end = ev(), ev()
+        t_start.record()
+        for i in range(args.steps):
+            step(i, stage_ev[i])
+        t_end.record()
+        torch.cuda.synchronize()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    barrier()
+    counts = fe.read_counts(out)
+    n_pillars, n_kept = int(counts[0]), int(counts[1])
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_max = float(t.item())
+    else:
+        elapsed_max = elapsed_ms
+    ms_per_step = elapsed_max / args.steps
+    value = world * B * args.steps / (elapsed_max * 1e-3)
+
+    # per-stage device time inside the timed region (same stream, CUDA events)
+    stage_ms = [statistics.mean(stage_ev[i][j].elapsed_time(stage_ev[i][j + 1]) for i in range(args.steps)) for j in range(3)]
+    stage_names = ["voxelize(6 launches)", "pfn_kernel", "canvas_kernel"]
+    row_bytes = 4 * dev_batches[0].shape[1]
+    alg = {
+        "voxelize(6 launches)": n_points * row_bytes + n_pillars * 16,
+        "pfn_kernel": n_kept * row_bytes + n_pillars * 64 * 4,
+        "canvas_kernel": B * 64 * gs.ny * gs.nx * 4 + n_pillars * 64 * 4,
+    }
+    chain_bytes = n_points * row_bytes + n_pillars * 64 * 4 + n_pillars * 16 + B * 64 * gs.ny * gs.nx * 4
+    peak, peak_src = measured_peak_gbs()
+    dom = max(range(3), key=lambda j: stage_ms[j])
+    dom_name = stage_names[dom]
+    achieved = alg[dom_name] / (stage_ms[dom] * 1e-3) / 1e9
+    chain_achieved = chain_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- e2e: drop-in modules, pinned host input, H2D + counts D2H inside the timed region ----------------
+    vfe_cfg, scat_cfg = model_cfgs(C_RAW)
+    vfe = pcp_b200.DynamicPillarVFE(model_cfg=vfe_cfg, num_point_features=C_RAW, voxel_size=vox, grid_size=grid,
+                                    point_cloud_range=rng)
+    vfe.load_state_dict(sd)
+    vfe = vfe.to(dev).eval()
+    scat = pcp_b200.PointPillarScatter(model_cfg=scat_cfg, grid_size=grid).to(dev).eval()
+    del canvas, out
+    torch.cuda.empty_cache()
+
+    def e2e_step(i):
+        pts = host_batches[i & 1].to(dev, non_blocking=True)             # H2D from pinned memory
+        with torch.no_grad():
+            bd = scat(vfe({"points": pts, "batch_size": B}))             # vfe reads the 32-byte counts block back
+        return bd["spatial_features"].shape[0], bd["voxel_coords"].shape[0]
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    s0, s1 = ev(), ev()
+    s0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    s1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(s0.elapsed_time(s1), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 or True:
+            fps, sec, cores, threads = cpu_reference_frames_per_s(steps=3, warmup=1)
+            cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"1 frame of {POINTS_PER_FRAME} points x 3 runs (oracle port, torch.unique(dim=0) as the reference calls it)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "mpts_per_s": value * POINTS_PER_FRAME / 1e6,
+            "pillars_per_step": n_pillars, "kept_points_per_step": n_kept,
+            "stage_ms": dict(zip(stage_names, stage_ms)),
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": alg[dom_name]},
+            "roofline_chain": {"bound": "hbm", "achieved": chain_achieved, "peak": peak, "unit": "GB/s",
+                               "frac": chain_achieved / peak, "algorithmic_bytes": chain_bytes,
+                               "note": "SURVEY 8d bytes of the whole voxelize+PFN+scatter chain / step time"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_batches[0].numel() * 4),
+                    "d2h_bytes_per_step": 4 * _lib.PCP_COUNTS_LEN, "steps": e2e_steps,
+                    "api": "DynamicPillarVFE.forward + PointPillarScatter.forward on pinned host points"},
+            "gpu_launches": 7 * args.steps,   # quantise, scan, place, 2 x segment sort, pfn, canvas (+1 memset) per step
+            "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,138 @@
+"""GPU parity of the MoDAR exchange kernel: against the CPU oracle, against the reference's own
+apply_se3_ outputs (tests/golden/modar_small.npz) and - for box membership - against the REFERENCE'S OWN
+CUDA KERNEL compiled from its source for sm_100a (oracle/_ref/libroiaware_ref.so, built by oracle/Makefile)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import modar_oracle as mo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libroiaware_ref.so")
+
+
+def run_exchange(ego, agents, t_detect=0.0, t_query=0.2, **kw):
+    import pcp_b200
+    out = pcp_b200.modar_exchange([a["modar"] for a in agents], [a.get("foreground") for a in agents],
+                                  [a["target_se3_agent"] for a in agents], t_detect, t_query, ego.to(DEV), **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+def oracle_exchange(ego13, agents, max_sweep, scale):
+    ags = [{"modar": a["modar"].numpy(), "foreground": None if a.get("foreground") is None else a["foreground"].numpy(),
+            "target_se3_agent": a["target_se3_agent"]} for a in agents]
+    return mo.modar_exchange(ego13.numpy(), ags, max_sweep, scale)
+
+
+def compare_rows(got, want, n_ego):
+    got, want = got.cpu().numpy(), np.asarray(want)
+    assert got.shape == want.shape
+    assert np.array_equal(got[:n_ego], want[:n_ego]), "ego rows must be copied verbatim"
+    g, w = got[n_ego:], want[n_ego:]
+    # exact columns: zeros, dims, score, label, sweep idx, instance idx
+    for c in (3, 4, 5, 6, 7, 9, 10, 11, 12):
+        assert np.array_equal(g[:, c], w[:, c]), f"column {c}"
+    # xyz: fp32 sums + fp64 SE(3); heading: fp32 sin/cos/atan2 (libdevice vs numpy SIMD kernels, few ulp)
+    np.testing.assert_allclose(g[:, :3], w[:, :3], rtol=1e-5, atol=1e-5)
+    d = np.abs(g[:, 8] - w[:, 8])
+    d = np.minimum(d, 2 * np.pi - d)
+    assert d.max() < 2e-6, f"heading differs by {d.max()}"
+
+
+@pytest.mark.parametrize("n_agents", [1, 5])
+def test_config2_scene_against_oracle(n_agents):
+    from pcp_b200 import synthetic as syn
+    ego14, agents = syn.modar_scene(2, 0, n_agents=n_agents, n_ego_points=4096)
+    ego13 = ego14[:, 1:].contiguous()
+    max_sweep = float(ego13[:, -2].max())
+    got, box_idx = run_exchange(ego13, agents, return_box_idx=True)
+    want = oracle_exchange(ego13, agents, max_sweep, 2.0)
+    compare_rows(got, want, ego13.shape[0])
+    want_idx = np.concatenate([mo.points_in_boxes(a["foreground"][:, :3].numpy(), a["modar"][:, :7].numpy()) for a in agents])
+    assert np.array_equal(box_idx.cpu().numpy(), want_idx)
+    # 14-column layout (collate_batch frame column in front)
+    got14 = run_exchange(ego14, agents, batch_idx=0.0)
+    assert torch.equal(got14[:, 1:], got) and float(got14[:, 0].abs().max()) == 0.0
+
+
+def test_exchange_now_and_missing_foreground_skip_propagation():
+    from pcp_b200 import synthetic as syn
+    ego14, agents = syn.modar_scene(2, 1, n_agents=3, n_ego_points=512)
+    ego13 = ego14[:, 1:].contiguous()
+    max_sweep = float(ego13[:, -2].max())
+    now = run_exchange(ego13, agents, t_detect=3.0, t_query=3.0)
+    compare_rows(now, oracle_exchange(ego13, agents, max_sweep, 0.0), ego13.shape[0])
+    nofg = [dict(a, foreground=None) for a in agents]
+    got = run_exchange(ego13, nofg)
+    compare_rows(got, oracle_exchange(ego13, nofg, max_sweep, 2.0), ego13.shape[0])
+    assert torch.equal(got, now)
+
+
+def test_detections_dict_and_latency_scaling():
+    from pcp_b200 import synthetic as syn
+    import pcp_b200
+    ego14, agents = syn.modar_scene(2, 2, n_agents=2, n_ego_points=256)
+    ego13 = ego14[:, 1:].contiguous()
+    dets = [{"pred_boxes": a["modar"][:, :7], "pred_scores": a["modar"][:, 7], "pred_labels": a["modar"][:, 8].long()} for a in agents]
+    a = pcp_b200.modar_exchange(dets, [x["foreground"] for x in agents], [x["target_se3_agent"] for x in agents],
+                                10.0, 10.2, ego13.to(DEV))
+    b = run_exchange(ego13, agents)
+    assert torch.equal(a, b)
+    # 0.4 s of latency = two sample intervals -> scale 4
+    c = run_exchange(ego13, agents, t_detect=1.0, t_query=1.4)
+    compare_rows(c, oracle_exchange(ego13, agents, float(ego13[:, -2].max()), 4.0), ego13.shape[0])
+
+
+def test_golden_apply_se3_from_the_reference():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "modar_small.npz"))
+    for a in range(4):
+        modar = torch.from_numpy(z[f"a{a}/modar"])
+        ego = torch.zeros(1, 13)
+        got = run_exchange(ego, [{"modar": modar, "foreground": None, "target_se3_agent": z[f"a{a}/se3"]}],
+                           max_sweep_idx=10.0).cpu().numpy()[1:]
+        ref = z[f"a{a}/ref_apply_se3_boxes"]                      # the reference's own apply_se3_
+        np.testing.assert_allclose(got[:, :3], ref[:, :3], rtol=1e-6, atol=1e-6)
+        d = np.abs(got[:, 8] - ref[:, 6]); d = np.minimum(d, 2 * np.pi - d)
+        assert d.max() < 2e-6
+        assert np.array_equal(got[:, 5:8], ref[:, 3:6])
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_SO), reason="oracle/_ref/libroiaware_ref.so not built (make -C oracle)")
+def test_box_membership_bit_exact_against_reference_cuda_kernel():
+    """points_in_boxes_kernel of the reference (roiaware_pool3d_kernel.cu:313-359), compiled unmodified, run on
+    the same GPU: identical box index for every point, including knife-edge points on box faces."""
+    from pcp_b200 import synthetic as syn
+    ref = ctypes.CDLL(REF_SO)
+    launcher = getattr(ref, "_Z24points_in_boxes_launcheriiiPKfS0_Pi")
+    launcher.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+    launcher.restype = None
+    g = torch.Generator().manual_seed(0)
+    for seed in range(3):
+        ag = syn.modar_agent(900 + seed, n_boxes=83, fg_per_box=(50, 120), stray_fraction=0.3)
+        boxes, fg = ag["modar"].clone(), ag["foreground"].clone()
+        # add points exactly on / next to faces and corners of random boxes
+        k = torch.randint(0, boxes.shape[0], (4000,), generator=g)
+        sgn = torch.randint(0, 2, (4000, 3), generator=g).float() * 2 - 1
+        eps = (torch.randint(-2, 3, (4000, 3), generator=g).float()) * 1e-5
+        local = sgn * boxes[k, 3:6] / 2 + eps
+        c, s = torch.cos(boxes[k, 6]), torch.sin(boxes[k, 6])
+        edge = torch.zeros(4000, 13)
+        edge[:, 0] = local[:, 0] * c - local[:, 1] * s + boxes[k, 0]
+        edge[:, 1] = local[:, 0] * s + local[:, 1] * c + boxes[k, 1]
+        edge[:, 2] = local[:, 2] + boxes[k, 2]
+        fg = torch.cat([fg, edge], 0).contiguous()
+        b_dev, f_dev = boxes[:, :7].contiguous().to(DEV), fg[:, :3].contiguous().to(DEV)
+        want = torch.full((fg.shape[0],), -1, dtype=torch.int32, device=DEV)
+        torch.cuda.synchronize()
+        launcher(1, boxes.shape[0], fg.shape[0], b_dev.data_ptr(), f_dev.data_ptr(), want.data_ptr())
+        torch.cuda.synchronize()
+        _, got = run_exchange(torch.zeros(1, 13), [{"modar": boxes, "foreground": fg, "target_se3_agent": np.eye(4)}],
+                              return_box_idx=True, max_sweep_idx=0.0)
+        assert torch.equal(got, want), f"{int((got != want).sum())} of {fg.shape[0]} box indices differ"
+        assert int((want >= 0).sum()) > 1000

@@ -1,0 +1,291 @@
+"""GPU parity: the sm_100a kernels, called through the drop-in modules / C ABI, against the committed
+reference outputs (tests/golden) and against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): voxel_coords, point->pillar map and BEV occupancy bit-exact; per-pillar
+mean bit-exact (sums run in the reference CPU order); canvas = exact copy of pillar_features; PFN outputs
+within 1e-5 relative (fp32; absolute floor 1e-5 x tensor scale for values near zero).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pillar_oracle as po
+from tests.helpers import (assert_features_close, golden_cases, golden_cfg, layers_from_state_dict, load_golden,
+                           model_cfgs)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build_modules(c_raw, vox, rng, grid, sd, **opts):
+    import pcp_b200
+    vfe_cfg, scat_cfg = model_cfgs(c_raw, **opts)
+    vfe = pcp_b200.DynamicPillarVFE(model_cfg=vfe_cfg, num_point_features=c_raw, voxel_size=vox, grid_size=grid,
+                                    point_cloud_range=rng)
+    missing = vfe.load_state_dict(sd)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    scat = pcp_b200.PointPillarScatter(model_cfg=scat_cfg, grid_size=grid)
+    return vfe.to(DEV).eval(), scat.to(DEV).eval()
+
+
+def run_modules(vfe, scat, points, batch_size=None):
+    bd = {"points": points.to(DEV)}
+    if batch_size is not None:
+        bd["batch_size"] = batch_size
+    with torch.no_grad():
+        bd = scat(vfe(bd))
+    torch.cuda.synchronize()
+    return bd
+
+
+def check_against(bd, want, n_points):
+    """want: oracle-style dict of CPU tensors."""
+    from pcp_b200.modules import CTX_KEY
+    vc = bd["voxel_coords"].cpu()
+    assert vc.dtype == torch.int32
+    assert torch.equal(vc, want["voxel_coords"]), "voxel_coords differ"
+    pp = bd[CTX_KEY]["point_pillar"].cpu().long()
+    assert pp.shape[0] == n_points
+    assert torch.equal(pp[pp >= 0], want["unq_inv"].long()), "point->pillar map differs"
+    if "keep_mask" in want:
+        assert torch.equal(pp >= 0, want["keep_mask"]), "cull mask differs"
+    assert bd["voxel_features"] is bd["pillar_features"]
+    pf = bd["pillar_features"].cpu()
+    assert_features_close(pf.numpy(), want["pillar_features"].numpy(), "pillar_features")
+    sf = bd["spatial_features"].cpu()
+    assert tuple(sf.shape) == tuple(want["canvas_shape"])
+    occ = torch.nonzero((sf != 0).any(dim=1).flatten()).flatten()
+    assert torch.equal(occ.int(), want["occupied"].int()), "BEV occupancy differs"
+    # the canvas is a pure copy: must equal the reference scatter of OUR pillar features bit for bit
+    grid = (sf.shape[3], sf.shape[2], 1)
+    assert torch.equal(sf, po.pointpillar_scatter(pf, vc, grid, pf.shape[1])), "canvas is not an exact copy"
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_reference_outputs(name):
+    g = load_golden(name)
+    cfg, rng, vox, grid = golden_cfg(g)
+    vfe, scat = build_modules(int(g["c_raw"]), vox, rng, grid, g["sd"], num_filters=tuple(int(v) for v in g["num_filters"]),
+                              use_norm=bool(g["use_norm"]), with_distance=bool(g["with_distance"]), use_abs=bool(g["use_abs"]))
+    pts = torch.from_numpy(g["points"])
+    nb = int(np.nanmax(np.where(np.isfinite(g["points"][:, 0]), g["points"][:, 0], 0))) + 1
+    bd = run_modules(vfe, scat, pts, batch_size=nb)
+    want = {"voxel_coords": torch.from_numpy(g["voxel_coords"]), "unq_inv": torch.from_numpy(g["unq_inv"]),
+            "pillar_features": torch.from_numpy(g["pillar_features"]), "canvas_shape": g["canvas_shape"],
+            "occupied": torch.from_numpy(g["occupied"])}
+    check_against(bd, want, pts.shape[0])
+    if "spatial_features" in g:
+        assert_features_close(bd["spatial_features"].cpu().numpy(), g["spatial_features"], "spatial_features")
+
+
+def oracle_want(points, cfg, layers):
+    out = po.front_end(points, cfg, layers, unique_dim0=False)
+    sf = out["spatial_features"]
+    out["canvas_shape"] = tuple(sf.shape)
+    out["occupied"] = torch.nonzero((sf != 0).any(dim=1).flatten()).flatten()
+    return out
+
+
+def v2x_setup(c_raw, voxel=None, seed=0):
+    from pcp_b200 import synthetic as syn
+    voxel = voxel or syn.V2X_VOXEL
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    grid = syn.grid_size_of(rng, voxel)
+    sd = syn.pfn_state_dict(c_raw + 6, (64, 64), True, seed)
+    cfg = po.VFEConfig(c_raw, voxel, rng, grid)
+    return syn, rng, voxel, grid, sd, cfg
+
+
+@pytest.mark.parametrize("n_frames,n_points,config_id,ego", [
+    (1, 32768, 1, False),     # BASELINE config 1: one 32k-point ego frame, car layout
+    (1, 32768, 2, True),      # config 2 layout: 14 columns, C_raw 11
+    (1, 300000, 3, False),    # config 3: early fusion ~300k points
+    (4, 20000, 4, False),     # a sharded batch's local block
+])
+def test_seeded_configs_against_oracle(n_frames, n_points, config_id, ego):
+    c_raw = 11 if ego else 5
+    syn, rng, vox, grid, sd, cfg = v2x_setup(c_raw, seed=config_id)
+    pts = syn.batch_of_frames(n_frames, n_points, config_id, ego_columns=ego)
+    if ego:   # populate the MoDAR columns of some rows
+        g = torch.Generator().manual_seed(3)
+        sel = torch.randperm(pts.shape[0], generator=g)[:400]
+        pts[sel, 6:12] = torch.rand(400, 6, generator=g) * 4
+    vfe, scat = build_modules(c_raw, vox, rng, grid, sd)
+    bd = run_modules(vfe, scat, pts, batch_size=n_frames)
+    want = oracle_want(pts, cfg, layers_from_state_dict(sd))
+    check_against(bd, want, pts.shape[0])
+
+
+def test_batch_size_inferred_when_absent():
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    pts = syn.batch_of_frames(3, 5000, 9)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    bd = run_modules(vfe, scat, pts, batch_size=None)
+    check_against(bd, oracle_want(pts, cfg, layers_from_state_dict(sd)), pts.shape[0])
+
+
+def test_pillar_mean_and_segment_reductions_bit_exact():
+    """scatter_mean (sum in ascending row order / count) and scatter_max are exact, not approximate."""
+    from pcp_b200.frontend import FrontEnd, GridSpec
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    pts = syn.batch_of_frames(2, 60000, 11)
+    fe = FrontEnd(GridSpec(vox, rng, grid), 5)
+    l = layers_from_state_dict(sd)
+    fe.pack_params(sd["pfn_layers.0.linear.weight"].to(DEV), [sd[f"pfn_layers.0.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")],
+                   sd["pfn_layers.1.linear.weight"].to(DEV), [sd[f"pfn_layers.1.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")])
+    p_dev = pts.to(DEV)
+    out = fe.voxelize(p_dev, 2, want_point_pillar=True, want_counts_per_pillar=True)
+    fe.pfn(p_dev, out, want_mean=True)
+    counts = fe.read_counts(out)
+    P = int(counts[0])
+    want = po.dynamic_pillar_vfe(pts, cfg, l, unique_dim0=False)
+    assert P == want["voxel_coords"].shape[0] and int(counts[1]) == want["unq_inv"].shape[0]
+    assert torch.equal(out["pillar_count_buf"][:P].cpu().long(), want["unq_cnt"])
+    assert int(counts[4]) == int(want["unq_cnt"].max())
+    assert torch.equal(out["pillar_mean_buf"][:P].cpu(), want["points_mean"]), "pillar mean is not bit exact"
+    # standalone segmented reductions over arbitrary per-point values (indexed by original row)
+    g = torch.Generator().manual_seed(1)
+    vals = torch.randn(pts.shape[0], 64, generator=g)
+    kept = want["keep_mask"]
+    got_max = fe.segment_reduce(vals.to(DEV), "max")[:P].cpu()
+    got_mean = fe.segment_reduce(vals.to(DEV), "mean")[:P].cpu()
+    idx = want["unq_inv"].view(-1, 1).expand(-1, 64)
+    ref_max = torch.full((P, 64), float("-inf")).scatter_reduce_(0, idx, vals[kept], reduce="amax", include_self=True)
+    assert torch.equal(got_max, ref_max), "segment max is not bit exact"
+    assert torch.equal(got_mean, po.scatter_mean(vals[kept], want["unq_inv"], P)), "segment mean is not bit exact"
+
+
+@pytest.mark.parametrize("n_in_pillar", [2, 8, 9, 31, 32, 33, 127, 128, 129, 500, 4096, 5000, 20000])
+def test_long_pillars(n_in_pillar):
+    """Pillars longer than a 128-point chunk stream through the multi-chunk path; sorted-segment code
+    paths switch at 8 / 32 / 4096 points."""
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5, seed=2)
+    g = torch.Generator().manual_seed(n_in_pillar)
+    base = syn.lidar_frame(3000, 77)
+    dense = syn.lidar_frame(n_in_pillar, 78)
+    dense[:, 1] = 10.0 + torch.rand(n_in_pillar, generator=g) * 0.19
+    dense[:, 2] = -7.0 + torch.rand(n_in_pillar, generator=g) * 0.19
+    dense2 = dense.clone()
+    dense2[:, 1] += 0.2                               # a second long pillar right behind the first
+    pts = torch.cat([base, dense, dense2], 0)
+    pts = pts[torch.randperm(pts.shape[0], generator=g)].contiguous()
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    bd = run_modules(vfe, scat, pts, batch_size=1)
+    want = oracle_want(pts, cfg, layers_from_state_dict(sd))
+    check_against(bd, want, pts.shape[0])
+
+
+def test_all_points_in_one_pillar_and_all_culled_frame():
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    pts = syn.lidar_frame(3000, 5)
+    pts[:, 1], pts[:, 2] = 0.05, 0.05
+    far = syn.lidar_frame(100, 6, batch_idx=1)
+    far[:, 1] = 500.0                                 # frame 1 entirely outside the range
+    pts = torch.cat([pts, far], 0)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    bd = run_modules(vfe, scat, pts, batch_size=2)
+    assert bd["voxel_coords"].shape[0] == 1 and bd["spatial_features"].shape[0] == 1   # B shrinks (scatter :17)
+    check_against(bd, oracle_want(pts, cfg, layers_from_state_dict(sd)), pts.shape[0])
+
+
+def test_generic_scatter_path_matches_reference_semantics():
+    """PointPillarScatter on coords it did not produce: shuffled rows, a duplicate cell (last row wins as in the
+    CPU reference's sequential index_put), channels != 64."""
+    import pcp_b200
+    from tests.helpers import model_cfgs
+    g = torch.Generator().manual_seed(0)
+    nx, ny, B, C, P = 96, 40, 3, 32, 700
+    cells = torch.randperm(B * nx * ny, generator=g)[:P]
+    coords = torch.stack([cells // (nx * ny), torch.zeros(P, dtype=torch.long), (cells % (nx * ny)) // nx, cells % nx], 1).int()
+    coords = torch.cat([coords, coords[:5]], 0)       # 5 duplicate cells at higher row numbers
+    feats = torch.randn(coords.shape[0], C, generator=g)
+    scat = pcp_b200.PointPillarScatter(model_cfg=pcp_b200.CfgDict(NUM_BEV_FEATURES=C), grid_size=(nx, ny, 1))
+    bd = scat({"pillar_features": feats.to(DEV), "voxel_coords": coords.to(DEV)})
+    want = po.pointpillar_scatter(feats, coords, (nx, ny, 1), C)
+    assert torch.equal(bd["spatial_features"].cpu(), want)
+
+
+def test_results_are_deterministic_and_inputs_untouched():
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    pts = syn.batch_of_frames(2, 100000, 12)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    p_dev = pts.to(DEV)
+    a = scat(vfe({"points": p_dev, "batch_size": 2}))
+    b = scat(vfe({"points": p_dev, "batch_size": 2}))
+    torch.cuda.synchronize()
+    assert torch.equal(p_dev.cpu(), pts)
+    for k in ("pillar_features", "voxel_coords", "spatial_features"):
+        assert torch.equal(a[k], b[k]), f"{k} differs between two runs"
+        assert a[k].data_ptr() != b[k].data_ptr()
+
+
+def test_permuting_points_permutes_nothing_in_the_outputs():
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    pts = syn.batch_of_frames(2, 50000, 13)
+    perm = torch.randperm(pts.shape[0], generator=torch.Generator().manual_seed(4))
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    a = run_modules(vfe, scat, pts, 2)
+    b = run_modules(vfe, scat, pts[perm].contiguous(), 2)
+    assert torch.equal(a["voxel_coords"], b["voxel_coords"])
+    assert_features_close(a["pillar_features"].cpu().numpy(), b["pillar_features"].cpu().numpy(), "permuted")
+
+
+def test_error_behaviour():
+    import pcp_b200
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    pts = syn.batch_of_frames(2, 1000, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vfe({"points": pts, "batch_size": 2})
+    with pytest.raises(RuntimeError, match="frame index outside"):
+        vfe({"points": pts.to(DEV), "batch_size": 1})
+    vfe.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        vfe({"points": pts.to(DEV), "batch_size": 2})
+    with pytest.raises(NotImplementedError):
+        vfe.pfn_layers[0](torch.zeros(1, 11), torch.zeros(1, dtype=torch.long))
+    vfe_cfg, _ = model_cfgs(5, num_filters=(64, 128, 128))
+    bad = pcp_b200.DynamicPillarVFE(model_cfg=vfe_cfg, num_point_features=5, voxel_size=vox, grid_size=grid,
+                                    point_cloud_range=rng).to(DEV).eval()
+    with pytest.raises(NotImplementedError, match="NUM_FILTERS"):
+        bad({"points": pts.to(DEV), "batch_size": 2})
+
+
+def test_checkpoint_reload_repacks_parameters():
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5, seed=0)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    pts = syn.batch_of_frames(1, 8000, 3)
+    a = run_modules(vfe, scat, pts, 1)["pillar_features"].clone()
+    sd2 = syn.pfn_state_dict(11, (64, 64), True, seed=99)
+    vfe.load_state_dict(sd2)
+    b = run_modules(vfe, scat, pts, 1)["pillar_features"]
+    want = po.dynamic_pillar_vfe(pts, cfg, layers_from_state_dict(sd2), unique_dim0=False)["pillar_features"]
+    assert not torch.equal(a, b)
+    assert_features_close(b.cpu().numpy(), want.numpy(), "after reload")
+
+
+@pytest.mark.parametrize("n_frames,n_points,voxel,uniform", [
+    (8, 300000, None, False),                 # bench workload: 8 early-fusion frames on one GPU
+    (1, 4000000, [0.1, 0.1, 8.0], False),     # BASELINE config 5: 4 M points, 1024^2 canvas
+    (1, 2000000, [0.1, 0.1, 8.0], True),      # uniform xy: maximum occupancy
+])
+def test_full_size_properties(n_frames, n_points, voxel, uniform):
+    """At sizes the torch oracle does not finish quickly: integer half against numpy, occupancy == P,
+    canvas column sums == pillar feature column sums (every pillar lands exactly once), determinism."""
+    from pcp_b200.modules import CTX_KEY
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5, voxel=voxel)
+    pts = syn.batch_of_frames(n_frames, n_points, 5, uniform_xy=uniform)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    bd = run_modules(vfe, scat, pts, n_frames)
+    keep, keys, unq, inv, cnt = po.quantise_keys_numpy(pts.numpy(), cfg)
+    nxy, ny = int(grid[0]) * int(grid[1]), int(grid[1])
+    coords = np.stack([unq // nxy, np.zeros_like(unq), unq % ny, (unq % nxy) // ny], axis=1).astype(np.int32)
+    assert np.array_equal(bd["voxel_coords"].cpu().numpy(), coords)
+    pp = bd[CTX_KEY]["point_pillar"].cpu().numpy()
+    assert np.array_equal(pp >= 0, keep) and np.array_equal(pp[keep], inv.astype(np.int32))
+    sf, pf = bd["spatial_features"], bd["pillar_features"]
+    assert int((sf != 0).any(dim=1).sum()) == unq.shape[0]
+    assert torch.allclose(sf.double().sum(dim=(0, 2, 3)), pf.double().sum(dim=0), rtol=1e-12, atol=0)
+    assert bool(torch.isfinite(pf).all()) and float(pf.min()) >= 0.0
+    bd2 = run_modules(vfe, scat, pts, n_frames)
+    assert torch.equal(bd2["pillar_features"], pf)
