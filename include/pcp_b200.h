@@ -173,6 +173,13 @@ int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreg
               int32_t with_batch_col, float batch_idx, float* rows_out, int64_t out_stride,
               int32_t* box_idx_out, void* stream);
 
+/*
+ * Diagnostic: C[128 x n] = A[128 x k] . B[n x k]^T through exactly the tensor-core path pcp_pfn() uses
+ * (shared-memory operand panels, tcgen05.mma kind::tf32 with the 3xTF32 split, TMEM accumulator,
+ * tcgen05.ld).  k multiple of 8 up to 64, n = 32 or 64, all row-major fp32 device pointers.
+ */
+int pcp_selftest_umma(const float* a, const float* b, int32_t k, int32_t n, float* c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

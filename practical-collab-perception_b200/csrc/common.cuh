@@ -50,6 +50,8 @@ int  cuda_fail(cudaError_t e, const char* what);
 //   seg_off    int32[cap+1]     first sorted position of each pillar (exclusive scan of counts)
 //   sorted_idx int32[N]         input row numbers grouped by pillar, ascending inside a pillar
 //   big_list   int32[N/32+1]    pillars with more than kSmallSeg points (sorted by a CTA each)
+//   tile_first int32[N/kWin+3]  first pillar whose first sorted point lies in PFN window t (ascending)
+//   long_list  int32[N/128+1]   pillars with more than kLongSeg points (streamed by the SIMT PFN kernel)
 // [hdr | scan_state | cell] is cleared by one memset at the start of pcp_voxelize().
 // ---------------------------------------------------------------------------------------------
 constexpr int kHdrInts = 64;
@@ -58,9 +60,12 @@ constexpr int kHdrBigCount = 17;     // entries in big_list
 constexpr int kScanTileCells = 2048; // cells per scan tile (256 threads x 8)
 constexpr int kSmallSeg = 32;        // segments up to this size are index-sorted by one warp
 constexpr int kBigSegMax = 4096;     // segments up to this size are index-sorted by one CTA in smem
+constexpr int kHdrLongCount = 18;    // entries in long_list
+constexpr int kWin = 112;            // PFN group window: pillars whose first sorted point lies in a window of kWin positions
+constexpr int kLongSeg = 128;        // pillars with more points than one PFN sub-tile (handled by the streaming kernel)
 
 struct WsLayout {
-  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, big_list, total;
+  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, big_list, tile_first, long_list, total;
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
   int64_t cells, cap, scan_tiles;
 };
@@ -82,6 +87,8 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   L.seg_off = o;     o = align_up(o + sizeof(int32_t) * (size_t)(L.cap + 2), 256);
   L.sorted_idx = o;  o = align_up(o + sizeof(int32_t) * (size_t)(n + 1), 256);
   L.big_list = o;    o = align_up(o + sizeof(int32_t) * (size_t)(n / kSmallSeg + 2), 256);
+  L.tile_first = o;  o = align_up(o + sizeof(int32_t) * (size_t)(n / kWin + 4), 256);
+  L.long_list = o;   o = align_up(o + sizeof(int32_t) * (size_t)(n / kLongSeg + 2), 256);
   L.total = o;
   return L;
 }
@@ -95,6 +102,8 @@ struct WsView {
   int32_t* seg_off;
   int32_t* sorted_idx;
   int32_t* big_list;
+  int32_t* tile_first;
+  int32_t* long_list;
 };
 
 __host__ inline WsView ws_view(void* base, const WsLayout& L) {
@@ -108,15 +117,11 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.seg_off = reinterpret_cast<int32_t*>(p + L.seg_off);
   v.sorted_idx = reinterpret_cast<int32_t*>(p + L.sorted_idx);
   v.big_list = reinterpret_cast<int32_t*>(p + L.big_list);
+  v.tile_first = reinterpret_cast<int32_t*>(p + L.tile_first);
+  v.long_list = reinterpret_cast<int32_t*>(p + L.long_list);
   return v;
 }
 
-// The workspace header remembers the problem it was built for so that the consumers
-// (pcp_pfn, pcp_segment_reduce, pcp_bev_scatter_ws) can be given just the pointer.
-constexpr int kHdrN = 24;        // low / high 32 bits of n_points
-constexpr int kHdrFrames = 26;
-constexpr int kHdrNx = 27;
-constexpr int kHdrNy = 28;
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -7,6 +7,7 @@
 // Pillars with more points than a window are streamed through the same stages in 128-point chunks
 // (three passes: sums, layer-0 max, layer 1), so any point distribution is handled by one launch.
 #include "common.cuh"
+#include "pfn_tc.cuh"
 
 namespace pcp {
 
@@ -45,6 +46,8 @@ struct PfnArgs {
   const int32_t* hdr;
   const int32_t* seg_off;
   const int32_t* sorted_idx;
+  const int32_t* tile_first;
+  const int32_t* long_list;
   float* out;
   float* mean_out;
 };
@@ -72,54 +75,26 @@ __device__ __forceinline__ void tile_gemm(const float (*A)[kLd], const float* B,
 
 // packed parameter block (floats):  w0t[c_in][H0] | a0[H0] | b0[H0] | w1a_t[32][64] | w1b_t[32][64] | a1[64] | b1[64]
 __host__ __device__ inline int pfn_h0(int num_layers) { return num_layers == 2 ? kHidden : kCout; }
-__host__ __device__ inline size_t pfn_param_floats(int c_in, int num_layers) {
+__host__ __device__ inline size_t pfn_param_floats_simt(int c_in, int num_layers) {
   const int h0 = pfn_h0(num_layers);
   size_t n = (size_t)c_in * h0 + 2 * h0;
   if (num_layers == 2) n += 2 * (size_t)kHidden * kCout + 2 * kCout;
+  return (n + 3) / 4 * 4;   // keeps the tensor-core section 16-byte aligned
+}
+__host__ __device__ inline int pfn_k0(int c_in) { return (c_in + 7) / 8 * 8; }
+// tensor-core section (two layers only): w0h | w0l ([k0/4][32][4]) | w1h | w1l ([16][64][4])
+__host__ __device__ inline size_t pfn_param_floats(int c_in, int num_layers) {
+  size_t n = pfn_param_floats_simt(c_in, num_layers);
+  if (num_layers == 2) n += 2 * (size_t)pfn_k0(c_in) * 32 + 2 * 64 * 64;
   return n;
 }
 
+// all PFN stages for the pillars [pa, pb) (at most kT pillars), streamed in chunks of kT rows
 template <int kLayers>
-__global__ void __launch_bounds__(kThreads, 1)
-pfn_kernel(const PfnArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  PfnSmem& S = *reinterpret_cast<PfnSmem*>(smem_raw);
+__device__ __forceinline__ void pfn_process_range(PfnSmem& S, const PfnArgs& A, const int pa, const int pb) {
   constexpr int H0 = (kLayers == 2) ? kHidden : kCout;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int P = A.hdr[PCP_COUNT_PILLARS];
-  const int Nk = A.hdr[PCP_COUNT_KEPT];
-  const int64_t w_begin = (int64_t)blockIdx.x * kT;
-  if (w_begin >= Nk) return;
-  const int64_t w_end = w_begin + kT;
-
-  // pillars whose first point lies in [w_begin, w_end): lower_bound on seg_off (ascending, seg_off[P] = Nk)
-  if (tid < 2) {
-    const int64_t target = tid == 0 ? w_begin : w_end;
-    int lo = 0, hi = P;  // first r in [0, P] with seg_off[r] >= target
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (A.seg_off[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    S.off[kT + tid] = lo;  // stash pa / pb in the tail of the offset array
-  }
-  // stage the weights while the search runs
-  {
-    const float* p = A.params;
-    for (int i = tid; i < A.c_in * H0; i += kThreads) S.w0[i] = p[i];
-    p += A.c_in * H0;
-    for (int i = tid; i < H0; i += kThreads) { S.a0[i] = p[i]; S.b0[i] = p[H0 + i]; }
-    p += 2 * H0;
-    if (kLayers == 2) {
-      for (int i = tid; i < kHidden * kCout; i += kThreads) { S.w1a[i] = p[i]; S.w1b[i] = p[kHidden * kCout + i]; }
-      p += 2 * kHidden * kCout;
-      for (int i = tid; i < kCout; i += kThreads) { S.a1[i] = p[i]; S.b1[i] = p[kCout + i]; }
-    }
-  }
-  __syncthreads();
-  const int pa = S.off[kT], pb = S.off[kT + 1];
   const int npil = pb - pa;
-  if (npil <= 0) return;  // window lies inside one long pillar owned by an earlier CTA
-  __syncthreads();
   for (int i = tid; i <= npil; i += kThreads) S.off[i] = A.seg_off[pa + i];
   for (int i = tid; i < 3 * kLd; i += kThreads) (&S.mean[0][0])[i] = 0.f;
   __syncthreads();
@@ -332,6 +307,39 @@ pfn_kernel(const PfnArgs A) {
   }
 }
 
+// kFromList = false: one group (window of kWin sorted positions, tile_first[]) per loop iteration
+// kFromList = true : one long pillar (more than kLongSeg points, long_list[]) per loop iteration
+template <int kLayers, bool kFromList>
+__global__ void __launch_bounds__(kThreads, 1)
+pfn_kernel(const PfnArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PfnSmem& S = *reinterpret_cast<PfnSmem*>(smem_raw);
+  constexpr int H0 = (kLayers == 2) ? kHidden : kCout;
+  const int tid = threadIdx.x;
+  const int n_items = kFromList ? A.hdr[kHdrLongCount] : (A.hdr[PCP_COUNT_KEPT] + kWin - 1) / kWin;
+  if ((int)blockIdx.x >= n_items) return;
+  {
+    const float* p = A.params;
+    for (int i = tid; i < A.c_in * H0; i += kThreads) S.w0[i] = p[i];
+    p += A.c_in * H0;
+    for (int i = tid; i < H0; i += kThreads) { S.a0[i] = p[i]; S.b0[i] = p[H0 + i]; }
+    p += 2 * H0;
+    if (kLayers == 2) {
+      for (int i = tid; i < kHidden * kCout; i += kThreads) { S.w1a[i] = p[i]; S.w1b[i] = p[kHidden * kCout + i]; }
+      p += 2 * kHidden * kCout;
+      for (int i = tid; i < kCout; i += kThreads) { S.a1[i] = p[i]; S.b1[i] = p[kCout + i]; }
+    }
+  }
+  __syncthreads();
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    int pa, pb;
+    if (kFromList) { pa = A.long_list[it]; pb = pa + 1; }
+    else { pa = A.tile_first[it]; pb = A.tile_first[it + 1]; }
+    if (pb > pa) pfn_process_range<kLayers>(S, A, pa, pb);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // parameter packing: fold BN(eval) into scale / shift, transpose the weights
 // ------------------------------------------------------------------------------------------------
@@ -459,6 +467,8 @@ extern "C" int pcp_pack_pfn_params(const pcp_pfn_desc* desc, const float* w0, co
                                             bn0_var, w1, lin_bias1, bn1_weight, bn1_bias, bn1_mean, bn1_var, eps,
                                             packed_out);
   PCP_LAUNCH_CHECK("pack_params_kernel");
+  if (desc->num_layers == 2)
+    return launch_pack_tc(c_in, pfn_k0(c_in), w0, w1, packed_out + pfn_param_floats_simt(c_in, 2), stream);
   return 0;
 }
 
@@ -484,14 +494,26 @@ extern "C" int pcp_pfn(const float* points, int64_t row_stride, int64_t n_points
   a.with_distance = desc->with_distance;
   a.params = packed_params; a.hdr = W.hdr; a.seg_off = W.seg_off; a.sorted_idx = W.sorted_idx;
   a.out = pillar_features_out; a.mean_out = pillar_mean_out;
-  const unsigned blocks = (unsigned)((n_points + kT - 1) / kT);
+  a.tile_first = W.tile_first; a.long_list = W.long_list;
   const size_t smem = sizeof(PfnSmem);
   if (desc->num_layers == 2) {
-    PCP_CUDA(cudaFuncSetAttribute(pfn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pfn_kernel<2><<<blocks, kThreads, smem, stream>>>(a);
+    // tensor-core kernel for every pillar of up to kLongSeg points ...
+    TcArgs t;
+    t.points = points; t.stride = row_stride; t.g = *grid; t.c_in = c_in; t.n_raw = a.n_raw; t.raw_col0 = a.raw_col0;
+    t.with_distance = a.with_distance; t.k0 = pfn_k0(c_in);
+    t.params_simt = packed_params; t.params_tc = packed_params + pfn_param_floats_simt(c_in, 2);
+    t.a0_off = c_in * kHidden; t.a1_off = c_in * kHidden + 2 * kHidden + 2 * kHidden * kCout;
+    t.hdr = W.hdr; t.seg_off = W.seg_off; t.sorted_idx = W.sorted_idx; t.tile_first = W.tile_first;
+    t.out = pillar_features_out; t.mean_out = pillar_mean_out;
+    if (int rc = launch_pfn_tc(t, n_points, stream)) return rc;
+    // ... and the chunk-streaming kernel for the (few) longer ones
+    PCP_CUDA(cudaFuncSetAttribute(pfn_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfn_kernel<2, true><<<148, kThreads, smem, stream>>>(a);
   } else {
-    PCP_CUDA(cudaFuncSetAttribute(pfn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pfn_kernel<1><<<blocks, kThreads, smem, stream>>>(a);
+    const int64_t groups = (n_points + kWin - 1) / kWin;
+    const unsigned blocks = (unsigned)(groups < 148 * 8 ? groups : 148 * 8);
+    PCP_CUDA(cudaFuncSetAttribute(pfn_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfn_kernel<1, false><<<blocks, kThreads, smem, stream>>>(a);
   }
   PCP_LAUNCH_CHECK("pfn_kernel");
   return 0;

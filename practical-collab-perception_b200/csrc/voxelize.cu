@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t ny,
                   unsigned long long* __restrict__ state, int32_t* __restrict__ hdr,
                   int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
-                  int32_t* __restrict__ pillar_count, int32_t* __restrict__ big_list, int64_t scan_tiles) {
+                  int32_t* __restrict__ pillar_count, int32_t* __restrict__ big_list,
+                  int32_t* __restrict__ long_list, int64_t scan_tiles) {
   __shared__ int s_tile;
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_prefix;
@@ -188,6 +189,7 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
         if (pillar_count) pillar_count[r] = c[j];
         cell[idx] = r;
         if (c[j] > kSmallSeg) big_list[atomicAdd(&hdr[kHdrBigCount], 1)] = r;
+        if (c[j] > kLongSeg) long_list[atomicAdd(&hdr[kHdrLongCount], 1)] = r;
         excl += ((unsigned long long)(uint32_t)c[j] << 32) | 1ull;
       } else {
         cell[idx] = -1;
@@ -230,13 +232,23 @@ __device__ __forceinline__ void cswap(int32_t& a, int32_t& b) {
 // one thread per pillar for n <= 8 (19-comparator network), one warp per pillar for 9..32
 __global__ void __launch_bounds__(256)
 sort_small_segments_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
-                           const int32_t* __restrict__ hdr) {
+                           const int32_t* __restrict__ hdr, int32_t* __restrict__ tile_first) {
   const int32_t P = hdr[PCP_COUNT_PILLARS];
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   if ((r - lane) >= P) return;  // whole warp out of range
   int32_t off = 0, n = 0;
-  if (r < P) { off = seg_off[r]; n = seg_off[r + 1] - off; }
+  if (r < P) {
+    off = seg_off[r];
+    n = seg_off[r + 1] - off;
+    // PFN windows: tile_first[t] = first pillar whose first sorted point lies at or after position t * kWin
+    const int t = off / kWin, t_prev = (r > 0) ? seg_off[r - 1] / kWin : -1;
+    for (int u = t_prev + 1; u <= t; ++u) tile_first[u] = r;
+    if (r == P - 1) {
+      const int n_groups = (hdr[PCP_COUNT_KEPT] + kWin - 1) / kWin;
+      for (int u = t + 1; u <= n_groups; ++u) tile_first[u] = P;
+    }
+  }
   if (n >= 2 && n <= 8) {
     int32_t v[8];
 #pragma unroll
@@ -345,7 +357,7 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   }
   scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
       W.cell, L.cells, grid->nx, grid->ny, W.scan_state, W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
-      W.big_list, L.scan_tiles);
+      W.big_list, W.long_list, L.scan_tiles);
   PCP_LAUNCH_CHECK("scan_cells_kernel");
   {
     const unsigned blocks = (unsigned)((n_points + 255) / 256);
@@ -355,7 +367,7 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   }
   if (n_points > 0) {
     const unsigned blocks = (unsigned)((L.cap + 255) / 256);
-    sort_small_segments_kernel<<<blocks, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.hdr);
+    sort_small_segments_kernel<<<blocks, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.hdr, W.tile_first);
     PCP_LAUNCH_CHECK("sort_small_segments_kernel");
     sort_big_segments_kernel<<<296, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.big_list, W.hdr);
     PCP_LAUNCH_CHECK("sort_big_segments_kernel");
