@@ -82,10 +82,10 @@ __host__ __device__ inline size_t pfn_param_floats_simt(int c_in, int num_layers
   return (n + 3) / 4 * 4;   // keeps the tensor-core section 16-byte aligned
 }
 __host__ __device__ inline int pfn_k0(int c_in) { return (c_in + 7) / 8 * 8; }
-// tensor-core section (two layers only): w0h | w0l ([k0/4][32][4]) | w1h | w1l ([16][64][4])
+// tensor-core section (two layers only): w0h | w0l ([k0/4][32][4]) | w1h | w1l ([16][64][4], sign-folded) | |alpha1|[64]
 __host__ __device__ inline size_t pfn_param_floats(int c_in, int num_layers) {
   size_t n = pfn_param_floats_simt(c_in, num_layers);
-  if (num_layers == 2) n += 2 * (size_t)pfn_k0(c_in) * 32 + 2 * 64 * 64;
+  if (num_layers == 2) n += 2 * (size_t)pfn_k0(c_in) * 32 + 2 * 64 * 64 + 64;   // + |alpha1|
   return n;
 }
 
@@ -468,7 +468,9 @@ extern "C" int pcp_pack_pfn_params(const pcp_pfn_desc* desc, const float* w0, co
                                             packed_out);
   PCP_LAUNCH_CHECK("pack_params_kernel");
   if (desc->num_layers == 2)
-    return launch_pack_tc(c_in, pfn_k0(c_in), w0, w1, packed_out + pfn_param_floats_simt(c_in, 2), stream);
+    return launch_pack_tc(c_in, pfn_k0(c_in), w0, w1,
+                          packed_out + c_in * kHidden + 2 * kHidden + 2 * kHidden * kCout /* a1 */,
+                          packed_out + pfn_param_floats_simt(c_in, 2), stream);
   return 0;
 }
 

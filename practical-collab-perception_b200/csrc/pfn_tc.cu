@@ -29,6 +29,8 @@ constexpr int kRows = 128;        // MMA M = rows per sub-tile
 constexpr int kTcThreads = 256;
 constexpr int kTmemCols = 128;    // D0: columns [0, 32), D1: columns [32, 96)
 constexpr int kMaxK0 = 24;        // layer-0 K (c_in rounded up to 8)
+constexpr int kOffWin = kRows + 2;  // pillar-offset window: a sub-tile spans at most 128 pillars (+ end)
+constexpr int kCoop = 16;         // pillars with more rows than this are reduced by a whole warp
 
 struct TcSmem {
   // ---- operands (16-byte aligned panels, see umma.cuh) ----
@@ -41,35 +43,54 @@ struct TcSmem {
   // ---- per sub-tile metadata ----
   float xyz[3][kRows];
   float mean[3][kRows];
-  int off[kRows + 2];       // sorted position of the first row of each pillar of the group (+ end)
-  int lp[kRows];            // group-local pillar of each row
+  int off[2][kOffWin];      // double-buffered window of seg_off starting at the current pillar
+  int lp[kRows];            // window-local pillar of each row
+  int big[8];               // window-local pillars with more than kCoop rows (at most 7 fit in 128 rows)
+  int nbig;
   alignas(16) float a0[32], b0[32], a1[64], b1[64];
   alignas(8) uint64_t bar[2];
   uint32_t tmem_base;
-  int sub_begin, sub_end;   // current sub-tile's pillar range (group-local)
 };
-
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
-// lexicographic max over (hi, lo) pairs == split of the max of the exact values (both maps are monotone)
-__device__ __forceinline__ void lexmax(float& h, float& l, float h2, float l2) {
-  const bool take = (h2 > h) || (h2 == h && l2 > l);
-  h = take ? h2 : h;
-  l = take ? l2 : l;
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
+__device__ __forceinline__ float4 warp_max4(float4 v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v.x = fmaxf(v.x, __shfl_xor_sync(0xffffffffu, v.x, d));
+    v.y = fmaxf(v.y, __shfl_xor_sync(0xffffffffu, v.y, d));
+    v.z = fmaxf(v.z, __shfl_xor_sync(0xffffffffu, v.z, d));
+    v.w = fmaxf(v.w, __shfl_xor_sync(0xffffffffu, v.w, d));
+  }
+  return v;
+}
+
+// Row prefetch: each row is fetched by two threads as up to 4 float2 each (columns 0 .. c_raw of a row whose
+// stride is even and whose base is 8-byte aligned: the 8-column car layout and the 14-column ego layout).
+struct RowRegs { float2 v[4]; };
 
 __global__ void __launch_bounds__(kTcThreads, 2)
 pfn_tc_kernel(const TcArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int P = A.hdr[PCP_COUNT_PILLARS];
   const int Nk = A.hdr[PCP_COUNT_KEPT];
   const int n_groups = (Nk + kWin - 1) / kWin;
+  // contiguous, point-balanced pillar range of this CTA: windows [g0, g1) of kWin sorted positions
+  const int g0 = (int)((int64_t)n_groups * blockIdx.x / gridDim.x);
+  const int g1 = (int)((int64_t)n_groups * (blockIdx.x + 1) / gridDim.x);
+  if (g0 >= g1) return;
+  int cur = A.tile_first[g0];
+  const int pe = A.tile_first[g1];
+  if (cur >= pe) return;
   const int k0 = A.k0;
+  const int np4 = k0 >> 2;                      // layer-0 panels
+  const int nf2 = (A.raw_col0 + A.n_raw + 1) >> 1;   // float2 per row covering columns 0 .. raw_col0 + n_raw - 1
 
   // ---- one-time setup: weights -> smem, barriers, TMEM ----
   {
@@ -84,7 +105,10 @@ pfn_tc_kernel(const TcArgs A) {
       reinterpret_cast<float4*>(S.w1l)[i] = __ldg(src + 2 * n0 + n1 + i);
     }
     if (tid < 32) { S.a0[tid] = A.params_simt[A.a0_off + tid]; S.b0[tid] = A.params_simt[A.a0_off + 32 + tid]; }
-    if (tid < 64) { S.a1[tid] = A.params_simt[A.a1_off + tid]; S.b1[tid] = A.params_simt[A.a1_off + 64 + tid]; }
+    if (tid < 64) {
+      S.a1[tid] = A.params_tc[(2 * n0 + 2 * n1) * 4 + tid];      // |alpha1| (the sign lives in the weight rows)
+      S.b1[tid] = A.params_simt[A.a1_off + 64 + tid];
+    }
     if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&S.tmem_base, kTmemCols);
     fence_proxy_async_smem();
@@ -102,208 +126,300 @@ pfn_tc_kernel(const TcArgs A) {
   uint32_t phase0 = 0, phase1 = 0;
   const int row = (warp & 3) * 32 + lane;      // TMEM lane == sub-tile row owned in the epilogues
   const int half = warp >> 2;                  // which half of the accumulator columns this warp reads
+  const int prow = tid & (kRows - 1), ph = tid >> 7;   // gather: row and which half of its float2s
+  const bool fast_rows = ((A.stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(A.points) & 7) == 0) && nf2 <= 8;
 
-  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int pa = A.tile_first[grp], pb = A.tile_first[grp + 1];
-    const int npil = pb - pa;
-    if (npil <= 0) continue;
-    __syncthreads();
-    for (int i = tid; i <= npil; i += kTcThreads) S.off[i] = A.seg_off[pa + i];
-    if (tid == 0) { S.sub_begin = 0; S.sub_end = 0; }
-    __syncthreads();
+  auto load_off_window = [&](int first, int buf) {   // seg_off[first .. first + kOffWin) clipped to pe
+    for (int i = tid; i < kOffWin; i += kTcThreads) S.off[buf][i] = A.seg_off[min(first + i, pe)];
+  };
+  auto load_row = [&](int pos, RowRegs& r) {          // this thread's half of the row at sorted position pos
+    const float2* rp = reinterpret_cast<const float2*>(A.points + (int64_t)__ldg(A.sorted_idx + pos) * A.stride);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f2 = ph * 4 + j;
+      r.v[j] = (f2 < nf2) ? __ldg(rp + f2) : make_float2(0.f, 0.f);
+    }
+  };
 
-    while (true) {
-      // ---- greedy sub-tile: pillars [la, lb) with at most 128 rows; pillars longer than 128 rows are skipped ----
-      if (tid == 0) {
-        int la = S.sub_end;
-        while (la < npil && S.off[la + 1] - S.off[la] > kRows) ++la;     // long pillar: SIMT kernel's job
-        int lb = la;
-        while (lb < npil && S.off[lb + 1] - S.off[la] <= kRows) ++lb;
-        S.sub_begin = la; S.sub_end = lb;
-      }
-      __syncthreads();
-      const int la = S.sub_begin, lb = S.sub_end;
-      if (la >= npil) break;
-      const int r0 = S.off[la];
-      const int nrows = S.off[lb] - r0;
+  int buf = 0;
+  load_off_window(cur, 0);
+  __syncthreads();
+  RowRegs pre;                 // prefetched rows of the NEXT sub-tile
+  int pre_r0 = -1;             // sorted position the prefetch started at (-1: nothing prefetched)
+  int pre_idx = 0;
 
-      // ================= P1a: gather =================
-      if (tid < kRows) {
-        float x = 0.f, y = 0.f, z = 0.f;
-        int lp = -1;
-        if (tid < nrows) {
-          const int pos = r0 + tid;
-          int lo = la, hi = lb;                      // last pillar with off <= pos
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (S.off[mid] <= pos) lo = mid; else hi = mid;
-          }
-          lp = lo;
-          const float* rp = A.points + (int64_t)__ldg(A.sorted_idx + pos) * A.stride;
-          x = __ldg(rp + 1); y = __ldg(rp + 2); z = __ldg(rp + 3);
-          // raw features staged (unsplit) in the A0 hi panels
-          for (int f = 0; f < A.n_raw; ++f) a0h[(f >> 2) * (kRows * 4) + tid * 4 + (f & 3)] = __ldg(rp + A.raw_col0 + f);
-        }
-        S.lp[tid] = lp;
-        S.xyz[0][tid] = x; S.xyz[1][tid] = y; S.xyz[2][tid] = z;
-      }
+  while (cur < pe) {
+    const int* off = S.off[buf];
+    // ---- greedy sub-tile: window-local pillars [0, lb) with at most 128 rows ----
+    const int base = off[0];
+    const int lim = min(pe - cur, kRows);
+    const int lb = __syncthreads_count(tid >= 1 && tid <= lim && off[tid] - base <= kRows);
+    if (lb == 0) {             // the pillar at `cur` has more than 128 points: the streaming SIMT kernel owns it
+      cur += 1;
       __syncthreads();
-      // ================= P1b: per-pillar mean (sequential, ascending row order) =================
-      if (tid < lb - la) {
-        const int p = la + tid;
-        const int qs = S.off[p] - r0, qe = S.off[p + 1] - r0;
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int q = qs; q < qe; ++q) {
-          sx = __fadd_rn(sx, S.xyz[0][q]); sy = __fadd_rn(sy, S.xyz[1][q]); sz = __fadd_rn(sz, S.xyz[2][q]);
-        }
-        const float cnt = (float)max(qe - qs, 1);
-        const float mx = __fdiv_rn(sx, cnt), my = __fdiv_rn(sy, cnt), mz = __fdiv_rn(sz, cnt);
-        S.mean[0][p] = mx; S.mean[1][p] = my; S.mean[2][p] = mz;
-        if (A.mean_out) {
-          float* m = A.mean_out + (int64_t)(pa + p) * 3;
-          m[0] = mx; m[1] = my; m[2] = mz;
-        }
-      }
+      load_off_window(cur, buf);
+      pre_r0 = -1;
       __syncthreads();
-      // ================= P1c: features + TF32 split -> A0 =================
-      // the A0 hi panels double as an fp32 staging row: raw features were written by P1a, the derived
-      // features are appended here, then every panel is split in place (hi stays, lo goes to A0 lo)
-      if (tid < kRows) {
-        if (tid < nrows) {
-          const int lp = S.lp[tid];
-          const float x = S.xyz[0][tid], y = S.xyz[1][tid], z = S.xyz[2][tid];
-          float e[8];
-          e[0] = __fsub_rn(x, S.mean[0][lp]);                                  // f_cluster (:111)
-          e[1] = __fsub_rn(y, S.mean[1][lp]);
-          e[2] = __fsub_rn(z, S.mean[2][lp]);
-          const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
-          const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
-          e[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
-          e[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
-          e[5] = __fsub_rn(z, A.g.z_offset);
-          e[6] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // :124
-          e[7] = 0.f;
-          const int n_derived = A.with_distance ? 7 : 6;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int f = A.n_raw + j;
-            if (f < k0) a0h[(f >> 2) * (kRows * 4) + tid * 4 + (f & 3)] = (j < n_derived) ? e[j] : 0.f;
-          }
-          for (int f = A.n_raw + 8; f < k0; ++f) a0h[(f >> 2) * (kRows * 4) + tid * 4 + (f & 3)] = 0.f;
-        }
-        for (int kc = 0; kc * 4 < k0; ++kc) {
-          float* ph = a0h + kc * (kRows * 4) + tid * 4;
-          float4 v = (tid < nrows) ? ld4(ph) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float h[4], l[4];
-          split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
-          split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
-          st4(ph, h[0], h[1], h[2], h[3]);
-          st4(a0l + kc * (kRows * 4) + tid * 4, l[0], l[1], l[2], l[3]);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      __syncthreads();
-      // ================= M0 =================
-      if (tid == 0) {
-        tc_fence_after_sync();
-        mma_3xtf32(tmem_d0, sa0h, sa0l, kRows, smem_u32(S.w0h), smem_u32(S.w0l), 32, k0 / 8, idesc32, false);
-        mma_commit(&S.bar[0]);
-      }
-      mbar_wait(&S.bar[0], phase0);
-      phase0 ^= 1;
-      tc_fence_after_sync();
-      // ================= P2: layer-0 epilogue -> A1 panels 0..7 =================
-      if ((warp & 3) * 32 < nrows) {
-        float v[16];
-        tmem_ld16(tmem_d0 + ((uint32_t)((warp & 3) * 32) << 16) + half * 16, v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float h[4], l[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = half * 16 + j * 4 + i;
-            const float x = fmaxf(fmaf(v[j * 4 + i], S.a0[c], S.b0[c]), 0.f);
-            split_tf32(x, h[i], l[i]);
-          }
-          const int kc = half * 4 + j;
-          st4(S.a1h + kc * (kRows * 4) + row * 4, h[0], h[1], h[2], h[3]);
-          st4(S.a1l + kc * (kRows * 4) + row * 4, l[0], l[1], l[2], l[3]);
-        }
-      }
-      tc_fence_before_sync();
-      __syncthreads();
-      // ================= P3: per-pillar max of x0 -> A1 panels 8..15 of every row of the pillar =================
-      {
-        const int np = lb - la;
-        for (int item = tid; item < np * 8; item += kTcThreads) {
-          const int p = la + item % np, kc = item / np;
-          const int qs = S.off[p] - r0, qe = S.off[p + 1] - r0;
-          const float* ph = S.a1h + kc * (kRows * 4);
-          const float* pl = S.a1l + kc * (kRows * 4);
-          float4 h = ld4(ph + qs * 4), l = ld4(pl + qs * 4);
-          for (int q = qs + 1; q < qe; ++q) {
-            const float4 h2 = ld4(ph + q * 4), l2 = ld4(pl + q * 4);
-            lexmax(h.x, l.x, h2.x, l2.x); lexmax(h.y, l.y, h2.y, l2.y);
-            lexmax(h.z, l.z, h2.z, l2.z); lexmax(h.w, l.w, h2.w, l2.w);
-          }
-          float* qh = S.a1h + (8 + kc) * (kRows * 4);
-          float* ql = S.a1l + (8 + kc) * (kRows * 4);
-          for (int q = qs; q < qe; ++q) {
-            *reinterpret_cast<float4*>(qh + q * 4) = h;
-            *reinterpret_cast<float4*>(ql + q * 4) = l;
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      __syncthreads();
-      // ================= M1 =================
-      if (tid == 0) {
-        tc_fence_after_sync();
-        mma_3xtf32(tmem_d1, sa1h, sa1l, kRows, smem_u32(S.w1h), smem_u32(S.w1l), 64, 8, idesc64, false);
-        mma_commit(&S.bar[1]);
-      }
-      mbar_wait(&S.bar[1], phase1);
-      phase1 ^= 1;
-      tc_fence_after_sync();
-      // ================= P4: layer-1 epilogue -> y (aliases A1 hi; the MMAs that read it have completed) =================
-      if ((warp & 3) * 32 < nrows) {
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          float v[16];
-          tmem_ld16(tmem_d1 + ((uint32_t)((warp & 3) * 32) << 16) + half * 32 + part * 16, v);
+      continue;
+    }
+    const int r0 = base, nrows = off[lb] - base;
+    if (tid == 0) S.nbig = 0;
+    // ---- prefetch (registers): offsets of the next window, row indices of the next sub-tile ----
+    int pre_off[2];
+    pre_off[0] = (tid < kOffWin) ? __ldg(A.seg_off + min(cur + lb + tid, pe)) : 0;
+    const int next_r0 = r0 + nrows;
+    const bool have_next = fast_rows && (cur + lb < pe);
+    int nidx = 0;
+    if (have_next && next_r0 + prow < Nk) nidx = __ldg(A.sorted_idx + next_r0 + prow);
+
+    // ================= P1a: rows -> smem (xyz, staged raw features, window-local pillar) =================
+    {
+      RowRegs r;
+      const bool valid = prow < nrows;
+      if (pre_r0 == r0) r = pre;
+      else if (valid && fast_rows) load_row(r0 + prow, r);
+      if (fast_rows) {
+        if (valid) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float o[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = half * 32 + part * 16 + j * 4 + i;
-              o[i] = fmaxf(fmaf(v[j * 4 + i], S.a1[c], S.b1[c]), 0.f);
+            for (int e = 0; e < 2; ++e) {
+              const int c = (ph * 4 + j) * 2 + e;            // column of the input row
+              const float val = e ? r.v[j].y : r.v[j].x;
+              if (c >= 1 && c <= 3) S.xyz[c - 1][prow] = val;
+              const int f = c - A.raw_col0;
+              if (f >= 0 && f < A.n_raw) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = val;
             }
-            const int f4 = half * 8 + part * 4 + j;                         // float4 slot 0..15 of the row
-            st4(S.a1h + row * 64 + ((f4 ^ (row & 15)) << 2), o[0], o[1], o[2], o[3]);
           }
         }
+      } else if (ph == 0 && valid) {                          // generic layout: scalar loads, no prefetch
+        const float* rp = A.points + (int64_t)__ldg(A.sorted_idx + r0 + prow) * A.stride;
+        S.xyz[0][prow] = __ldg(rp + 1); S.xyz[1][prow] = __ldg(rp + 2); S.xyz[2][prow] = __ldg(rp + 3);
+        for (int f = 0; f < A.n_raw; ++f) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = __ldg(rp + A.raw_col0 + f);
       }
-      tc_fence_before_sync();
-      __syncthreads();
-      // ================= P5: per-pillar max of y -> pillar_features =================
-      {
-        const int np = lb - la;
-        for (int item = tid; item < np * 16; item += kTcThreads) {
-          const int p = la + (item >> 4), f4 = item & 15;
-          const int qs = S.off[p] - r0, qe = S.off[p + 1] - r0;
-          float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int q = qs; q < qe; ++q) {
-            const float4 t = ld4(S.a1h + q * 64 + ((f4 ^ (q & 15)) << 2));
-            m.x = fmaxf(m.x, t.x); m.y = fmaxf(m.y, t.y); m.z = fmaxf(m.z, t.z); m.w = fmaxf(m.w, t.w);
+      if (ph == 0) {
+        int lp = -1;
+        if (valid) {
+          const int pos = r0 + prow;
+          int lo = 0, hi = lb;                                 // last pillar with off <= pos
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (off[mid] <= pos) lo = mid; else hi = mid;
           }
-          *reinterpret_cast<float4*>(A.out + (int64_t)(pa + p) * 64 + f4 * 4) = m;
+          lp = lo;
         }
+        S.lp[prow] = lp;
       }
-      __syncthreads();
-      if (lb >= npil) break;
     }
+    __syncthreads();
+    // issue the row loads of the next sub-tile now; they land while this sub-tile computes
+    if (have_next && next_r0 + prow < Nk) {
+      const float2* rp = reinterpret_cast<const float2*>(A.points + (int64_t)nidx * A.stride);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f2 = ph * 4 + j;
+        pre.v[j] = (f2 < nf2) ? __ldg(rp + f2) : make_float2(0.f, 0.f);
+      }
+    }
+    pre_r0 = have_next ? next_r0 : -1;
+    (void)pre_idx;
+    // ================= P1b: per-pillar mean (sequential, ascending row order: exact) =================
+    if (tid < lb) {
+      const int qs = off[tid] - r0, qe = off[tid + 1] - r0;
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      for (int q = qs; q < qe; ++q) {
+        sx = __fadd_rn(sx, S.xyz[0][q]); sy = __fadd_rn(sy, S.xyz[1][q]); sz = __fadd_rn(sz, S.xyz[2][q]);
+      }
+      const float cnt = (float)max(qe - qs, 1);
+      const float mx = __fdiv_rn(sx, cnt), my = __fdiv_rn(sy, cnt), mz = __fdiv_rn(sz, cnt);
+      S.mean[0][tid] = mx; S.mean[1][tid] = my; S.mean[2][tid] = mz;
+      if (A.mean_out) {
+        float* m = A.mean_out + (int64_t)(cur + tid) * 3;
+        m[0] = mx; m[1] = my; m[2] = mz;
+      }
+      if (qe - qs > kCoop) S.big[atomicAdd(&S.nbig, 1)] = tid;
+    }
+    __syncthreads();
+    // ================= P1c: derived features + TF32 split -> A0 =================
+    // the A0 hi panels double as an fp32 staging row; both threads of a row append the derived features
+    // (identical values) and each splits its own panels in place (hi stays, lo goes to A0 lo)
+    {
+      const bool valid = prow < nrows;
+      if (valid) {
+        const int lp = S.lp[prow];
+        const float x = S.xyz[0][prow], y = S.xyz[1][prow], z = S.xyz[2][prow];
+        float e[8];
+        e[0] = __fsub_rn(x, S.mean[0][lp]);                                  // f_cluster (:111)
+        e[1] = __fsub_rn(y, S.mean[1][lp]);
+        e[2] = __fsub_rn(z, S.mean[2][lp]);
+        const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
+        const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
+        e[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
+        e[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
+        e[5] = __fsub_rn(z, A.g.z_offset);
+        e[6] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // :124
+        e[7] = 0.f;
+        const int n_derived = A.with_distance ? 7 : 6;
+        // a thread only touches the panels it splits below (the other thread of the row owns the rest)
+        const int f_lo = (ph ? (np4 + 1) / 2 : 0) * 4, f_hi = (ph ? np4 : (np4 + 1) / 2) * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int f = A.n_raw + j;
+          if (f >= f_lo && f < f_hi) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = (j < n_derived) ? e[j] : 0.f;
+        }
+        for (int f = max(A.n_raw + 8, f_lo); f < f_hi; ++f) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = 0.f;
+      }
+      const int kc0 = ph ? (np4 + 1) / 2 : 0, kc1 = ph ? np4 : (np4 + 1) / 2;
+      for (int kc = kc0; kc < kc1; ++kc) {
+        float* php = a0h + kc * (kRows * 4) + prow * 4;
+        const float4 v = valid ? ld4(php) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float h[4], l[4];
+        split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
+        split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
+        st4(php, h[0], h[1], h[2], h[3]);
+        st4(a0l + kc * (kRows * 4) + prow * 4, l[0], l[1], l[2], l[3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    // ================= M0 =================
+    if (tid == 0) {
+      tc_fence_after_sync();
+      mma_3xtf32(tmem_d0, sa0h, sa0l, kRows, smem_u32(S.w0h), smem_u32(S.w0l), 32, k0 / 8, idesc32, false);
+      mma_commit(&S.bar[0]);
+    }
+    mbar_wait(&S.bar[0], phase0);
+    phase0 ^= 1;
+    tc_fence_after_sync();
+    // ================= P2: layer-0 epilogue -> A1 panels 0..7 =================
+    if ((warp & 3) * 32 < nrows) {
+      float v[16];
+      tmem_ld16(tmem_d0 + ((uint32_t)((warp & 3) * 32) << 16) + half * 16, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float h[4], l[4];
+        const float4 al = ld4(S.a0 + half * 16 + j * 4), be = ld4(S.b0 + half * 16 + j * 4);
+        split_tf32(fmaxf(fmaf(v[j * 4 + 0], al.x, be.x), 0.f), h[0], l[0]);
+        split_tf32(fmaxf(fmaf(v[j * 4 + 1], al.y, be.y), 0.f), h[1], l[1]);
+        split_tf32(fmaxf(fmaf(v[j * 4 + 2], al.z, be.z), 0.f), h[2], l[2]);
+        split_tf32(fmaxf(fmaf(v[j * 4 + 3], al.w, be.w), 0.f), h[3], l[3]);
+        const int kc = half * 4 + j;
+        st4(S.a1h + kc * (kRows * 4) + row * 4, h[0], h[1], h[2], h[3]);
+        st4(S.a1l + kc * (kRows * 4) + row * 4, l[0], l[1], l[2], l[3]);
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    // ================= P3: per-pillar max of x0 -> A1 panels 8..15 of every row of the pillar =================
+    // x0 = hi + lo exactly, so the max is taken on the exact values and split once per pillar
+    {
+      const int nbig = S.nbig;
+      // short pillars: one thread per (pillar, panel); 8 consecutive lanes = 8 pillars of one panel
+      for (int item = tid; item < ((lb + 7) >> 3) * 64; item += kTcThreads) {
+        const int p = (item & 7) | ((item >> 6) << 3), kc = (item >> 3) & 7;
+        if (p >= lb) continue;
+        const int qs = off[p] - r0, qe = off[p + 1] - r0;
+        if (qe - qs > kCoop) continue;
+        const float* phh = S.a1h + kc * (kRows * 4);
+        const float* pll = S.a1l + kc * (kRows * 4);
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = qs; q < qe; ++q) {
+          const float4 h = ld4(phh + q * 4), l = ld4(pll + q * 4);
+          m = max4(m, make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w));
+        }
+        float4 mh, ml;
+        split_tf32(m.x, mh.x, ml.x); split_tf32(m.y, mh.y, ml.y); split_tf32(m.z, mh.z, ml.z); split_tf32(m.w, mh.w, ml.w);
+        float* qh = S.a1h + (8 + kc) * (kRows * 4);
+        float* ql = S.a1l + (8 + kc) * (kRows * 4);
+        for (int q = qs; q < qe; ++q) {
+          *reinterpret_cast<float4*>(qh + q * 4) = mh;
+          *reinterpret_cast<float4*>(ql + q * 4) = ml;
+        }
+      }
+      // long pillars: one warp per (pillar, panel), lanes stride the rows
+      for (int t = warp; t < nbig * 8; t += kTcThreads / 32) {
+        const int p = S.big[t >> 3], kc = t & 7;
+        const int qs = off[p] - r0, qe = off[p + 1] - r0;
+        const float* phh = S.a1h + kc * (kRows * 4);
+        const float* pll = S.a1l + kc * (kRows * 4);
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = qs + lane; q < qe; q += 32) {
+          const float4 h = ld4(phh + q * 4), l = ld4(pll + q * 4);
+          m = max4(m, make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w));
+        }
+        m = warp_max4(m);
+        float4 mh, ml;
+        split_tf32(m.x, mh.x, ml.x); split_tf32(m.y, mh.y, ml.y); split_tf32(m.z, mh.z, ml.z); split_tf32(m.w, mh.w, ml.w);
+        float* qh = S.a1h + (8 + kc) * (kRows * 4);
+        float* ql = S.a1l + (8 + kc) * (kRows * 4);
+        for (int q = qs + lane; q < qe; q += 32) {
+          *reinterpret_cast<float4*>(qh + q * 4) = mh;
+          *reinterpret_cast<float4*>(ql + q * 4) = ml;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    // ================= M1 =================
+    if (tid == 0) {
+      tc_fence_after_sync();
+      mma_3xtf32(tmem_d1, sa1h, sa1l, kRows, smem_u32(S.w1h), smem_u32(S.w1l), 64, 8, idesc64, false);
+      mma_commit(&S.bar[1]);
+    }
+    // stage the prefetched offset window while the tensor core works
+    if (tid < kOffWin) S.off[buf ^ 1][tid] = pre_off[0];
+    mbar_wait(&S.bar[1], phase1);
+    phase1 ^= 1;
+    tc_fence_after_sync();
+    // ================= P4: raw layer-1 accumulators -> smem (aliases A1 hi; its MMAs have completed) =================
+    // BN + ReLU are monotone per channel once the sign of alpha is folded into the weight row, so they
+    // commute with the max over the pillar's rows and are applied once per pillar in P5 (bit-identical)
+    if ((warp & 3) * 32 < nrows) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        float v[16];
+        tmem_ld16(tmem_d1 + ((uint32_t)((warp & 3) * 32) << 16) + half * 32 + part * 16, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f4 = half * 8 + part * 4 + j;                         // float4 slot 0..15 of the row
+          st4(S.a1h + row * 64 + ((f4 ^ (row & 15)) << 2), v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+        }
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    // ================= P5: per-pillar max, BN(eval) + ReLU -> pillar_features =================
+    {
+      const int nbig = S.nbig;
+      for (int item = tid; item < lb * 16; item += kTcThreads) {
+        const int p = item >> 4, f4 = item & 15;
+        const int qs = off[p] - r0, qe = off[p + 1] - r0;
+        if (qe - qs > kCoop) continue;
+        float4 m = ld4(S.a1h + qs * 64 + ((f4 ^ (qs & 15)) << 2));
+        for (int q = qs + 1; q < qe; ++q) m = max4(m, ld4(S.a1h + q * 64 + ((f4 ^ (q & 15)) << 2)));
+        const float4 al = ld4(S.a1 + f4 * 4), be = ld4(S.b1 + f4 * 4);
+        m.x = fmaxf(fmaf(m.x, al.x, be.x), 0.f); m.y = fmaxf(fmaf(m.y, al.y, be.y), 0.f);
+        m.z = fmaxf(fmaf(m.z, al.z, be.z), 0.f); m.w = fmaxf(fmaf(m.w, al.w, be.w), 0.f);
+        *reinterpret_cast<float4*>(A.out + (int64_t)(cur + p) * 64 + f4 * 4) = m;
+      }
+      for (int t = warp; t < nbig * 16; t += kTcThreads / 32) {
+        const int p = S.big[t >> 4], f4 = t & 15;
+        const int qs = off[p] - r0, qe = off[p + 1] - r0;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int q = qs + lane; q < qe; q += 32) m = max4(m, ld4(S.a1h + q * 64 + ((f4 ^ (q & 15)) << 2)));
+        m = warp_max4(m);
+        if (lane == 0) {
+          const float4 al = ld4(S.a1 + f4 * 4), be = ld4(S.b1 + f4 * 4);
+          m.x = fmaxf(fmaf(m.x, al.x, be.x), 0.f); m.y = fmaxf(fmaf(m.y, al.y, be.y), 0.f);
+          m.z = fmaxf(fmaf(m.z, al.z, be.z), 0.f); m.w = fmaxf(fmaf(m.w, al.w, be.w), 0.f);
+          *reinterpret_cast<float4*>(A.out + (int64_t)(cur + p) * 64 + f4 * 4) = m;
+        }
+      }
+    }
+    cur += lb;
+    buf ^= 1;
+    __syncthreads();
   }
   // ---- teardown ----
   tc_fence_before_sync();
@@ -315,7 +431,7 @@ pfn_tc_kernel(const TcArgs A) {
 // TC parameter panels: w0h | w0l ([k0/4][32][4]) | w1h | w1l ([16][64][4]), round-to-nearest TF32 split
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_tc_params_kernel(int c_in, int k0, const float* __restrict__ w0, const float* __restrict__ w1,
-                                      float* __restrict__ out) {
+                                      const float* __restrict__ alpha1, float* __restrict__ out) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int n0 = k0 * 32, n1 = 64 * 64;
   for (int i = tid; i < n0; i += nth) {
@@ -328,9 +444,13 @@ __global__ void pack_tc_params_kernel(int c_in, int k0, const float* __restrict_
   for (int i = tid; i < n1; i += nth) {
     const int kc = i / (64 * 4), n = (i / 4) % 64, k = kc * 4 + (i & 3);
     float h, l;
-    split_tf32_rn(w1[n * 64 + k], h, l);
+    // rows whose BN scale is negative are negated (exact) so that BN+ReLU is non-decreasing in the
+    // accumulator for every channel and commutes with the per-pillar max
+    const float sgn = (alpha1[n] < 0.f) ? -1.f : 1.f;
+    split_tf32_rn(sgn * w1[n * 64 + k], h, l);
     out[2 * n0 + i] = h; out[2 * n0 + n1 + i] = l;
   }
+  for (int i = tid; i < 64; i += nth) out[2 * n0 + 2 * n1 + i] = fabsf(alpha1[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,8 +532,9 @@ int launch_pfn_tc(const TcArgs& a, int64_t n_points, cudaStream_t stream) {
   PCP_LAUNCH_CHECK("pfn_tc_kernel");
   return 0;
 }
-int launch_pack_tc(int c_in, int k0, const float* w0, const float* w1, float* out, cudaStream_t stream) {
-  pack_tc_params_kernel<<<8, 256, 0, stream>>>(c_in, k0, w0, w1, out);
+int launch_pack_tc(int c_in, int k0, const float* w0, const float* w1, const float* alpha1, float* out,
+                   cudaStream_t stream) {
+  pack_tc_params_kernel<<<8, 256, 0, stream>>>(c_in, k0, w0, w1, alpha1, out);
   PCP_LAUNCH_CHECK("pack_tc_params_kernel");
   return 0;
 }

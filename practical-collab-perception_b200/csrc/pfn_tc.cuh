@@ -21,6 +21,8 @@ struct TcArgs {
 };
 
 int launch_pfn_tc(const TcArgs& a, int64_t n_points, cudaStream_t stream);
-int launch_pack_tc(int c_in, int k0, const float* w0, const float* w1, float* out, cudaStream_t stream);
+// alpha1: the folded BN scale of layer 1 (device pointer into the SIMT parameter block, already written on `stream`)
+int launch_pack_tc(int c_in, int k0, const float* w0, const float* w1, const float* alpha1, float* out,
+                   cudaStream_t stream);
 
 }  // namespace pcp
