@@ -180,6 +180,10 @@ int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreg
  */
 int pcp_selftest_umma(const float* a, const float* b, int32_t k, int32_t n, float* c, void* stream);
 
+/* Same product with the A operand staged in TENSOR MEMORY (tcgen05.st, then tcgen05.mma with a TMEM A address):
+ * the path layer 1 of pcp_pfn() uses for the activations it reads back from layer 0.  k multiple of 8 up to 32. */
+int pcp_selftest_umma_ts(const float* a, const float* b, int32_t k, int32_t n, float* c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

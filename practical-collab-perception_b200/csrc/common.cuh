@@ -40,8 +40,34 @@ int  cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// pillar length classes.  The PFN kernel puts ONE PILLAR PER TENSOR-MEMORY LANE and walks the pillar's
+// points as "slots" (slot j = j-th point of each of the 128 pillars of a group), so the per-pillar max is an
+// elementwise max between accumulators inside a thread.  Pillars are therefore binned by length: class k
+// holds pillars of kClassMinLen[k] .. kClassSlots[k] points and is processed with kClassSlots[k] slots
+// (shorter pillars repeat their last point - a max is idempotent).  Pillars above kSegRows points are cut
+// into SEGMENTS of kSegRows rows that are processed like a 32-slot class; their partial maxima meet in a
+// per-pillar accumulator (ordered-int atomicMax) that a finishing kernel turns into the output row.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNumClasses = 10;
+constexpr int kSegList = kNumClasses;       // list index of the long-pillar segments
+constexpr int kNumLists = kNumClasses + 1;
+constexpr int kSegRows = 32;                // rows per segment == largest class
+constexpr int kGroup = 128;                 // pillars (TMEM lanes) per group
+constexpr int kBigSegMax = 4096;            // long pillars up to this size are index-sorted by one CTA in smem
+__host__ __device__ constexpr int class_slots(int k) {
+  return k < 4 ? k + 1 : (k == 4 ? 6 : k == 5 ? 8 : k == 6 ? 12 : k == 7 ? 16 : k == 8 ? 24 : 32);
+}
+__host__ __device__ constexpr int class_min_len(int k) {
+  return k < 4 ? k + 1 : (k == 4 ? 5 : k == 5 ? 7 : k == 6 ? 9 : k == 7 ? 13 : k == 8 ? 17 : k == 9 ? 25 : 33);
+}
+// class of a pillar of n points, 1 <= n <= kSegRows
+__host__ __device__ inline int class_of(int n) {
+  return n <= 4 ? n - 1 : (n <= 6 ? 4 : n <= 8 ? 5 : n <= 12 ? 6 : n <= 16 ? 7 : n <= 24 ? 8 : 9);
+}
+
+// ---------------------------------------------------------------------------------------------
 // workspace layout.  One contiguous caller-owned block:
-//   hdr        int32[64]        counts (PCP_COUNT_*), scan ticket, big-segment list length
+//   hdr        int32[64]        counts (PCP_COUNT_*), scan ticket, list lengths, long-pillar count
 //   scan_state uint64[tiles]    decoupled look-back tile descriptors
 //   cell       int32[cells]     per-cell point count -> (after the scan) pillar rank or -1;
 //                               x-major like the reference's linear key: b*nx*ny + cx*ny + cy
@@ -49,25 +75,27 @@ int  cuda_fail(cudaError_t e, const char* what);
 //   within     int32[N]         arrival slot of the row inside its cell
 //   seg_off    int32[cap+1]     first sorted position of each pillar (exclusive scan of counts)
 //   sorted_idx int32[N]         input row numbers grouped by pillar, ascending inside a pillar
-//   big_list   int32[N/32+1]    pillars with more than kSmallSeg points (sorted by a CTA each)
-//   tile_first int32[N/kWin+3]  first pillar whose first sorted point lies in PFN window t (ascending)
-//   long_list  int32[N/128+1]   pillars with more than kLongSeg points (streamed by the SIMT PFN kernel)
+//   lists      int32[...]       per length class: pillar ranks (list k at list_off[k], capacity N / min_len + 1)
+//   seg_table  int4[N/16+2]     long-pillar segments {first sorted position, rows, long index, 0}
+//   long_table int4[N/33+1]     long pillars {pillar rank, first sorted position, rows, first segment}
+//   long_mean  float4[N/33+1]   mean xyz of each long pillar (sequential fp32 sum in ascending row order)
+//   long_acc   uint32[96*(N/33+1)] per long pillar: ordered-int running max of layer-0 (32) and layer-1 (64) values
 // [hdr | scan_state | cell] is cleared by one memset at the start of pcp_voxelize().
 // ---------------------------------------------------------------------------------------------
 constexpr int kHdrInts = 64;
 constexpr int kHdrScanTicket = 16;   // dynamic tile id of the scan
-constexpr int kHdrBigCount = 17;     // entries in big_list
+constexpr int kHdrListCount = 32;    // [32, 32 + kNumLists): entries in each list
+constexpr int kHdrLongCount = 48;    // long pillars
 constexpr int kScanTileCells = 2048; // cells per scan tile (256 threads x 8)
-constexpr int kSmallSeg = 32;        // segments up to this size are index-sorted by one warp
-constexpr int kBigSegMax = 4096;     // segments up to this size are index-sorted by one CTA in smem
-constexpr int kHdrLongCount = 18;    // entries in long_list
-constexpr int kWin = 112;            // PFN group window: pillars whose first sorted point lies in a window of kWin positions
-constexpr int kLongSeg = 128;        // pillars with more points than one PFN sub-tile (handled by the streaming kernel)
+constexpr unsigned kAccInit = 0x007fffffu;   // ordered-int encoding of -inf
+
+struct ListOffsets { int64_t off[kNumLists]; };   // int32 offsets of every list inside `lists`
 
 struct WsLayout {
-  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, big_list, tile_first, long_list, total;
+  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, lists, seg_table, long_table, long_mean, long_acc, total;
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
-  int64_t cells, cap, scan_tiles;
+  int64_t cells, cap, scan_tiles, seg_cap, long_cap;
+  ListOffsets lo;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -77,6 +105,8 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   L.cells = (int64_t)frames * nx * ny;
   L.cap = n < L.cells ? n : L.cells;
   L.scan_tiles = (L.cells + kScanTileCells - 1) / kScanTileCells;
+  L.seg_cap = n / 16 + 2;
+  L.long_cap = n / (kSegRows + 1) + 1;
   size_t o = 0;
   L.hdr = o;         o = align_up(o + sizeof(int32_t) * kHdrInts, 256);
   L.scan_state = o;  o = align_up(o + sizeof(uint64_t) * (size_t)(L.scan_tiles + 1), 256);
@@ -86,9 +116,20 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   L.within = o;      o = align_up(o + sizeof(int32_t) * (size_t)(n + 1), 256);
   L.seg_off = o;     o = align_up(o + sizeof(int32_t) * (size_t)(L.cap + 2), 256);
   L.sorted_idx = o;  o = align_up(o + sizeof(int32_t) * (size_t)(n + 1), 256);
-  L.big_list = o;    o = align_up(o + sizeof(int32_t) * (size_t)(n / kSmallSeg + 2), 256);
-  L.tile_first = o;  o = align_up(o + sizeof(int32_t) * (size_t)(n / kWin + 4), 256);
-  L.long_list = o;   o = align_up(o + sizeof(int32_t) * (size_t)(n / kLongSeg + 2), 256);
+  L.lists = o;
+  int64_t lo = 0;
+  for (int k = 0; k < kNumClasses; ++k) {
+    L.lo.off[k] = lo;
+    int64_t c = n / class_min_len(k) + 1;
+    if (c > L.cap + 1) c = L.cap + 1;
+    lo += (c + 63) / 64 * 64;
+  }
+  L.lo.off[kSegList] = lo;   // the segment "list" is the identity (entry e = segment e): no storage
+  o = align_up(o + sizeof(int32_t) * (size_t)(lo + 64), 256);
+  L.seg_table = o;   o = align_up(o + 16 * (size_t)L.seg_cap, 256);
+  L.long_table = o;  o = align_up(o + 16 * (size_t)L.long_cap, 256);
+  L.long_mean = o;   o = align_up(o + 16 * (size_t)L.long_cap, 256);
+  L.long_acc = o;    o = align_up(o + sizeof(uint32_t) * 96 * (size_t)L.long_cap, 256);
   L.total = o;
   return L;
 }
@@ -101,9 +142,11 @@ struct WsView {
   int32_t* within;
   int32_t* seg_off;
   int32_t* sorted_idx;
-  int32_t* big_list;
-  int32_t* tile_first;
-  int32_t* long_list;
+  int32_t* lists;
+  int4* seg_table;
+  int4* long_table;
+  float4* long_mean;
+  unsigned* long_acc;
 };
 
 __host__ inline WsView ws_view(void* base, const WsLayout& L) {
@@ -116,9 +159,11 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.within = reinterpret_cast<int32_t*>(p + L.within);
   v.seg_off = reinterpret_cast<int32_t*>(p + L.seg_off);
   v.sorted_idx = reinterpret_cast<int32_t*>(p + L.sorted_idx);
-  v.big_list = reinterpret_cast<int32_t*>(p + L.big_list);
-  v.tile_first = reinterpret_cast<int32_t*>(p + L.tile_first);
-  v.long_list = reinterpret_cast<int32_t*>(p + L.long_list);
+  v.lists = reinterpret_cast<int32_t*>(p + L.lists);
+  v.seg_table = reinterpret_cast<int4*>(p + L.seg_table);
+  v.long_table = reinterpret_cast<int4*>(p + L.long_table);
+  v.long_mean = reinterpret_cast<float4*>(p + L.long_mean);
+  v.long_acc = reinterpret_cast<unsigned*>(p + L.long_acc);
   return v;
 }
 
@@ -135,5 +180,14 @@ __device__ __forceinline__ float quantise(float v, float vmin, float vsize) {
 }
 
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldg(p); }
+
+// order-preserving float <-> uint32 map (atomicMax on the encoded value == max on the float)
+__device__ __forceinline__ unsigned ord_enc(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_dec(unsigned u) {
+  return (u & 0x80000000u) ? __uint_as_float(u & 0x7fffffffu) : __uint_as_float(~u);
+}
 
 }  // namespace pcp

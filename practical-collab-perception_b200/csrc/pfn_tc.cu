@@ -1,22 +1,30 @@
 // pfn_tc.cu - the PFN on 5th-generation tensor cores (tcgen05 + TMEM), 3xTF32 for fp32-grade accuracy.
 //
-// Reference: dynamic_pillar_vfe.py:110-129 + PFNLayerV2.forward :35-46 (two layers, NUM_FILTERS [64, 64]).
+// Reference: dynamic_pillar_vfe.py:110-129 + PFNLayerV2.forward :35-46 (NUM_FILTERS [64, 64] or [64]).
 //
-// Work unit: a GROUP = the pillars whose first sorted point lies in a window of kWin sorted positions
-// (tile_first[] from the voxelize stage).  A persistent CTA (two per SM) walks its groups; inside a group
-// the pillars are packed greedily into SUB-TILES of <= 128 rows (one row = one point), so a pillar is never
-// split and everything a pillar needs stays on chip:
-//   P1  gather rows, per-pillar mean (sequential fp32 sum in ascending row order, exact), features,
-//       TF32 hi/lo split -> A0 panels in shared memory
-//   M0  D0[128x32]  = A0 . W0^T                  (tcgen05.mma kind::tf32, 3 MMAs per K step: lo.hi, hi.lo, hi.hi)
-//   P2  TMEM -> regs: BN(eval)+ReLU -> x0, split -> A1 panels 0..7
-//   P3  per-pillar max of x0 (exact: lexicographic max over the (hi, lo) pairs), broadcast into A1 panels 8..15
-//       of every row of the pillar  == torch.cat([x, x_max[unq_inv]])
-//   M1  D1[128x64]  = A1 . W1^T  (K = 64)
-//   P4  TMEM -> regs: BN(eval)+ReLU -> y staged in shared memory (aliases A1)
-//   P5  per-pillar max of y -> pillar_features, 256-byte coalesced rows
-// Pillars with more than 128 points are left to the chunk-streaming SIMT kernel (pfn.cu), launched on the
-// `long_list` the scan produced.
+// Layout idea: ONE PILLAR PER TENSOR-MEMORY LANE.  A group is 128 pillars of one length class (work lists
+// built by the voxelize scan); slot j of the group is the j-th point of each of its pillars (pillars shorter
+// than the class repeat their last point).  Every slot is one M = 128 MMA tile whose accumulator row p
+// belongs to pillar p, so the per-pillar max - the reference's scatter_max - is an ELEMENTWISE max between
+// successive accumulators inside the thread that owns lane p: no cross-lane traffic, no shared-memory
+// transpose, no atomics.  Per slot:
+//   A0   gather the slot's rows, features (f_cluster / f_center need the pillar mean, computed per group in
+//        ascending row order), TF32 hi/lo split -> A0 panels in shared memory
+//   M0   D0[128 x 32] = A0 . W0^T                      (tcgen05.mma kind::tf32, SS, 3 MMAs per K step)
+//   E0   TMEM -> regs: BN(eval)+ReLU -> x0; running max0; hi/lo split -> written BACK TO TENSOR MEMORY as the
+//        A operand of layer 1 (tcgen05.st): the N' x 32 activation never touches shared memory or HBM
+//   M1   D1[128 x 64] = x0 . W1[:, :32]^T              (A from TMEM, B from smem)
+//   E1   TMEM -> regs: running max m1 (raw accumulators: BN+ReLU are applied once per pillar, see below)
+// and once per group
+//   H    D [128 x 64] = max0 . W1[:, 32:]^T            the x_max half of torch.cat([x, x_max[unq_inv]]) is the same
+//        for every point of a pillar, so it is evaluated once per pillar and added after the max:
+//        max_i(P_i + h) == max_i(P_i) + h exactly in fp32 because rounding is monotone
+//   OUT  relu(|a1| * (m1 + h) + b1): BN+ReLU after the max is exact because the sign of the BN scale is folded
+//        into the weight rows, which makes the map non-decreasing
+// Pillars above 32 points are cut into 32-row segments that run through the same slots; their partial maxima
+// meet in a per-pillar ordered-int accumulator (atomicMax) and pfn_finish_long_kernel (pfn.cu) applies H / OUT.
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "pfn_tc.cuh"
@@ -25,401 +33,359 @@ namespace pcp {
 
 using namespace umma;
 
-constexpr int kRows = 128;        // MMA M = rows per sub-tile
 constexpr int kTcThreads = 256;
-constexpr int kTmemCols = 128;    // D0: columns [0, 32), D1: columns [32, 96)
-constexpr int kMaxK0 = 24;        // layer-0 K (c_in rounded up to 8)
-constexpr int kOffWin = kRows + 2;  // pillar-offset window: a sub-tile spans at most 128 pillars (+ end)
-constexpr int kCoop = 16;         // pillars with more rows than this are reduced by a whole warp
-
-struct TcSmem {
-  // ---- operands (16-byte aligned panels, see umma.cuh) ----
-  alignas(128) float w0h[kMaxK0 * 32];
-  alignas(128) float w0l[kMaxK0 * 32];
-  alignas(128) float w1h[64 * 64];
-  alignas(128) float w1l[64 * 64];
-  alignas(128) float a1h[16 * kRows * 4];   // panels 0..7: x0, 8..15: pillar max; A0 aliases panels 8..13; y aliases all
-  alignas(128) float a1l[16 * kRows * 4];
-  // ---- per sub-tile metadata ----
-  float xyz[3][kRows];
-  float mean[3][kRows];
-  int off[2][kOffWin];      // double-buffered window of seg_off starting at the current pillar
-  int lp[kRows];            // window-local pillar of each row
-  int big[8];               // window-local pillars with more than kCoop rows (at most 7 fit in 128 rows)
-  int nbig;
-  alignas(16) float a0[32], b0[32], a1[64], b1[64];
-  alignas(8) uint64_t bar[2];
-  uint32_t tmem_base;
-};
+constexpr int kTmemCols = 128;    // accumulator: columns [0, 64); layer-1 A operand: hi [64, 96), lo [96, 128)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
-__device__ __forceinline__ float4 max4(float4 a, float4 b) {
-  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
-}
-__device__ __forceinline__ float4 warp_max4(float4 v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    v.x = fmaxf(v.x, __shfl_xor_sync(0xffffffffu, v.x, d));
-    v.y = fmaxf(v.y, __shfl_xor_sync(0xffffffffu, v.y, d));
-    v.z = fmaxf(v.z, __shfl_xor_sync(0xffffffffu, v.z, d));
-    v.w = fmaxf(v.w, __shfl_xor_sync(0xffffffffu, v.w, d));
+
+// kCfg: 0 = any layout (scalar loads, run-time feature map)
+//       1 = car / early-fusion rows: c_raw 5, absolute xyz, no distance, row stride % 4 == 0, 16-byte aligned
+//       2 = ego (lately fusion) rows: c_raw 11, absolute xyz, no distance, even row stride, 8-byte aligned
+template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0; };
+template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16; };
+template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24; };
+
+struct SmemPlan {   // float offsets into dynamic shared memory
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, a0h, a0l, prm_a0, prm_b0, prm_a1, prm_b1, mean, ints, total_bytes;
+};
+__host__ __device__ inline SmemPlan smem_plan(int k0, int layers) {
+  SmemPlan S{};
+  const int n0 = layers == 2 ? kHidden : kCout;
+  int o = 0;
+  S.w0h = o; o += k0 * n0;
+  S.w0l = o; o += k0 * n0;
+  if (layers == 2) {
+    S.w1ah = o; o += kHidden * kCout;
+    S.w1al = o; o += kHidden * kCout;
+    S.w1bh = o; o += kHidden * kCout;
+    S.w1bl = o; o += kHidden * kCout;
   }
-  return v;
+  S.a0h = o; o += k0 * kGroup;
+  S.a0l = o; o += k0 * kGroup;
+  S.prm_a0 = o; o += n0;
+  S.prm_b0 = o; o += n0;
+  if (layers == 2) {
+    S.prm_a1 = o; o += kCout;
+    S.prm_b1 = o; o += kCout;
+  }
+  S.mean = o; o += 3 * kGroup;
+  S.ints = o; o += 32;        // 2 mbarriers (16 B) | tmem base | group prefix [kNumLists + 1]
+  S.total_bytes = o * 4;
+  return S;
 }
 
-// Row prefetch: each row is fetched by two threads as up to 4 float2 each (columns 0 .. c_raw of a row whose
-// stride is even and whose base is 8-byte aligned: the 8-column car layout and the 14-column ego layout).
-struct RowRegs { float2 v[4]; };
-
-__global__ void __launch_bounds__(kTcThreads, 2)
-pfn_tc_kernel(const TcArgs A) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+template <int kLayers, int kCfg>
+__global__ void __launch_bounds__(kTcThreads, 3)
+pfn_slot_kernel(const TcArgs A) {
+  extern __shared__ __align__(128) float smem[];
+  constexpr int N0 = (kLayers == 2) ? kHidden : kCout;
+  const int k0 = kCfg ? RowCfg<kCfg>::k0 : A.k0;
+  const int n_raw = kCfg ? RowCfg<kCfg>::n_raw : A.n_raw;
+  const int raw_col0 = kCfg ? 1 : A.raw_col0;
+  const bool with_dist = kCfg ? false : (A.with_distance != 0);
+  const SmemPlan SP = smem_plan(k0, kLayers);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Nk = A.hdr[PCP_COUNT_KEPT];
-  const int n_groups = (Nk + kWin - 1) / kWin;
-  // contiguous, point-balanced pillar range of this CTA: windows [g0, g1) of kWin sorted positions
-  const int g0 = (int)((int64_t)n_groups * blockIdx.x / gridDim.x);
-  const int g1 = (int)((int64_t)n_groups * (blockIdx.x + 1) / gridDim.x);
-  if (g0 >= g1) return;
-  int cur = A.tile_first[g0];
-  const int pe = A.tile_first[g1];
-  if (cur >= pe) return;
-  const int k0 = A.k0;
-  const int np4 = k0 >> 2;                      // layer-0 panels
-  const int nf2 = (A.raw_col0 + A.n_raw + 1) >> 1;   // float2 per row covering columns 0 .. raw_col0 + n_raw - 1
+  const int p = tid & (kGroup - 1);      // pillar of the group == TMEM lane
+  const int h = tid >> 7;                // which half of the accumulator columns / which A0 panels
+  float* const a0h = smem + SP.a0h;
+  float* const a0l = smem + SP.a0l;
+  float* const s_mean = smem + SP.mean;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + SP.ints);
+  uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 4);
+  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 8);     // [kNumLists + 1] group prefix, processing order
 
-  // ---- one-time setup: weights -> smem, barriers, TMEM ----
+  // ---- one-time setup: parameters -> smem, barriers, TMEM, work prefix ----
   {
-    const float4* src = reinterpret_cast<const float4*>(A.params_tc);
-    const int n0 = k0 * 32 / 4, n1 = 64 * 64 / 4;
-    for (int i = tid; i < n0; i += kTcThreads) {
-      reinterpret_cast<float4*>(S.w0h)[i] = __ldg(src + i);
-      reinterpret_cast<float4*>(S.w0l)[i] = __ldg(src + n0 + i);
+    const int n_par = SP.a0h;                                   // all operand panels are contiguous in both layouts
+    const float4* src = reinterpret_cast<const float4*>(A.params);
+    float4* dst = reinterpret_cast<float4*>(smem);
+    for (int i = tid; i < n_par / 4; i += kTcThreads) dst[i] = __ldg(src + i);
+    const ParamLayout PL = param_layout(A.c_in, kLayers);
+    for (int i = tid; i < N0; i += kTcThreads) {
+      smem[SP.prm_a0 + i] = A.params[PL.a0 + i];
+      smem[SP.prm_b0 + i] = A.params[PL.b0 + i];
     }
-    for (int i = tid; i < n1; i += kTcThreads) {
-      reinterpret_cast<float4*>(S.w1h)[i] = __ldg(src + 2 * n0 + i);
-      reinterpret_cast<float4*>(S.w1l)[i] = __ldg(src + 2 * n0 + n1 + i);
+    if (kLayers == 2)
+      for (int i = tid; i < kCout; i += kTcThreads) {
+        smem[SP.prm_a1 + i] = A.params[PL.a1 + i];
+        smem[SP.prm_b1 + i] = A.params[PL.b1 + i];
+      }
+    for (int i = tid; i < 2 * k0 * kGroup; i += kTcThreads) a0h[i] = 0.f;    // a0h and a0l are adjacent
+    if (tid == 0) {
+      mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init();
+      int acc = 0;
+      for (int q = 0; q < kNumLists; ++q) {                     // processing order: segments, then classes 9 .. 0
+        s_pre[q] = acc;
+        acc += (A.hdr[kHdrListCount + (kNumLists - 1 - q)] + kGroup - 1) / kGroup;
+      }
+      s_pre[kNumLists] = acc;
     }
-    if (tid < 32) { S.a0[tid] = A.params_simt[A.a0_off + tid]; S.b0[tid] = A.params_simt[A.a0_off + 32 + tid]; }
-    if (tid < 64) {
-      S.a1[tid] = A.params_tc[(2 * n0 + 2 * n1) * 4 + tid];      // |alpha1| (the sign lives in the weight rows)
-      S.b1[tid] = A.params_simt[A.a1_off + 64 + tid];
-    }
-    if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(&S.tmem_base, kTmemCols);
+    if (warp == 0) tmem_alloc(s_tmem, kTmemCols);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
   }
-  const uint32_t tmem = S.tmem_base;
-  const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + 32;
-  const uint32_t sa1h = smem_u32(S.a1h), sa1l = smem_u32(S.a1l);
-  const uint32_t sa0h = sa1h + 8 * kRows * 16, sa0l = sa1l + 8 * kRows * 16;   // A0 aliases A1 panels 8..
-  float* const a0h = S.a1h + 8 * kRows * 4;
-  float* const a0l = S.a1l + 8 * kRows * 4;
-  const uint32_t idesc32 = idesc_tf32_m128(32), idesc64 = idesc_tf32_m128(64);
-  uint32_t phase0 = 0, phase1 = 0;
-  const int row = (warp & 3) * 32 + lane;      // TMEM lane == sub-tile row owned in the epilogues
-  const int half = warp >> 2;                  // which half of the accumulator columns this warp reads
-  const int prow = tid & (kRows - 1), ph = tid >> 7;   // gather: row and which half of its float2s
-  const bool fast_rows = ((A.stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(A.points) & 7) == 0) && nf2 <= 8;
+  const uint32_t tmem = *s_tmem;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t t_d = tmem, t_a1h = tmem + 64, t_a1l = tmem + 96;
+  const uint32_t sa0h = smem_u32(a0h), sa0l = smem_u32(a0l);
+  const uint32_t sw0h = smem_u32(smem + SP.w0h), sw0l = smem_u32(smem + SP.w0l);
+  const uint32_t sw1ah = smem_u32(smem + SP.w1ah), sw1al = smem_u32(smem + SP.w1al);
+  const uint32_t sw1bh = smem_u32(smem + SP.w1bh), sw1bl = smem_u32(smem + SP.w1bl);
+  const uint32_t idesc0 = idesc_tf32_m128(N0), idesc1 = idesc_tf32_m128(kCout);
+  uint32_t ph0 = 0, ph1 = 0;
+  const int total_groups = s_pre[kNumLists];
+  const int np4 = k0 >> 2;
 
-  auto load_off_window = [&](int first, int buf) {   // seg_off[first .. first + kOffWin) clipped to pe
-    for (int i = tid; i < kOffWin; i += kTcThreads) S.off[buf][i] = A.seg_off[min(first + i, pe)];
-  };
-  auto load_row = [&](int pos, RowRegs& r) {          // this thread's half of the row at sorted position pos
-    const float2* rp = reinterpret_cast<const float2*>(A.points + (int64_t)__ldg(A.sorted_idx + pos) * A.stride);
+  for (int w = blockIdx.x; w < total_groups; w += gridDim.x) {
+    // ---- which list / group ----
+    int q = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int f2 = ph * 4 + j;
-      r.v[j] = (f2 < nf2) ? __ldg(rp + f2) : make_float2(0.f, 0.f);
-    }
-  };
-
-  int buf = 0;
-  load_off_window(cur, 0);
-  __syncthreads();
-  RowRegs pre;                 // prefetched rows of the NEXT sub-tile
-  int pre_r0 = -1;             // sorted position the prefetch started at (-1: nothing prefetched)
-  int pre_idx = 0;
-
-  while (cur < pe) {
-    const int* off = S.off[buf];
-    // ---- greedy sub-tile: window-local pillars [0, lb) with at most 128 rows ----
-    const int base = off[0];
-    const int lim = min(pe - cur, kRows);
-    const int lb = __syncthreads_count(tid >= 1 && tid <= lim && off[tid] - base <= kRows);
-    if (lb == 0) {             // the pillar at `cur` has more than 128 points: the streaming SIMT kernel owns it
-      cur += 1;
-      __syncthreads();
-      load_off_window(cur, buf);
-      pre_r0 = -1;
-      __syncthreads();
-      continue;
-    }
-    const int r0 = base, nrows = off[lb] - base;
-    if (tid == 0) S.nbig = 0;
-    // ---- prefetch (registers): offsets of the next window, row indices of the next sub-tile ----
-    int pre_off[2];
-    pre_off[0] = (tid < kOffWin) ? __ldg(A.seg_off + min(cur + lb + tid, pe)) : 0;
-    const int next_r0 = r0 + nrows;
-    const bool have_next = fast_rows && (cur + lb < pe);
-    int nidx = 0;
-    if (have_next && next_r0 + prow < Nk) nidx = __ldg(A.sorted_idx + next_r0 + prow);
-
-    // ================= P1a: rows -> smem (xyz, staged raw features, window-local pillar) =================
-    {
-      RowRegs r;
-      const bool valid = prow < nrows;
-      if (pre_r0 == r0) r = pre;
-      else if (valid && fast_rows) load_row(r0 + prow, r);
-      if (fast_rows) {
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = (ph * 4 + j) * 2 + e;            // column of the input row
-              const float val = e ? r.v[j].y : r.v[j].x;
-              if (c >= 1 && c <= 3) S.xyz[c - 1][prow] = val;
-              const int f = c - A.raw_col0;
-              if (f >= 0 && f < A.n_raw) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = val;
-            }
-          }
-        }
-      } else if (ph == 0 && valid) {                          // generic layout: scalar loads, no prefetch
-        const float* rp = A.points + (int64_t)__ldg(A.sorted_idx + r0 + prow) * A.stride;
-        S.xyz[0][prow] = __ldg(rp + 1); S.xyz[1][prow] = __ldg(rp + 2); S.xyz[2][prow] = __ldg(rp + 3);
-        for (int f = 0; f < A.n_raw; ++f) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = __ldg(rp + A.raw_col0 + f);
-      }
-      if (ph == 0) {
-        int lp = -1;
-        if (valid) {
-          const int pos = r0 + prow;
-          int lo = 0, hi = lb;                                 // last pillar with off <= pos
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (off[mid] <= pos) lo = mid; else hi = mid;
-          }
-          lp = lo;
-        }
-        S.lp[prow] = lp;
+    for (int t = 1; t < kNumLists; ++t) q += (w >= s_pre[t]) ? 1 : 0;
+    const int list = kNumLists - 1 - q;
+    const bool is_seg = (list == kSegList);
+    const int slots = is_seg ? kSegRows : class_slots(list);
+    const int e = (w - s_pre[q]) * kGroup + p;
+    const bool valid = e < A.hdr[kHdrListCount + list];
+    int r = -1, off = 0, len = 0, li = -1;
+    if (valid) {
+      if (is_seg) {
+        const int4 sg = __ldg(A.seg_table + e);
+        off = sg.x; len = sg.y; li = sg.z;
+      } else {
+        r = __ldg(A.lists + A.lo.off[list] + e);
+        off = __ldg(A.seg_off + r);
+        len = __ldg(A.seg_off + r + 1) - off;
       }
     }
-    __syncthreads();
-    // issue the row loads of the next sub-tile now; they land while this sub-tile computes
-    if (have_next && next_r0 + prow < Nk) {
-      const float2* rp = reinterpret_cast<const float2*>(A.points + (int64_t)nidx * A.stride);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int f2 = ph * 4 + j;
-        pre.v[j] = (f2 < nf2) ? __ldg(rp + f2) : make_float2(0.f, 0.f);
-      }
-    }
-    pre_r0 = have_next ? next_r0 : -1;
-    (void)pre_idx;
-    // ================= P1b: per-pillar mean (sequential, ascending row order: exact) =================
-    if (tid < lb) {
-      const int qs = off[tid] - r0, qe = off[tid + 1] - r0;
-      float sx = 0.f, sy = 0.f, sz = 0.f;
-      for (int q = qs; q < qe; ++q) {
-        sx = __fadd_rn(sx, S.xyz[0][q]); sy = __fadd_rn(sy, S.xyz[1][q]); sz = __fadd_rn(sz, S.xyz[2][q]);
-      }
-      const float cnt = (float)max(qe - qs, 1);
-      const float mx = __fdiv_rn(sx, cnt), my = __fdiv_rn(sy, cnt), mz = __fdiv_rn(sz, cnt);
-      S.mean[0][tid] = mx; S.mean[1][tid] = my; S.mean[2][tid] = mz;
-      if (A.mean_out) {
-        float* m = A.mean_out + (int64_t)(cur + tid) * 3;
-        m[0] = mx; m[1] = my; m[2] = mz;
-      }
-      if (qe - qs > kCoop) S.big[atomicAdd(&S.nbig, 1)] = tid;
-    }
-    __syncthreads();
-    // ================= P1c: derived features + TF32 split -> A0 =================
-    // the A0 hi panels double as an fp32 staging row; both threads of a row append the derived features
-    // (identical values) and each splits its own panels in place (hi stays, lo goes to A0 lo)
-    {
-      const bool valid = prow < nrows;
+    // ---- pillar mean: scatter_mean = sum in ascending row order / count (dynamic_pillar_vfe.py:110) ----
+    if (h == 0) {
+      float mx = 0.f, my = 0.f, mz = 0.f;
       if (valid) {
-        const int lp = S.lp[prow];
-        const float x = S.xyz[0][prow], y = S.xyz[1][prow], z = S.xyz[2][prow];
-        float e[8];
-        e[0] = __fsub_rn(x, S.mean[0][lp]);                                  // f_cluster (:111)
-        e[1] = __fsub_rn(y, S.mean[1][lp]);
-        e[2] = __fsub_rn(z, S.mean[2][lp]);
+        if (is_seg) {
+          const float4 m = __ldg(A.long_mean + li);
+          mx = m.x; my = m.y; mz = m.z;
+        } else {
+          float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 4
+          for (int j = 0; j < len; ++j) {
+            const float* row = A.points + (int64_t)__ldg(A.sorted_idx + off + j) * A.stride;
+            float x, y, z;
+            if (kCfg == 1) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+              x = v.y; y = v.z; z = v.w;
+            } else {
+              x = __ldg(row + 1); y = __ldg(row + 2); z = __ldg(row + 3);
+            }
+            sx = __fadd_rn(sx, x); sy = __fadd_rn(sy, y); sz = __fadd_rn(sz, z);
+          }
+          const float cnt = (float)len;
+          mx = __fdiv_rn(sx, cnt); my = __fdiv_rn(sy, cnt); mz = __fdiv_rn(sz, cnt);
+          if (A.mean_out) {
+            float* m = A.mean_out + (int64_t)r * 3;
+            m[0] = mx; m[1] = my; m[2] = mz;
+          }
+        }
+      }
+      s_mean[p] = mx; s_mean[kGroup + p] = my; s_mean[2 * kGroup + p] = mz;
+    }
+    __syncthreads();
+    const float mean_x = s_mean[p], mean_y = s_mean[kGroup + p], mean_z = s_mean[2 * kGroup + p];
+
+    float max0[16];            // layer-0 running max, this thread's 16 channels (two layers only)
+    float m1[32];              // last-layer running max of the raw accumulators, this thread's 32 channels
+#pragma unroll
+    for (int i = 0; i < 16; ++i) max0[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
+
+    for (int j = 0; j < slots; ++j) {
+      // ================= A0: this slot's rows -> features -> TF32 hi/lo panels =================
+      {
+        const int jj = min(j, len - 1);
+        const bool have = valid;                       // slots past the pillar's length repeat its last point
+        const float* row = A.points;
+        if (have) row += (int64_t)__ldg(A.sorted_idx + off + jj) * A.stride;
+        float rv[12];
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (have) {
+          if (kCfg == 1) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(row));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(row) + 1);
+            rv[0] = v0.x; rv[1] = v0.y; rv[2] = v0.z; rv[3] = v0.w; rv[4] = v1.x; rv[5] = v1.y; rv[6] = v1.z; rv[7] = v1.w;
+            x = rv[1]; y = rv[2]; z = rv[3];
+          } else if (kCfg == 2) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(row) + c);
+              rv[2 * c] = v.x; rv[2 * c + 1] = v.y;
+            }
+            x = rv[1]; y = rv[2]; z = rv[3];
+          } else {
+            x = __ldg(row + 1); y = __ldg(row + 2); z = __ldg(row + 3);
+          }
+        }
+        float ed[7];
+        ed[0] = __fsub_rn(x, mean_x);                                              // f_cluster (:111)
+        ed[1] = __fsub_rn(y, mean_y);
+        ed[2] = __fsub_rn(z, mean_z);
         const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
         const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
-        e[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
-        e[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
-        e[5] = __fsub_rn(z, A.g.z_offset);
-        e[6] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // :124
-        e[7] = 0.f;
-        const int n_derived = A.with_distance ? 7 : 6;
-        // a thread only touches the panels it splits below (the other thread of the row owns the rest)
-        const int f_lo = (ph ? (np4 + 1) / 2 : 0) * 4, f_hi = (ph ? np4 : (np4 + 1) / 2) * 4;
+        ed[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
+        ed[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
+        ed[5] = __fsub_rn(z, A.g.z_offset);
+        ed[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
+        const int n_feat = n_raw + (with_dist ? 7 : 6);
+        auto feature = [&](int f) -> float {
+          if (f < n_raw) {
+            if (kCfg) return rv[(raw_col0 + f) < 12 ? (raw_col0 + f) : 11];
+            return __ldg(row + raw_col0 + f);
+          }
+          const int d = f - n_raw;
+          if (f >= n_feat) return 0.f;
+          return d == 0 ? ed[0] : d == 1 ? ed[1] : d == 2 ? ed[2] : d == 3 ? ed[3] : d == 4 ? ed[4] : d == 5 ? ed[5] : ed[6];
+        };
+        auto build = [&](auto hc) {
+          constexpr int H = decltype(hc)::value;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int f = A.n_raw + j;
-          if (f >= f_lo && f < f_hi) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = (j < n_derived) ? e[j] : 0.f;
-        }
-        for (int f = max(A.n_raw + 8, f_lo); f < f_hi; ++f) a0h[(f >> 2) * (kRows * 4) + prow * 4 + (f & 3)] = 0.f;
-      }
-      const int kc0 = ph ? (np4 + 1) / 2 : 0, kc1 = ph ? np4 : (np4 + 1) / 2;
-      for (int kc = kc0; kc < kc1; ++kc) {
-        float* php = a0h + kc * (kRows * 4) + prow * 4;
-        const float4 v = valid ? ld4(php) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float h[4], l[4];
-        split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
-        split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
-        st4(php, h[0], h[1], h[2], h[3]);
-        st4(a0l + kc * (kRows * 4) + prow * 4, l[0], l[1], l[2], l[3]);
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    // ================= M0 =================
-    if (tid == 0) {
-      tc_fence_after_sync();
-      mma_3xtf32(tmem_d0, sa0h, sa0l, kRows, smem_u32(S.w0h), smem_u32(S.w0l), 32, k0 / 8, idesc32, false);
-      mma_commit(&S.bar[0]);
-    }
-    mbar_wait(&S.bar[0], phase0);
-    phase0 ^= 1;
-    tc_fence_after_sync();
-    // ================= P2: layer-0 epilogue -> A1 panels 0..7 =================
-    if ((warp & 3) * 32 < nrows) {
-      float v[16];
-      tmem_ld16(tmem_d0 + ((uint32_t)((warp & 3) * 32) << 16) + half * 16, v);
+          for (int kc = H; kc < kMaxCin / 4; kc += 2) {
+            if (kc < np4) {
+              float v[4], hi[4], lo[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float h[4], l[4];
-        const float4 al = ld4(S.a0 + half * 16 + j * 4), be = ld4(S.b0 + half * 16 + j * 4);
-        split_tf32(fmaxf(fmaf(v[j * 4 + 0], al.x, be.x), 0.f), h[0], l[0]);
-        split_tf32(fmaxf(fmaf(v[j * 4 + 1], al.y, be.y), 0.f), h[1], l[1]);
-        split_tf32(fmaxf(fmaf(v[j * 4 + 2], al.z, be.z), 0.f), h[2], l[2]);
-        split_tf32(fmaxf(fmaf(v[j * 4 + 3], al.w, be.w), 0.f), h[3], l[3]);
-        const int kc = half * 4 + j;
-        st4(S.a1h + kc * (kRows * 4) + row * 4, h[0], h[1], h[2], h[3]);
-        st4(S.a1l + kc * (kRows * 4) + row * 4, l[0], l[1], l[2], l[3]);
+              for (int t = 0; t < 4; ++t) {
+                v[t] = have ? feature(kc * 4 + t) : 0.f;
+                split_tf32(v[t], hi[t], lo[t]);
+              }
+              st4(a0h + kc * (kGroup * 4) + p * 4, hi[0], hi[1], hi[2], hi[3]);
+              st4(a0l + kc * (kGroup * 4) + p * 4, lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        };
+        if (h == 0) build(std::integral_constant<int, 0>{}); else build(std::integral_constant<int, 1>{});
       }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    // ================= P3: per-pillar max of x0 -> A1 panels 8..15 of every row of the pillar =================
-    // x0 = hi + lo exactly, so the max is taken on the exact values and split once per pillar
-    {
-      const int nbig = S.nbig;
-      // short pillars: one thread per (pillar, panel); 8 consecutive lanes = 8 pillars of one panel
-      for (int item = tid; item < ((lb + 7) >> 3) * 64; item += kTcThreads) {
-        const int p = (item & 7) | ((item >> 6) << 3), kc = (item >> 3) & 7;
-        if (p >= lb) continue;
-        const int qs = off[p] - r0, qe = off[p + 1] - r0;
-        if (qe - qs > kCoop) continue;
-        const float* phh = S.a1h + kc * (kRows * 4);
-        const float* pll = S.a1l + kc * (kRows * 4);
-        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = qs; q < qe; ++q) {
-          const float4 h = ld4(phh + q * 4), l = ld4(pll + q * 4);
-          m = max4(m, make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w));
-        }
-        float4 mh, ml;
-        split_tf32(m.x, mh.x, ml.x); split_tf32(m.y, mh.y, ml.y); split_tf32(m.z, mh.z, ml.z); split_tf32(m.w, mh.w, ml.w);
-        float* qh = S.a1h + (8 + kc) * (kRows * 4);
-        float* ql = S.a1l + (8 + kc) * (kRows * 4);
-        for (int q = qs; q < qe; ++q) {
-          *reinterpret_cast<float4*>(qh + q * 4) = mh;
-          *reinterpret_cast<float4*>(ql + q * 4) = ml;
-        }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      // ================= M0 =================
+      if (tid == 0) {
+        tc_fence_after_sync();
+        mma_3xtf32(t_d, sa0h, sa0l, kGroup, sw0h, sw0l, N0, k0 / 8, idesc0, false);
+        mma_commit(&bars[0]);
       }
-      // long pillars: one warp per (pillar, panel), lanes stride the rows
-      for (int t = warp; t < nbig * 8; t += kTcThreads / 32) {
-        const int p = S.big[t >> 3], kc = t & 7;
-        const int qs = off[p] - r0, qe = off[p + 1] - r0;
-        const float* phh = S.a1h + kc * (kRows * 4);
-        const float* pll = S.a1l + kc * (kRows * 4);
-        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = qs + lane; q < qe; q += 32) {
-          const float4 h = ld4(phh + q * 4), l = ld4(pll + q * 4);
-          m = max4(m, make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w));
-        }
-        m = warp_max4(m);
-        float4 mh, ml;
-        split_tf32(m.x, mh.x, ml.x); split_tf32(m.y, mh.y, ml.y); split_tf32(m.z, mh.z, ml.z); split_tf32(m.w, mh.w, ml.w);
-        float* qh = S.a1h + (8 + kc) * (kRows * 4);
-        float* ql = S.a1l + (8 + kc) * (kRows * 4);
-        for (int q = qs + lane; q < qe; q += 32) {
-          *reinterpret_cast<float4*>(qh + q * 4) = mh;
-          *reinterpret_cast<float4*>(ql + q * 4) = ml;
-        }
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    // ================= M1 =================
-    if (tid == 0) {
+      mbar_wait(&bars[0], ph0);
+      ph0 ^= 1;
       tc_fence_after_sync();
-      mma_3xtf32(tmem_d1, sa1h, sa1l, kRows, smem_u32(S.w1h), smem_u32(S.w1l), 64, 8, idesc64, false);
-      mma_commit(&S.bar[1]);
-    }
-    // stage the prefetched offset window while the tensor core works
-    if (tid < kOffWin) S.off[buf ^ 1][tid] = pre_off[0];
-    mbar_wait(&S.bar[1], phase1);
-    phase1 ^= 1;
-    tc_fence_after_sync();
-    // ================= P4: raw layer-1 accumulators -> smem (aliases A1 hi; its MMAs have completed) =================
-    // BN + ReLU are monotone per channel once the sign of alpha is folded into the weight row, so they
-    // commute with the max over the pillar's rows and are applied once per pillar in P5 (bit-identical)
-    if ((warp & 3) * 32 < nrows) {
+      if (kLayers == 2) {
+        // ================= E0: BN+ReLU, running max0, x0 -> TMEM as the A operand of layer 1 =================
+        {
+          uint32_t rr[16];
+          tmem_ld16_nowait(t_d + lane_base + 16 * h, rr);
+          tmem_ld_wait();
+          float hi[16], lo[16];
+          const float* pa = smem + SP.prm_a0 + 16 * h;
+          const float* pb = smem + SP.prm_b0 + 16 * h;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 al = ld4(pa + i), be = ld4(pb + i);
+            const float a4[4] = {al.x, al.y, al.z, al.w}, b4[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float v = fmaxf(fmaf(__uint_as_float(rr[i + t]), a4[t], b4[t]), 0.f);
+              max0[i + t] = fmaxf(max0[i + t], v);
+              split_tf32(v, hi[i + t], lo[i + t]);
+            }
+          }
+          tmem_st16(t_a1h + lane_base + 16 * h, hi);
+          tmem_st16(t_a1l + lane_base + 16 * h, lo);
+          tmem_st_wait();
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+        // ================= M1 =================
+        if (tid == 0) {
+          tc_fence_after_sync();
+          mma_3xtf32_ts(t_d, t_a1h, t_a1l, sw1ah, sw1al, kCout, kHidden / 8, idesc1, false);
+          mma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], ph1);
+        ph1 ^= 1;
+        tc_fence_after_sync();
+      }
+      // ================= E1: running max of the raw last-layer accumulators =================
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
-        float v[16];
-        tmem_ld16(tmem_d1 + ((uint32_t)((warp & 3) * 32) << 16) + half * 32 + part * 16, v);
+        uint32_t rr[16];
+        tmem_ld16_nowait(t_d + lane_base + 32 * h + 16 * part, rr);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int f4 = half * 8 + part * 4 + j;                         // float4 slot 0..15 of the row
-          st4(S.a1h + row * 64 + ((f4 ^ (row & 15)) << 2), v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+        for (int i = 0; i < 16; ++i) m1[part * 16 + i] = fmaxf(m1[part * 16 + i], __uint_as_float(rr[i]));
+      }
+      tc_fence_before_sync();
+    }
+
+    if (is_seg) {
+      // ---- long pillar segment: partial maxima -> the pillar's accumulator ----
+      if (valid) {
+        unsigned* acc = A.long_acc + (int64_t)li * 96;
+        if (kLayers == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicMax(acc + 16 * h + i, ord_enc(max0[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicMax(acc + 32 + 32 * h + i, ord_enc(m1[i]));
+      }
+    } else {
+      if (kLayers == 2) {
+        // ================= H: max0 . W1[:, 32:]^T once per pillar =================
+        {
+          float hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) split_tf32(max0[i], hi[i], lo[i]);
+          tmem_st16(t_a1h + lane_base + 16 * h, hi);
+          tmem_st16(t_a1l + lane_base + 16 * h, lo);
+          tmem_st_wait();
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after_sync();
+          mma_3xtf32_ts(t_d, t_a1h, t_a1l, sw1bh, sw1bl, kCout, kHidden / 8, idesc1, false);
+          mma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], ph1);
+        ph1 ^= 1;
+        tc_fence_after_sync();
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          uint32_t rr[16];
+          tmem_ld16_nowait(t_d + lane_base + 32 * h + 16 * part, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m1[part * 16 + i] = __fadd_rn(m1[part * 16 + i], __uint_as_float(rr[i]));
+        }
+        tc_fence_before_sync();
+      }
+      // ================= OUT: BN(eval) + ReLU once per pillar, 128 contiguous bytes per thread =================
+      if (valid) {
+        const float* pa = smem + (kLayers == 2 ? SP.prm_a1 : SP.prm_a0) + 32 * h;
+        const float* pb = smem + (kLayers == 2 ? SP.prm_b1 : SP.prm_b0) + 32 * h;
+        float* dst = A.out + (int64_t)r * kCout + 32 * h;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 al = ld4(pa + i), be = ld4(pb + i);
+          float4 o;
+          o.x = fmaxf(fmaf(m1[i + 0], al.x, be.x), 0.f);
+          o.y = fmaxf(fmaf(m1[i + 1], al.y, be.y), 0.f);
+          o.z = fmaxf(fmaf(m1[i + 2], al.z, be.z), 0.f);
+          o.w = fmaxf(fmaf(m1[i + 3], al.w, be.w), 0.f);
+          *reinterpret_cast<float4*>(dst + i) = o;
         }
       }
     }
-    tc_fence_before_sync();
-    __syncthreads();
-    // ================= P5: per-pillar max, BN(eval) + ReLU -> pillar_features =================
-    {
-      const int nbig = S.nbig;
-      for (int item = tid; item < lb * 16; item += kTcThreads) {
-        const int p = item >> 4, f4 = item & 15;
-        const int qs = off[p] - r0, qe = off[p + 1] - r0;
-        if (qe - qs > kCoop) continue;
-        float4 m = ld4(S.a1h + qs * 64 + ((f4 ^ (qs & 15)) << 2));
-        for (int q = qs + 1; q < qe; ++q) m = max4(m, ld4(S.a1h + q * 64 + ((f4 ^ (q & 15)) << 2)));
-        const float4 al = ld4(S.a1 + f4 * 4), be = ld4(S.b1 + f4 * 4);
-        m.x = fmaxf(fmaf(m.x, al.x, be.x), 0.f); m.y = fmaxf(fmaf(m.y, al.y, be.y), 0.f);
-        m.z = fmaxf(fmaf(m.z, al.z, be.z), 0.f); m.w = fmaxf(fmaf(m.w, al.w, be.w), 0.f);
-        *reinterpret_cast<float4*>(A.out + (int64_t)(cur + p) * 64 + f4 * 4) = m;
-      }
-      for (int t = warp; t < nbig * 16; t += kTcThreads / 32) {
-        const int p = S.big[t >> 4], f4 = t & 15;
-        const int qs = off[p] - r0, qe = off[p + 1] - r0;
-        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        for (int q = qs + lane; q < qe; q += 32) m = max4(m, ld4(S.a1h + q * 64 + ((f4 ^ (q & 15)) << 2)));
-        m = warp_max4(m);
-        if (lane == 0) {
-          const float4 al = ld4(S.a1 + f4 * 4), be = ld4(S.b1 + f4 * 4);
-          m.x = fmaxf(fmaf(m.x, al.x, be.x), 0.f); m.y = fmaxf(fmaf(m.y, al.y, be.y), 0.f);
-          m.z = fmaxf(fmaf(m.z, al.z, be.z), 0.f); m.w = fmaxf(fmaf(m.w, al.w, be.w), 0.f);
-          *reinterpret_cast<float4*>(A.out + (int64_t)(cur + p) * 64 + f4 * 4) = m;
-        }
-      }
-    }
-    cur += lb;
-    buf ^= 1;
-    __syncthreads();
   }
   // ---- teardown ----
   tc_fence_before_sync();
@@ -428,50 +394,26 @@ pfn_tc_kernel(const TcArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// TC parameter panels: w0h | w0l ([k0/4][32][4]) | w1h | w1l ([16][64][4]), round-to-nearest TF32 split
-// ------------------------------------------------------------------------------------------------
-__global__ void pack_tc_params_kernel(int c_in, int k0, const float* __restrict__ w0, const float* __restrict__ w1,
-                                      const float* __restrict__ alpha1, float* __restrict__ out) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  const int n0 = k0 * 32, n1 = 64 * 64;
-  for (int i = tid; i < n0; i += nth) {
-    const int kc = i / (32 * 4), n = (i / 4) % 32, k = kc * 4 + (i & 3);
-    const float w = (k < c_in) ? w0[n * c_in + k] : 0.f;
-    float h, l;
-    split_tf32_rn(w, h, l);
-    out[i] = h; out[n0 + i] = l;
-  }
-  for (int i = tid; i < n1; i += nth) {
-    const int kc = i / (64 * 4), n = (i / 4) % 64, k = kc * 4 + (i & 3);
-    float h, l;
-    // rows whose BN scale is negative are negated (exact) so that BN+ReLU is non-decreasing in the
-    // accumulator for every channel and commutes with the per-pillar max
-    const float sgn = (alpha1[n] < 0.f) ? -1.f : 1.f;
-    split_tf32_rn(sgn * w1[n * 64 + k], h, l);
-    out[2 * n0 + i] = h; out[2 * n0 + n1 + i] = l;
-  }
-  for (int i = tid; i < 64; i += nth) out[2 * n0 + 2 * n1 + i] = fabsf(alpha1[i]);
-}
-
-// ------------------------------------------------------------------------------------------------
-// self test: C[128 x N] = A[128 x K] . B[N x K]^T through the exact operand layout / descriptor / TMEM path
+// self test: C[128 x N] = A[128 x K] . B[N x K]^T through the exact operand layouts / descriptors / TMEM paths
+// mode 0: A and B from shared memory (layer 0);  mode 1: A written to tensor memory with tcgen05.st (layer 1)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads)
-umma_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, int K, int N, float* __restrict__ Cg) {
+umma_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, int K, int N, int mode,
+                     float* __restrict__ Cg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ah = reinterpret_cast<float*>(smem_raw);
-  float* al = ah + 64 * kRows;
-  float* bh = al + 64 * kRows;
+  float* al = ah + 64 * kGroup;
+  float* bh = al + 64 * kGroup;
   float* bl = bh + 64 * 64;
   __shared__ alignas(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kRows * K; i += kTcThreads) {
+  for (int i = tid; i < kGroup * K; i += kTcThreads) {
     const int r = i / K, k = i % K;
     float h, l;
     split_tf32(Ag[i], h, l);
-    ah[(k >> 2) * (kRows * 4) + r * 4 + (k & 3)] = h;
-    al[(k >> 2) * (kRows * 4) + r * 4 + (k & 3)] = l;
+    ah[(k >> 2) * (kGroup * 4) + r * 4 + (k & 3)] = h;
+    al[(k >> 2) * (kGroup * 4) + r * 4 + (k & 3)] = l;
   }
   for (int i = tid; i < N * K; i += kTcThreads) {
     const int n = i / K, k = i % K;
@@ -481,61 +423,101 @@ umma_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg,
     bl[(k >> 2) * (N * 4) + n * 4 + (k & 3)] = l;
   }
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(&tmem_base, 64);
+  if (warp == 0) tmem_alloc(&tmem_base, 128);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  if (mode == 1) {
+    // A (K <= 32) -> tensor memory: hi at columns [64, 64 + K), lo at [96, 96 + K); each half writes 16 columns
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = half * 16 + i;
+      const float v = (k < K) ? Ag[row * K + k] : 0.f;
+      split_tf32(v, hi[i], lo[i]);
+    }
+    tmem_st16(tmem + 64 + lane_base + 16 * half, hi);
+    tmem_st16(tmem + 96 + lane_base + 16 * half, lo);
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+  }
   if (tid == 0) {
-    mma_3xtf32(tmem, smem_u32(ah), smem_u32(al), kRows, smem_u32(bh), smem_u32(bl), (uint32_t)N, K / 8,
-               idesc_tf32_m128((uint32_t)N), false);
+    tc_fence_after_sync();
+    if (mode == 0)
+      mma_3xtf32(tmem, smem_u32(ah), smem_u32(al), kGroup, smem_u32(bh), smem_u32(bl), (uint32_t)N, K / 8,
+                 idesc_tf32_m128((uint32_t)N), false);
+    else
+      mma_3xtf32_ts(tmem, tmem + 64, tmem + 96, smem_u32(bh), smem_u32(bl), (uint32_t)N, K / 8,
+                    idesc_tf32_m128((uint32_t)N), false);
     mma_commit(&bar);
   }
   mbar_wait(&bar, 0);
   tc_fence_after_sync();
-  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   for (int c0 = half * 16; c0 < N; c0 += 32) {
     float v[16];
-    tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+    tmem_ld16(tmem + lane_base + c0, v);
 #pragma unroll
     for (int i = 0; i < 16; ++i) Cg[row * N + c0 + i] = v[i];
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 }  // namespace pcp
 
 using namespace pcp;
 
-extern "C" int pcp_selftest_umma(const float* a, const float* b, int32_t k, int32_t n, float* c, void* stream_) {
+static int selftest(const float* a, const float* b, int32_t k, int32_t n, int mode, float* c, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PCP_REQUIRE(a && b && c, PCP_E_INVALID, "pcp_selftest_umma: null argument");
-  PCP_REQUIRE(k > 0 && k <= 64 && k % 8 == 0 && (n == 32 || n == 64), PCP_E_INVALID, "pcp_selftest_umma: bad k/n");
-  const size_t smem = sizeof(float) * (2 * 64 * kRows + 2 * 64 * 64);
+  PCP_REQUIRE(k > 0 && k <= (mode ? 32 : 64) && k % 8 == 0 && (n == 32 || n == 64), PCP_E_INVALID,
+              "pcp_selftest_umma: bad k/n");
+  const size_t smem = sizeof(float) * (2 * 64 * kGroup + 2 * 64 * 64);
   PCP_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_selftest_kernel<<<1, kTcThreads, smem, stream>>>(a, b, k, n, c);
+  umma_selftest_kernel<<<1, kTcThreads, smem, stream>>>(a, b, k, n, mode, c);
   PCP_LAUNCH_CHECK("umma_selftest_kernel");
   return 0;
 }
 
+extern "C" int pcp_selftest_umma(const float* a, const float* b, int32_t k, int32_t n, float* c, void* stream_) {
+  return selftest(a, b, k, n, 0, c, stream_);
+}
+extern "C" int pcp_selftest_umma_ts(const float* a, const float* b, int32_t k, int32_t n, float* c, void* stream_) {
+  return selftest(a, b, k, n, 1, c, stream_);
+}
+
 // launched from pfn.cu
 namespace pcp {
+
+template <int kLayers, int kCfg>
+static int launch_cfg(const TcArgs& a, int64_t n_points, cudaStream_t stream) {
+  const SmemPlan SP = smem_plan(kCfg ? RowCfg<kCfg>::k0 : a.k0, kLayers);
+  PCP_CUDA(cudaFuncSetAttribute(pfn_slot_kernel<kLayers, kCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP.total_bytes));
+  // upper bound of the group count: every list may end in a partial group
+  const int64_t groups = n_points / kGroup + kNumLists;
+  const unsigned blocks = (unsigned)(groups < 148 * 3 ? groups : 148 * 3);
+  pfn_slot_kernel<kLayers, kCfg><<<blocks, kTcThreads, SP.total_bytes, stream>>>(a);
+  PCP_LAUNCH_CHECK("pfn_slot_kernel");
+  return 0;
+}
+
 int launch_pfn_tc(const TcArgs& a, int64_t n_points, cudaStream_t stream) {
-  const size_t smem = sizeof(TcSmem);
-  PCP_CUDA(cudaFuncSetAttribute(pfn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t groups = (n_points + kWin - 1) / kWin;
-  const unsigned blocks = (unsigned)(groups < 296 ? (groups > 0 ? groups : 1) : 296);
-  pfn_tc_kernel<<<blocks, kTcThreads, smem, stream>>>(a);
-  PCP_LAUNCH_CHECK("pfn_tc_kernel");
-  return 0;
+  const bool abs_nodist = (a.raw_col0 == 1) && !a.with_distance;
+  const uintptr_t base = reinterpret_cast<uintptr_t>(a.points);
+  if (a.num_layers == 2) {
+    if (abs_nodist && a.n_raw == 5 && a.stride % 4 == 0 && a.stride >= 8 && (base & 15) == 0)
+      return launch_cfg<2, 1>(a, n_points, stream);
+    if (abs_nodist && a.n_raw == 11 && a.stride % 2 == 0 && a.stride >= 12 && (base & 7) == 0)
+      return launch_cfg<2, 2>(a, n_points, stream);
+    return launch_cfg<2, 0>(a, n_points, stream);
+  }
+  return launch_cfg<1, 0>(a, n_points, stream);
 }
-int launch_pack_tc(int c_in, int k0, const float* w0, const float* w1, const float* alpha1, float* out,
-                   cudaStream_t stream) {
-  pack_tc_params_kernel<<<8, 256, 0, stream>>>(c_in, k0, w0, w1, alpha1, out);
-  PCP_LAUNCH_CHECK("pack_tc_params_kernel");
-  return 0;
-}
+
 }  // namespace pcp

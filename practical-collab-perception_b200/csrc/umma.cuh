@@ -83,6 +83,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// same with the A operand in TENSOR MEMORY: A[128 x 8] occupies lanes 0..127 x 8 consecutive 32-bit columns at a_tmem
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when they complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -101,6 +110,41 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint3
     mma_tf32(d_tmem, ah, bh, idesc, true);
   }
 }
+
+// 3xTF32 with A (hi at a_hi_tmem, lo at a_lo_tmem, K consecutive columns each) in tensor memory
+__device__ __forceinline__ void mma_3xtf32_ts(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo_tmem, uint32_t b_hi,
+                                              uint32_t b_lo, uint32_t b_rows, int ksteps, uint32_t idesc, bool accumulate) {
+  for (int s = 0; s < ksteps; ++s) {
+    const uint32_t bo = (uint32_t)s * 2u * b_rows * 16u;
+    const uint64_t bh = smem_desc_kmajor(b_hi + bo, b_rows), bl = smem_desc_kmajor(b_lo + bo, b_rows);
+    mma_tf32_ts(d_tmem, a_lo_tmem + 8u * s, bh, idesc, accumulate || s > 0);
+    mma_tf32_ts(d_tmem, a_hi_tmem + 8u * s, bl, idesc, true);
+    mma_tf32_ts(d_tmem, a_hi_tmem + 8u * s, bh, idesc, true);
+  }
+}
+
+// ---- registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns ---------------------
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// tcgen05.ld without the wait (several loads in flight, one wait)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns -----------------------
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {

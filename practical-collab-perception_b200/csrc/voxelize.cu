@@ -8,9 +8,12 @@
 //   2. scan_cells     : ONE pass decoupled look-back scan over the cells produces, for every
 //                       non-empty cell, its pillar rank (ascending key order == torch.unique order),
 //                       the first sorted position of its points, voxel_coords and the counts;
+//                       and bins the pillars by length into the work lists the PFN kernel consumes;
 //   3. place          : counting-sort scatter of the row numbers + the point->pillar map (unq_inv);
-//   4. sort_segments  : row numbers inside each pillar are put in ascending order so that every
-//                       later per-pillar sum runs in the reference CPU path's order (deterministic).
+//   4. sort_*         : row numbers inside each pillar are put in ascending order so that every
+//                       later per-pillar sum runs in the reference CPU path's order (deterministic);
+//                       launched on the dense per-class lists (thread / warp / CTA per pillar);
+//                       long pillars also get their mean and their segment table here.
 // No kernel synchronises with the host; the only data-dependent size (P) is read back by the caller.
 #include "common.cuh"
 
@@ -74,14 +77,16 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t ny,
                   unsigned long long* __restrict__ state, int32_t* __restrict__ hdr,
                   int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
-                  int32_t* __restrict__ pillar_count, int32_t* __restrict__ big_list,
-                  int32_t* __restrict__ long_list, int64_t scan_tiles) {
+                  int32_t* __restrict__ pillar_count, int32_t* __restrict__ lists, const ListOffsets lo,
+                  int4* __restrict__ long_table, int64_t scan_tiles) {
   __shared__ int s_tile;
+  __shared__ int s_cls[kNumClasses], s_cls_base[kNumClasses];
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_red[2][kScanThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&hdr[kHdrScanTicket], 1);
+  if (tid < kNumClasses) s_cls[tid] = 0;
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t base = tile * kScanTileCells + (int64_t)tid * kScanItems;
@@ -173,9 +178,11 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
   }
   __syncthreads();
   unsigned long long excl = s_prefix + warp_excl + (incl - mine);
+  int my_rank[kScanItems], my_slot[kScanItems];   // pillar rank and (class << 16 | slot inside this tile's class batch)
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     const int64_t idx = base + j;
+    my_rank[j] = -1; my_slot[j] = -1;
     if (idx < cells) {
       if (c[j] > 0) {
         const int32_t r = (int32_t)(excl & 0xffffffffull);
@@ -188,12 +195,32 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
         *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4(b, 0, cy, cx);
         if (pillar_count) pillar_count[r] = c[j];
         cell[idx] = r;
-        if (c[j] > kSmallSeg) big_list[atomicAdd(&hdr[kHdrBigCount], 1)] = r;
-        if (c[j] > kLongSeg) long_list[atomicAdd(&hdr[kHdrLongCount], 1)] = r;
+        if (c[j] <= kSegRows) {
+          const int k = class_of(c[j]);
+          my_rank[j] = r;
+          my_slot[j] = (k << 16) | atomicAdd(&s_cls[k], 1);
+        } else {
+          // long pillar: reserve its segments; sort_long_kernel fills the segment table
+          const int nseg = (c[j] + kSegRows - 1) / kSegRows;
+          const int li = atomicAdd(&hdr[kHdrLongCount], 1);
+          const int sb = atomicAdd(&hdr[kHdrListCount + kSegList], nseg);
+          long_table[li] = make_int4(r, off, c[j], sb);
+        }
         excl += ((unsigned long long)(uint32_t)c[j] << 32) | 1ull;
       } else {
         cell[idx] = -1;
       }
+    }
+  }
+  // work lists: one global atomic per (tile, class)
+  __syncthreads();
+  if (tid < kNumClasses) s_cls_base[tid] = s_cls[tid] > 0 ? atomicAdd(&hdr[kHdrListCount + tid], s_cls[tid]) : 0;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    if (my_slot[j] >= 0) {
+      const int k = my_slot[j] >> 16;
+      lists[lo.off[k] + s_cls_base[k] + (my_slot[j] & 0xffff)] = my_rank[j];
     }
   }
 }
@@ -222,34 +249,27 @@ place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within
 }
 
 // ------------------------------------------------------------------------------------------------
-// 4. ascending row order inside every pillar
+// 4. ascending row order inside every pillar, on the dense per-class lists
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cswap(int32_t& a, int32_t& b) {
   const int32_t lo = min(a, b), hi = max(a, b);
   a = lo; b = hi;
 }
 
-// one thread per pillar for n <= 8 (19-comparator network), one warp per pillar for 9..32
+// classes 1..5 (2..8 points): one thread per pillar, 19-comparator network in registers
 __global__ void __launch_bounds__(256)
-sort_small_segments_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
-                           const int32_t* __restrict__ hdr, int32_t* __restrict__ tile_first) {
-  const int32_t P = hdr[PCP_COUNT_PILLARS];
-  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  if ((r - lane) >= P) return;  // whole warp out of range
-  int32_t off = 0, n = 0;
-  if (r < P) {
-    off = seg_off[r];
-    n = seg_off[r + 1] - off;
-    // PFN windows: tile_first[t] = first pillar whose first sorted point lies at or after position t * kWin
-    const int t = off / kWin, t_prev = (r > 0) ? seg_off[r - 1] / kWin : -1;
-    for (int u = t_prev + 1; u <= t; ++u) tile_first[u] = r;
-    if (r == P - 1) {
-      const int n_groups = (hdr[PCP_COUNT_KEPT] + kWin - 1) / kWin;
-      for (int u = t + 1; u <= n_groups; ++u) tile_first[u] = P;
-    }
-  }
-  if (n >= 2 && n <= 8) {
+sort_short_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
+                  const int32_t* __restrict__ lists, const ListOffsets lo, const int32_t* __restrict__ hdr) {
+  int pre[6];
+  pre[0] = 0;
+#pragma unroll
+  for (int k = 1; k <= 5; ++k) pre[k] = pre[k - 1] + hdr[kHdrListCount + k];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < pre[5]; w += gridDim.x * blockDim.x) {
+    int k = 1;
+#pragma unroll
+    for (int q = 1; q < 5; ++q) k += (w >= pre[q]) ? 1 : 0;
+    const int32_t r = __ldg(lists + lo.off[k] + (w - pre[k - 1]));
+    const int32_t off = __ldg(seg_off + r), n = __ldg(seg_off + r + 1) - off;
     int32_t v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
@@ -265,50 +285,108 @@ sort_small_segments_kernel(const int32_t* __restrict__ seg_off, int32_t* __restr
     for (int j = 0; j < 8; ++j)
       if (j < n) sorted_idx[off + j] = v[j];
   }
-  unsigned mid = __ballot_sync(0xffffffffu, n > 8 && n <= kSmallSeg);
-  while (mid) {
-    const int l = __ffs(mid) - 1;
-    mid &= mid - 1;
-    const int32_t o = __shfl_sync(0xffffffffu, off, l);
-    const int32_t m = __shfl_sync(0xffffffffu, n, l);
-    const int32_t v = (lane < m) ? sorted_idx[o + lane] : 0x7fffffff;
+}
+
+// classes 6..9 (9..32 points): one warp per pillar, rank by counting
+__global__ void __launch_bounds__(256)
+sort_mid_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
+                const int32_t* __restrict__ lists, const ListOffsets lo, const int32_t* __restrict__ hdr) {
+  int pre[5];
+  pre[0] = 0;
+#pragma unroll
+  for (int k = 6; k <= 9; ++k) pre[k - 5] = pre[k - 6] + hdr[kHdrListCount + k];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < pre[4]; w += gridDim.x * wpb) {
+    int q = 0;
+#pragma unroll
+    for (int t = 1; t < 4; ++t) q += (w >= pre[t]) ? 1 : 0;
+    const int32_t r = __ldg(lists + lo.off[6 + q] + (w - pre[q]));
+    const int32_t off = __ldg(seg_off + r), n = __ldg(seg_off + r + 1) - off;
+    const int32_t v = (lane < n) ? sorted_idx[off + lane] : 0x7fffffff;
     int rank = 0;
-    for (int i = 0; i < m; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
+    for (int i = 0; i < n; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
     __syncwarp();
-    if (lane < m) sorted_idx[o + rank] = v;
+    if (lane < n) sorted_idx[off + rank] = v;
   }
 }
 
-// one CTA per pillar with more than kSmallSeg points: bitonic sort in shared memory (<= kBigSegMax).
-// Larger pillars keep their arrival order (documented: sums over them stay within tolerance but are
-// not order-canonical).
+// long pillars (> kSegRows points): one CTA per pillar.  Bitonic index sort in shared memory (<= kBigSegMax
+// rows; larger pillars keep their arrival order: their sums stay within tolerance but are not order-canonical),
+// the pillar mean (sequential fp32 sum in ascending row order for <= kBigSegMax rows, dynamic_pillar_vfe.py:110),
+// its segment table entries and its running-max accumulator.
 __global__ void __launch_bounds__(256)
-sort_big_segments_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
-                         const int32_t* __restrict__ big_list, const int32_t* __restrict__ hdr) {
-  __shared__ int32_t s[kBigSegMax];
-  const int nbig = hdr[kHdrBigCount];
-  for (int e = blockIdx.x; e < nbig; e += gridDim.x) {
-    const int32_t r = big_list[e];
-    const int32_t off = seg_off[r], n = seg_off[r + 1] - off;
-    if (n > kBigSegMax) continue;
-    int m = 64;
-    while (m < n) m <<= 1;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
-    __syncthreads();
-    for (int k = 2; k <= m; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
-          const int p = i ^ j;
-          if (p > i) {
-            const int32_t a = s[i], b = s[p];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { s[i] = b; s[p] = a; }
+sort_long_kernel(const float* __restrict__ points, int64_t stride, const int32_t* __restrict__ hdr,
+                 const int4* __restrict__ long_table, int32_t* __restrict__ sorted_idx, int4* __restrict__ seg_table,
+                 float4* __restrict__ long_mean, unsigned* __restrict__ long_acc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s = reinterpret_cast<int32_t*>(smem_raw);                  // [kBigSegMax]
+  float* sx = reinterpret_cast<float*>(smem_raw) + kBigSegMax;         // [3][kBigSegMax]
+  __shared__ float s_red[3][8];
+  const int nlong = hdr[kHdrLongCount];
+  const int tid = threadIdx.x;
+  for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+    const int4 e = long_table[li];
+    const int32_t off = e.y, n = e.z, sb = e.w;
+    const int nseg = (n + kSegRows - 1) / kSegRows;
+    for (int i = tid; i < nseg; i += blockDim.x)
+      seg_table[sb + i] = make_int4(off + i * kSegRows, min(kSegRows, n - i * kSegRows), li, 0);
+    for (int i = tid; i < 96; i += blockDim.x) long_acc[(int64_t)li * 96 + i] = kAccInit;
+    float mx, my, mz;
+    if (n <= kBigSegMax) {
+      int m = 64;
+      while (m < n) m <<= 1;
+      for (int i = tid; i < m; i += blockDim.x) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+      __syncthreads();
+      for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < m; i += blockDim.x) {
+            const int p = i ^ j;
+            if (p > i) {
+              const int32_t a = s[i], b = s[p];
+              const bool up = (i & k) == 0;
+              if ((a > b) == up) { s[i] = b; s[p] = a; }
+            }
           }
+          __syncthreads();
         }
-        __syncthreads();
       }
+      for (int i = tid; i < n; i += blockDim.x) {
+        const int32_t idx = s[i];
+        sorted_idx[off + i] = idx;
+        const float* row = points + (int64_t)idx * stride;
+        sx[i] = __ldg(row + 1); sx[kBigSegMax + i] = __ldg(row + 2); sx[2 * kBigSegMax + i] = __ldg(row + 3);
+      }
+      __syncthreads();
+      if (tid < 3) {
+        const float* v = sx + tid * kBigSegMax;
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, v[i]);
+        s_red[tid][0] = __fdiv_rn(acc, (float)n);
+      }
+      __syncthreads();
+      mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
+    } else {
+      // giant pillar: strided partial sums + tree (deterministic for a given row order)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const float* row = points + (int64_t)sorted_idx[off + i] * stride;
+        a0 += __ldg(row + 1); a1 += __ldg(row + 2); a2 += __ldg(row + 3);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d); a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+      }
+      if ((tid & 31) == 0) { s_red[0][tid >> 5] = a0; s_red[1][tid >> 5] = a1; s_red[2][tid >> 5] = a2; }
+      __syncthreads();
+      if (tid < 3) {
+        float acc = 0.f;
+        for (int w = 0; w < 8; ++w) acc += s_red[tid][w];
+        s_red[tid][0] = __fdiv_rn(acc, (float)n);
+      }
+      __syncthreads();
+      mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted_idx[off + i] = s[i];
+    if (tid == 0) long_mean[li] = make_float4(mx, my, mz, 0.f);
     __syncthreads();
   }
 }
@@ -357,7 +435,7 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   }
   scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
       W.cell, L.cells, grid->nx, grid->ny, W.scan_state, W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
-      W.big_list, W.long_list, L.scan_tiles);
+      W.lists, L.lo, W.long_table, L.scan_tiles);
   PCP_LAUNCH_CHECK("scan_cells_kernel");
   {
     const unsigned blocks = (unsigned)((n_points + 255) / 256);
@@ -366,11 +444,23 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
     PCP_LAUNCH_CHECK("place_kernel");
   }
   if (n_points > 0) {
-    const unsigned blocks = (unsigned)((L.cap + 255) / 256);
-    sort_small_segments_kernel<<<blocks, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.hdr, W.tile_first);
-    PCP_LAUNCH_CHECK("sort_small_segments_kernel");
-    sort_big_segments_kernel<<<296, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.big_list, W.hdr);
-    PCP_LAUNCH_CHECK("sort_big_segments_kernel");
+    const int64_t want = (n_points / 2 + 255) / 256;
+    const unsigned blocks = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
+    sort_short_kernel<<<blocks, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.lists, L.lo, W.hdr);
+    PCP_LAUNCH_CHECK("sort_short_kernel");
+    const int64_t want_mid = (n_points / 9 + 7) / 8;
+    const unsigned blocks_mid = (unsigned)(want_mid < 148 * 8 ? (want_mid > 0 ? want_mid : 1) : 148 * 8);
+    sort_mid_kernel<<<blocks_mid, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.lists, L.lo, W.hdr);
+    PCP_LAUNCH_CHECK("sort_mid_kernel");
+    const int64_t want_long = n_points / (kSegRows + 1);
+    if (want_long > 0) {
+      const size_t smem = sizeof(int32_t) * kBigSegMax * 4;
+      PCP_CUDA(cudaFuncSetAttribute(sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned blocks_long = (unsigned)(want_long < 296 ? want_long : 296);
+      sort_long_kernel<<<blocks_long, 256, smem, stream>>>(points, row_stride, W.hdr, W.long_table, W.sorted_idx,
+                                                           W.seg_table, W.long_mean, W.long_acc);
+      PCP_LAUNCH_CHECK("sort_long_kernel");
+    }
   }
   return 0;
 }

@@ -61,9 +61,9 @@ def test_argument_validation_returns_codes_not_crashes(lib):
     rc = lib.pcp_voxelize(None, 8, 10, 1, C.byref(g), None, 0, None, None, None, 10, None, None)
     assert rc == -1 and b"null" in lib.pcp_last_error_string()
     d = PcpPfnDesc(5, 1, 0, 3, 32, 64)
-    simt = 11 * 32 + 64 + 2 * 32 * 64 + 128
-    assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 2, 32, 64))) == simt + 2 * 16 * 32 + 2 * 64 * 64 + 64   # + tensor-core panels, |alpha1|
-    assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 1, 0, 64))) == 11 * 64 + 128
+    # hi/lo operand panels (K padded to 16) of W0, W1[:, :32], W1[:, 32:] + folded BN + fp32 W1[:, 32:] (long pillars)
+    assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 2, 32, 64))) == 2 * 16 * 32 + 4 * 32 * 64 + 64 + 128 + 64 * 32
+    assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 1, 0, 64))) == 2 * 16 * 64 + 128
     rc = lib.pcp_pack_pfn_params(C.byref(d), *([None] * 12), C.c_float(1e-3), None, None)
     assert rc == -3 and b"num_layers" in lib.pcp_last_error_string()
     assert lib.pcp_modar(None, None, None, None, None, 0, 2.0, 10.0, 0, 0.0, None, 13, None, None) == 0
