@@ -184,6 +184,11 @@ int pcp_selftest_umma(const float* a, const float* b, int32_t k, int32_t n, floa
  * the path layer 1 of pcp_pfn() uses for the activations it reads back from layer 0.  k multiple of 8 up to 32. */
 int pcp_selftest_umma_ts(const float* a, const float* b, int32_t k, int32_t n, float* c, void* stream);
 
+/* Diagnostic micro-benchmark: SM cycles (clock64) of `reps` back-to-back 3xTF32 groups (3 * ksteps tcgen05.mma each,
+ * M = 128, N = n; mode 0: A from shared memory, 1: A from tensor memory), issue -> commit -> mbarrier wait.
+ * out[0] = total cycles, out[1] = cycles of an empty commit + wait, out[2] = cycles spent issuing. */
+int pcp_selftest_umma_cycles(int32_t mode, int32_t n, int32_t ksteps, int32_t reps, long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "pcp_num_frames": (C.c_int, [_P, C.c_int64, _P, _P]),
     "pcp_selftest_umma": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "pcp_selftest_umma_ts": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "pcp_selftest_umma_cycles": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "pcp_modar": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,
                             _P, C.c_int64, _P, _P]),
 }

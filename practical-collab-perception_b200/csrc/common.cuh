@@ -75,7 +75,8 @@ __host__ __device__ inline int class_of(int n) {
 //   within     int32[N]         arrival slot of the row inside its cell
 //   seg_off    int32[cap+1]     first sorted position of each pillar (exclusive scan of counts)
 //   sorted_idx int32[N]         input row numbers grouped by pillar, ascending inside a pillar
-//   lists      int32[...]       per length class: pillar ranks (list k at list_off[k], capacity N / min_len + 1)
+//   lists      uint64[...]      per length class: packed pillar descriptors (list k at list_off[k], capacity
+//                               N / min_len + 1): bits [0,29) pillar rank, [29,58) first sorted position, [58,63) rows - 1
 //   seg_table  int4[N/16+2]     long-pillar segments {first sorted position, rows, long index, 0}
 //   long_table int4[N/33+1]     long pillars {pillar rank, first sorted position, rows, first segment}
 //   long_mean  float4[N/33+1]   mean xyz of each long pillar (sequential fp32 sum in ascending row order)
@@ -89,7 +90,17 @@ constexpr int kHdrLongCount = 48;    // long pillars
 constexpr int kScanTileCells = 2048; // cells per scan tile (256 threads x 8)
 constexpr unsigned kAccInit = 0x007fffffu;   // ordered-int encoding of -inf
 
-struct ListOffsets { int64_t off[kNumLists]; };   // int32 offsets of every list inside `lists`
+struct ListOffsets { int64_t off[kNumLists]; };   // entry offsets of every list inside `lists`
+
+// packed work-list entry: one 8-byte load tells a PFN thread everything about its pillar
+__host__ __device__ inline unsigned long long pack_entry(int r, int off, int len) {
+  return (unsigned long long)(unsigned)r | ((unsigned long long)(unsigned)off << 29) | ((unsigned long long)(len - 1) << 58);
+}
+__host__ __device__ inline void unpack_entry(unsigned long long e, int& r, int& off, int& len) {
+  r = (int)(e & 0x1fffffffull);
+  off = (int)((e >> 29) & 0x1fffffffull);
+  len = (int)((e >> 58) & 31ull) + 1;
+}
 
 struct WsLayout {
   size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, lists, seg_table, long_table, long_mean, long_acc, total;
@@ -125,7 +136,7 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
     lo += (c + 63) / 64 * 64;
   }
   L.lo.off[kSegList] = lo;   // the segment "list" is the identity (entry e = segment e): no storage
-  o = align_up(o + sizeof(int32_t) * (size_t)(lo + 64), 256);
+  o = align_up(o + sizeof(unsigned long long) * (size_t)(lo + 64), 256);
   L.seg_table = o;   o = align_up(o + 16 * (size_t)L.seg_cap, 256);
   L.long_table = o;  o = align_up(o + 16 * (size_t)L.long_cap, 256);
   L.long_mean = o;   o = align_up(o + 16 * (size_t)L.long_cap, 256);
@@ -142,7 +153,7 @@ struct WsView {
   int32_t* within;
   int32_t* seg_off;
   int32_t* sorted_idx;
-  int32_t* lists;
+  unsigned long long* lists;
   int4* seg_table;
   int4* long_table;
   float4* long_mean;
@@ -159,7 +170,7 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.within = reinterpret_cast<int32_t*>(p + L.within);
   v.seg_off = reinterpret_cast<int32_t*>(p + L.seg_off);
   v.sorted_idx = reinterpret_cast<int32_t*>(p + L.sorted_idx);
-  v.lists = reinterpret_cast<int32_t*>(p + L.lists);
+  v.lists = reinterpret_cast<unsigned long long*>(p + L.lists);
   v.seg_table = reinterpret_cast<int4*>(p + L.seg_table);
   v.long_table = reinterpret_cast<int4*>(p + L.long_table);
   v.long_mean = reinterpret_cast<float4*>(p + L.long_mean);

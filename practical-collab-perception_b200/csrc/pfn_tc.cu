@@ -34,22 +34,26 @@ namespace pcp {
 using namespace umma;
 
 constexpr int kTcThreads = 256;
-constexpr int kTmemCols = 128;    // accumulator: columns [0, 64); layer-1 A operand: hi [64, 96), lo [96, 128)
+constexpr int kTmemCols = 256;
+// tensor-memory column map of one CTA
+constexpr uint32_t kColD0 = 0;      // layer-0 accumulator (32 columns; 64 for a single-layer PFN)
+constexpr uint32_t kColD1 = 64;     // layer-1 / hoist accumulator (64 columns)
+constexpr uint32_t kColA0h = 128;   // layer-0 A operand (features), TF32 hi part, k0 <= 24 columns
+constexpr uint32_t kColA0l = 160;   //                               lo part
+constexpr uint32_t kColA1h = 192;   // layer-1 A operand (x0, later max0), hi part, 32 columns
+constexpr uint32_t kColA1l = 224;   //                                     lo part
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
-  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
-}
 
 // kCfg: 0 = any layout (scalar loads, run-time feature map)
 //       1 = car / early-fusion rows: c_raw 5, absolute xyz, no distance, row stride % 4 == 0, 16-byte aligned
 //       2 = ego (lately fusion) rows: c_raw 11, absolute xyz, no distance, even row stride, 8-byte aligned
-template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0; };
-template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16; };
-template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24; };
+template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 1; };
+template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8; };
+template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12; };
 
 struct SmemPlan {   // float offsets into dynamic shared memory
-  int w0h, w0l, w1ah, w1al, w1bh, w1bl, a0h, a0l, prm_a0, prm_b0, prm_a1, prm_b1, mean, ints, total_bytes;
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, mean, idx, ints, total_bytes;
 };
 __host__ __device__ inline SmemPlan smem_plan(int k0, int layers) {
   SmemPlan S{};
@@ -63,8 +67,7 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers) {
     S.w1bh = o; o += kHidden * kCout;
     S.w1bl = o; o += kHidden * kCout;
   }
-  S.a0h = o; o += k0 * kGroup;
-  S.a0l = o; o += k0 * kGroup;
+  S.panels_end = o;
   S.prm_a0 = o; o += n0;
   S.prm_b0 = o; o += n0;
   if (layers == 2) {
@@ -72,37 +75,44 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers) {
     S.prm_b1 = o; o += kCout;
   }
   S.mean = o; o += 3 * kGroup;
-  S.ints = o; o += 32;        // 2 mbarriers (16 B) | tmem base | group prefix [kNumLists + 1]
+  S.idx = o; o += 2 * kSegRows * kGroup;     // row numbers of the current and the next group, [buffer][slot][pillar]
+  S.ints = o; o += 64;                       // 2 mbarriers | tmem base | group prefix | list counts | list offsets
   S.total_bytes = o * 4;
   return S;
 }
 
+struct Work {        // one thread's pillar (or long-pillar segment) of a group
+  int list, slots, r, off, len, li;
+  bool valid, is_seg;
+};
+
 template <int kLayers, int kCfg>
-__global__ void __launch_bounds__(kTcThreads, 3)
+__global__ void __launch_bounds__(kTcThreads, 2)
 pfn_slot_kernel(const TcArgs A) {
   extern __shared__ __align__(128) float smem[];
   constexpr int N0 = (kLayers == 2) ? kHidden : kCout;
+  constexpr int NREG = RowCfg<kCfg>::nreg;
   const int k0 = kCfg ? RowCfg<kCfg>::k0 : A.k0;
   const int n_raw = kCfg ? RowCfg<kCfg>::n_raw : A.n_raw;
   const int raw_col0 = kCfg ? 1 : A.raw_col0;
   const bool with_dist = kCfg ? false : (A.with_distance != 0);
   const SmemPlan SP = smem_plan(k0, kLayers);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int p = tid & (kGroup - 1);      // pillar of the group == TMEM lane
-  const int h = tid >> 7;                // which half of the accumulator columns / which A0 panels
-  float* const a0h = smem + SP.a0h;
-  float* const a0l = smem + SP.a0l;
+  const int h = tid >> 7;                // which half of the accumulator columns; hi (0) or lo (1) part of A0
   float* const s_mean = smem + SP.mean;
+  int* const s_idx = reinterpret_cast<int*>(smem + SP.idx);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + SP.ints);
   uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 4);
-  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 8);     // [kNumLists + 1] group prefix, processing order
+  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 8);       // [kNumLists + 1] group prefix, processing order
+  int* const s_cnt = reinterpret_cast<int*>(smem + SP.ints + 24);      // [kNumLists] entries per list
+  long long* const s_loff = reinterpret_cast<long long*>(smem + SP.ints + 40);   // [kNumLists] list offsets
 
   // ---- one-time setup: parameters -> smem, barriers, TMEM, work prefix ----
   {
-    const int n_par = SP.a0h;                                   // all operand panels are contiguous in both layouts
     const float4* src = reinterpret_cast<const float4*>(A.params);
     float4* dst = reinterpret_cast<float4*>(smem);
-    for (int i = tid; i < n_par / 4; i += kTcThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < SP.panels_end / 4; i += kTcThreads) dst[i] = __ldg(src + i);   // same order in both layouts
     const ParamLayout PL = param_layout(A.c_in, kLayers);
     for (int i = tid; i < N0; i += kTcThreads) {
       smem[SP.prm_a0 + i] = A.params[PL.a0 + i];
@@ -113,13 +123,16 @@ pfn_slot_kernel(const TcArgs A) {
         smem[SP.prm_a1 + i] = A.params[PL.a1 + i];
         smem[SP.prm_b1 + i] = A.params[PL.b1 + i];
       }
-    for (int i = tid; i < 2 * k0 * kGroup; i += kTcThreads) a0h[i] = 0.f;    // a0h and a0l are adjacent
     if (tid == 0) {
       mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init();
       int acc = 0;
       for (int q = 0; q < kNumLists; ++q) {                     // processing order: segments, then classes 9 .. 0
+        const int list = kNumLists - 1 - q;
+        const int cnt = A.hdr[kHdrListCount + list];
         s_pre[q] = acc;
-        acc += (A.hdr[kHdrListCount + (kNumLists - 1 - q)] + kGroup - 1) / kGroup;
+        s_cnt[list] = cnt;
+        s_loff[list] = A.lo.off[list];
+        acc += (cnt + kGroup - 1) / kGroup;
       }
       s_pre[kNumLists] = acc;
     }
@@ -131,49 +144,127 @@ pfn_slot_kernel(const TcArgs A) {
   }
   const uint32_t tmem = *s_tmem;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t t_d = tmem, t_a1h = tmem + 64, t_a1l = tmem + 96;
-  const uint32_t sa0h = smem_u32(a0h), sa0l = smem_u32(a0l);
+  const uint32_t t_d0 = tmem + kColD0, t_d1 = tmem + kColD1;
+  const uint32_t t_a0h = tmem + kColA0h, t_a0l = tmem + kColA0l, t_a1h = tmem + kColA1h, t_a1l = tmem + kColA1l;
   const uint32_t sw0h = smem_u32(smem + SP.w0h), sw0l = smem_u32(smem + SP.w0l);
   const uint32_t sw1ah = smem_u32(smem + SP.w1ah), sw1al = smem_u32(smem + SP.w1al);
   const uint32_t sw1bh = smem_u32(smem + SP.w1bh), sw1bl = smem_u32(smem + SP.w1bl);
   const uint32_t idesc0 = idesc_tf32_m128(N0), idesc1 = idesc_tf32_m128(kCout);
   uint32_t ph0 = 0, ph1 = 0;
-  const int total_groups = s_pre[kNumLists];
-  const int np4 = k0 >> 2;
+  const int total = s_pre[kNumLists];
+  const int G = gridDim.x;
 
-  for (int w = blockIdx.x; w < total_groups; w += gridDim.x) {
-    // ---- which list / group ----
+  // raw 16-byte descriptor of this thread's pillar in group w (loads only; decoded later so they stay in flight)
+  auto fetch = [&](int w, int& list, int4& raw) {
     int q = 0;
 #pragma unroll
     for (int t = 1; t < kNumLists; ++t) q += (w >= s_pre[t]) ? 1 : 0;
-    const int list = kNumLists - 1 - q;
-    const bool is_seg = (list == kSegList);
-    const int slots = is_seg ? kSegRows : class_slots(list);
+    list = kNumLists - 1 - q;
     const int e = (w - s_pre[q]) * kGroup + p;
-    const bool valid = e < A.hdr[kHdrListCount + list];
-    int r = -1, off = 0, len = 0, li = -1;
-    if (valid) {
-      if (is_seg) {
-        const int4 sg = __ldg(A.seg_table + e);
-        off = sg.x; len = sg.y; li = sg.z;
+    raw = make_int4(0, 0, 0, -1);
+    if (e < s_cnt[list]) {
+      if (list == kSegList) {
+        raw = __ldg(A.seg_table + e);
+        raw.w = 1;
       } else {
-        r = __ldg(A.lists + A.lo.off[list] + e);
-        off = __ldg(A.seg_off + r);
-        len = __ldg(A.seg_off + r + 1) - off;
+        const unsigned long long v = __ldg(A.lists + s_loff[list] + e);
+        raw.x = (int)(v & 0xffffffffull); raw.y = (int)(v >> 32); raw.w = 0;
       }
     }
+  };
+  auto decode = [&](int list, const int4& raw, Work& W) {
+    W.list = list;
+    W.is_seg = (list == kSegList);
+    W.slots = W.is_seg ? kSegRows : class_slots(list);
+    W.valid = raw.w >= 0;
+    W.r = -1; W.off = 0; W.len = 0; W.li = -1;
+    if (W.valid) {
+      if (W.is_seg) { W.off = raw.x; W.len = raw.y; W.li = raw.z; }
+      else unpack_entry(((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x, W.r, W.off, W.len);
+    }
+  };
+  // row numbers of every slot of a group -> s_idx[b] (cp.async: no registers, lands while the previous group computes)
+  auto issue_idx = [&](const Work& W, int b) {
+    if (h == 0 && W.valid) {
+      int* dst = s_idx + b * (kSegRows * kGroup) + p;
+      for (int j = 0; j < W.slots; ++j) cp_async4(dst + j * kGroup, A.sorted_idx + W.off + min(j, W.len - 1));
+    }
+  };
+
+  Work cur, nxt;
+  {
+    int list; int4 raw;
+    cur.valid = false; cur.slots = 0; cur.is_seg = false; cur.list = 0; cur.r = -1; cur.off = 0; cur.len = 0; cur.li = -1;
+    nxt = cur;
+    if ((int)blockIdx.x < total) { fetch(blockIdx.x, list, raw); decode(list, raw, cur); }
+    issue_idx(cur, 0);
+    cp_async_commit();
+    if ((int)blockIdx.x + G < total) { fetch(blockIdx.x + G, list, raw); decode(list, raw, nxt); }
+  }
+  int buf = 0;
+  bool pending = false, pend_valid = false;   // a finished group whose hoist MMA is in flight / whose output is not yet written
+  int pend_r = -1;
+  float max0[16];            // layer-0 running max, this thread's 16 channels (two layers only)
+  float m1[32];              // last-layer running max of the raw accumulators, this thread's 32 channels
+
+  // ================= OUT of a finished group: h = max0 . W1[:, 32:]^T landed in D1; BN(eval) + ReLU once per pillar =====
+  auto finish_pending = [&]() {
+    if (kLayers == 2) {
+      mbar_wait(&bars[1], ph1);
+      ph1 ^= 1;
+      tc_fence_after_sync();
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint32_t rr[16];
+        tmem_ld16_nowait(t_d1 + lane_base + 32 * h + 16 * part, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m1[part * 16 + i] = __fadd_rn(m1[part * 16 + i], __uint_as_float(rr[i]));
+      }
+      tc_fence_before_sync();
+    }
+    if (pend_valid) {
+      const float* pa = smem + (kLayers == 2 ? SP.prm_a1 : SP.prm_a0) + 32 * h;
+      const float* pb = smem + (kLayers == 2 ? SP.prm_b1 : SP.prm_b0) + 32 * h;
+      float* dst = A.out + (int64_t)pend_r * kCout + 32 * h;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 al = ld4(pa + i), be = ld4(pb + i);
+        float4 o;
+        o.x = fmaxf(fmaf(m1[i + 0], al.x, be.x), 0.f);
+        o.y = fmaxf(fmaf(m1[i + 1], al.y, be.y), 0.f);
+        o.z = fmaxf(fmaf(m1[i + 2], al.z, be.z), 0.f);
+        o.w = fmaxf(fmaf(m1[i + 3], al.w, be.w), 0.f);
+        *reinterpret_cast<float4*>(dst + i) = o;
+      }
+    }
+    pending = false;
+  };
+
+  for (int w = blockIdx.x; w < total; w += G) {
+    // ---- prefetch: row numbers of the next group, descriptor of the one after ----
+    if (w + G < total) issue_idx(nxt, buf ^ 1);
+    cp_async_commit();
+    int nn_list = 0; int4 nn_raw = make_int4(0, 0, 0, -1);
+    const bool have_nn = (w + 2 * G) < total;
+    if (have_nn) fetch(w + 2 * G, nn_list, nn_raw);
+    cp_async_wait<1>();                                   // this thread's copies of the current group have landed
+    const int* my_idx = s_idx + buf * (kSegRows * kGroup) + p;
+    const bool valid = cur.valid;
+    const int slots = cur.slots, len = cur.len;
+
     // ---- pillar mean: scatter_mean = sum in ascending row order / count (dynamic_pillar_vfe.py:110) ----
     if (h == 0) {
       float mx = 0.f, my = 0.f, mz = 0.f;
       if (valid) {
-        if (is_seg) {
-          const float4 m = __ldg(A.long_mean + li);
+        if (cur.is_seg) {
+          const float4 m = __ldg(A.long_mean + cur.li);
           mx = m.x; my = m.y; mz = m.z;
         } else {
           float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll 4
           for (int j = 0; j < len; ++j) {
-            const float* row = A.points + (int64_t)__ldg(A.sorted_idx + off + j) * A.stride;
+            const float* row = A.points + (int64_t)my_idx[j * kGroup] * A.stride;
             float x, y, z;
             if (kCfg == 1) {
               const float4 v = __ldg(reinterpret_cast<const float4*>(row));
@@ -186,96 +277,115 @@ pfn_slot_kernel(const TcArgs A) {
           const float cnt = (float)len;
           mx = __fdiv_rn(sx, cnt); my = __fdiv_rn(sy, cnt); mz = __fdiv_rn(sz, cnt);
           if (A.mean_out) {
-            float* m = A.mean_out + (int64_t)r * 3;
+            float* m = A.mean_out + (int64_t)cur.r * 3;
             m[0] = mx; m[1] = my; m[2] = mz;
           }
         }
       }
       s_mean[p] = mx; s_mean[kGroup + p] = my; s_mean[2 * kGroup + p] = mz;
     }
-    __syncthreads();
+    __syncthreads();                                      // means and row numbers visible to both halves
     const float mean_x = s_mean[p], mean_y = s_mean[kGroup + p], mean_z = s_mean[2 * kGroup + p];
 
-    float max0[16];            // layer-0 running max, this thread's 16 channels (two layers only)
-    float m1[32];              // last-layer running max of the raw accumulators, this thread's 32 channels
+    // the previous group's hoist MMA ran while the loads above were in flight
+    if (pending) finish_pending();
+
 #pragma unroll
     for (int i = 0; i < 16; ++i) max0[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
 
-    for (int j = 0; j < slots; ++j) {
-      // ================= A0: this slot's rows -> features -> TF32 hi/lo panels =================
-      {
-        const int jj = min(j, len - 1);
-        const bool have = valid;                       // slots past the pillar's length repeat its last point
-        const float* row = A.points;
-        if (have) row += (int64_t)__ldg(A.sorted_idx + off + jj) * A.stride;
-        float rv[12];
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (have) {
-          if (kCfg == 1) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(row));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(row) + 1);
-            rv[0] = v0.x; rv[1] = v0.y; rv[2] = v0.z; rv[3] = v0.w; rv[4] = v1.x; rv[5] = v1.y; rv[6] = v1.z; rv[7] = v1.w;
-            x = rv[1]; y = rv[2]; z = rv[3];
-          } else if (kCfg == 2) {
+    // ---- row fetch (registers; issued one slot ahead) and A0 = TF32 hi / lo features -> tensor memory ----
+    float rw[NREG];
+    const float* rowp = A.points;
+    auto load_row = [&](int j) {
+      if (!valid) return;
+      rowp = A.points + (int64_t)my_idx[j * kGroup] * A.stride;
+      if (kCfg == 1) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(rowp));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(rowp) + 1);
+        rw[0] = v0.x; rw[1] = v0.y; rw[2] = v0.z; rw[3] = v0.w; rw[4] = v1.x; rw[5] = v1.y; rw[6] = v1.z; rw[7] = v1.w;
+      } else if (kCfg == 2) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-              const float2 v = __ldg(reinterpret_cast<const float2*>(row) + c);
-              rv[2 * c] = v.x; rv[2 * c + 1] = v.y;
-            }
-            x = rv[1]; y = rv[2]; z = rv[3];
-          } else {
-            x = __ldg(row + 1); y = __ldg(row + 2); z = __ldg(row + 3);
+        for (int c = 0; c < 6; ++c) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(rowp) + c);
+          rw[2 * c] = v.x; rw[2 * c + 1] = v.y;
+        }
+      }
+    };
+    auto build_a0 = [&]() {
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (valid) {
+        if (kCfg) { x = rw[1]; y = rw[2]; z = rw[3]; }
+        else { x = __ldg(rowp + 1); y = __ldg(rowp + 2); z = __ldg(rowp + 3); }
+      }
+      float ed[7];
+      ed[0] = __fsub_rn(x, mean_x);                                              // f_cluster (:111)
+      ed[1] = __fsub_rn(y, mean_y);
+      ed[2] = __fsub_rn(z, mean_z);
+      const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
+      const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
+      ed[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
+      ed[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
+      ed[5] = __fsub_rn(z, A.g.z_offset);
+      ed[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
+      const int n_feat = n_raw + (with_dist ? 7 : 6);
+      float v[kMaxCin];
+#pragma unroll
+      for (int f = 0; f < kMaxCin; ++f) {
+        float val = 0.f;
+        if (f < k0 && valid) {
+          if (f < n_raw) {
+            if (kCfg) val = rw[(1 + f) < NREG ? (1 + f) : (NREG - 1)];
+            else val = __ldg(rowp + raw_col0 + f);
+          } else if (f < n_feat) {
+            const int d = f - n_raw;
+            val = d == 0 ? ed[0] : d == 1 ? ed[1] : d == 2 ? ed[2] : d == 3 ? ed[3] : d == 4 ? ed[4] : d == 5 ? ed[5] : ed[6];
           }
         }
-        float ed[7];
-        ed[0] = __fsub_rn(x, mean_x);                                              // f_cluster (:111)
-        ed[1] = __fsub_rn(y, mean_y);
-        ed[2] = __fsub_rn(z, mean_z);
-        const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
-        const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
-        ed[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
-        ed[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
-        ed[5] = __fsub_rn(z, A.g.z_offset);
-        ed[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
-        const int n_feat = n_raw + (with_dist ? 7 : 6);
-        auto feature = [&](int f) -> float {
-          if (f < n_raw) {
-            if (kCfg) return rv[(raw_col0 + f) < 12 ? (raw_col0 + f) : 11];
-            return __ldg(row + raw_col0 + f);
-          }
-          const int d = f - n_raw;
-          if (f >= n_feat) return 0.f;
-          return d == 0 ? ed[0] : d == 1 ? ed[1] : d == 2 ? ed[2] : d == 3 ? ed[3] : d == 4 ? ed[4] : d == 5 ? ed[5] : ed[6];
-        };
-        auto build = [&](auto hc) {
-          constexpr int H = decltype(hc)::value;
-#pragma unroll
-          for (int kc = H; kc < kMaxCin / 4; kc += 2) {
-            if (kc < np4) {
-              float v[4], hi[4], lo[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                v[t] = have ? feature(kc * 4 + t) : 0.f;
-                split_tf32(v[t], hi[t], lo[t]);
-              }
-              st4(a0h + kc * (kGroup * 4) + p * 4, hi[0], hi[1], hi[2], hi[3]);
-              st4(a0l + kc * (kGroup * 4) + p * 4, lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-        };
-        if (h == 0) build(std::integral_constant<int, 0>{}); else build(std::integral_constant<int, 1>{});
+        float hi, lo;
+        split_tf32(val, hi, lo);
+        v[f] = h ? lo : hi;                                 // the two threads of a pillar write the hi and the lo operand
       }
-      fence_proxy_async_smem();
+      const uint32_t dst = (h ? t_a0l : t_a0h) + lane_base;
+      if (k0 >= 16) {
+        float c16[16];
+#pragma unroll
+        for (int f = 0; f < 16; ++f) c16[f] = v[f];
+        tmem_st16(dst, c16);
+        if (k0 > 16) {
+          float c8[8];
+#pragma unroll
+          for (int f = 0; f < 8; ++f) c8[f] = v[16 + f];
+          tmem_st8(dst + 16, c8);
+        }
+      } else {
+        float c8[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) c8[f] = v[f];
+        tmem_st8(dst, c8);
+      }
+      tmem_st_wait();
       tc_fence_before_sync();
-      __syncthreads();
-      // ================= M0 =================
-      if (tid == 0) {
-        tc_fence_after_sync();
-        mma_3xtf32(t_d, sa0h, sa0l, kGroup, sw0h, sw0l, N0, k0 / 8, idesc0, false);
-        mma_commit(&bars[0]);
+    };
+    auto issue_m0 = [&]() {
+      if (warp == 0) {
+        if (elect_one_sync()) {
+          tc_fence_after_sync();
+          mma_3xtf32_ts(t_d0, t_a0h, t_a0l, sw0h, sw0l, N0, k0 / 8, idesc0, false);
+          mma_commit(&bars[0]);
+        }
+        __syncwarp();
       }
+    };
+
+    load_row(0);
+    build_a0();
+    __syncthreads();
+    issue_m0();
+    if (slots > 1) load_row(1);
+
+    for (int j = 0; j < slots; ++j) {
       mbar_wait(&bars[0], ph0);
       ph0 ^= 1;
       tc_fence_after_sync();
@@ -283,7 +393,7 @@ pfn_slot_kernel(const TcArgs A) {
         // ================= E0: BN+ReLU, running max0, x0 -> TMEM as the A operand of layer 1 =================
         {
           uint32_t rr[16];
-          tmem_ld16_nowait(t_d + lane_base + 16 * h, rr);
+          tmem_ld16_nowait(t_d0 + lane_base + 16 * h, rr);
           tmem_ld_wait();
           float hi[16], lo[16];
           const float* pa = smem + SP.prm_a0 + 16 * h;
@@ -294,9 +404,9 @@ pfn_slot_kernel(const TcArgs A) {
             const float a4[4] = {al.x, al.y, al.z, al.w}, b4[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const float v = fmaxf(fmaf(__uint_as_float(rr[i + t]), a4[t], b4[t]), 0.f);
-              max0[i + t] = fmaxf(max0[i + t], v);
-              split_tf32(v, hi[i + t], lo[i + t]);
+              const float xv = fmaxf(fmaf(__uint_as_float(rr[i + t]), a4[t], b4[t]), 0.f);
+              max0[i + t] = fmaxf(max0[i + t], xv);
+              split_tf32(xv, hi[i + t], lo[i + t]);
             }
           }
           tmem_st16(t_a1h + lane_base + 16 * h, hi);
@@ -306,10 +416,20 @@ pfn_slot_kernel(const TcArgs A) {
         tc_fence_before_sync();
         __syncthreads();
         // ================= M1 =================
-        if (tid == 0) {
-          tc_fence_after_sync();
-          mma_3xtf32_ts(t_d, t_a1h, t_a1l, sw1ah, sw1al, kCout, kHidden / 8, idesc1, false);
-          mma_commit(&bars[1]);
+        if (warp == 0) {
+          if (elect_one_sync()) {
+            tc_fence_after_sync();
+            mma_3xtf32_ts(t_d1, t_a1h, t_a1l, sw1ah, sw1al, kCout, kHidden / 8, idesc1, false);
+            mma_commit(&bars[1]);
+          }
+          __syncwarp();
+        }
+        // ================= next slot's A0 and M0 go in behind M1 =================
+        if (j + 1 < slots) {
+          build_a0();
+          __syncthreads();
+          issue_m0();
+          if (j + 2 < slots) load_row(j + 2);
         }
         mbar_wait(&bars[1], ph1);
         ph1 ^= 1;
@@ -319,18 +439,24 @@ pfn_slot_kernel(const TcArgs A) {
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
         uint32_t rr[16];
-        tmem_ld16_nowait(t_d + lane_base + 32 * h + 16 * part, rr);
+        tmem_ld16_nowait((kLayers == 2 ? t_d1 : t_d0) + lane_base + 32 * h + 16 * part, rr);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) m1[part * 16 + i] = fmaxf(m1[part * 16 + i], __uint_as_float(rr[i]));
       }
       tc_fence_before_sync();
+      if (kLayers == 1 && j + 1 < slots) {
+        build_a0();
+        __syncthreads();
+        issue_m0();
+        if (j + 2 < slots) load_row(j + 2);
+      }
     }
 
-    if (is_seg) {
+    if (cur.is_seg) {
       // ---- long pillar segment: partial maxima -> the pillar's accumulator ----
       if (valid) {
-        unsigned* acc = A.long_acc + (int64_t)li * 96;
+        unsigned* acc = A.long_acc + (int64_t)cur.li * 96;
         if (kLayers == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) atomicMax(acc + 16 * h + i, ord_enc(max0[i]));
@@ -340,7 +466,7 @@ pfn_slot_kernel(const TcArgs A) {
       }
     } else {
       if (kLayers == 2) {
-        // ================= H: max0 . W1[:, 32:]^T once per pillar =================
+        // ================= H: max0 . W1[:, 32:]^T once per pillar; its result is collected by finish_pending() ======
         {
           float hi[16], lo[16];
 #pragma unroll
@@ -351,42 +477,24 @@ pfn_slot_kernel(const TcArgs A) {
         }
         tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
-          tc_fence_after_sync();
-          mma_3xtf32_ts(t_d, t_a1h, t_a1l, sw1bh, sw1bl, kCout, kHidden / 8, idesc1, false);
-          mma_commit(&bars[1]);
-        }
-        mbar_wait(&bars[1], ph1);
-        ph1 ^= 1;
-        tc_fence_after_sync();
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          uint32_t rr[16];
-          tmem_ld16_nowait(t_d + lane_base + 32 * h + 16 * part, rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) m1[part * 16 + i] = __fadd_rn(m1[part * 16 + i], __uint_as_float(rr[i]));
-        }
-        tc_fence_before_sync();
-      }
-      // ================= OUT: BN(eval) + ReLU once per pillar, 128 contiguous bytes per thread =================
-      if (valid) {
-        const float* pa = smem + (kLayers == 2 ? SP.prm_a1 : SP.prm_a0) + 32 * h;
-        const float* pb = smem + (kLayers == 2 ? SP.prm_b1 : SP.prm_b0) + 32 * h;
-        float* dst = A.out + (int64_t)r * kCout + 32 * h;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 al = ld4(pa + i), be = ld4(pb + i);
-          float4 o;
-          o.x = fmaxf(fmaf(m1[i + 0], al.x, be.x), 0.f);
-          o.y = fmaxf(fmaf(m1[i + 1], al.y, be.y), 0.f);
-          o.z = fmaxf(fmaf(m1[i + 2], al.z, be.z), 0.f);
-          o.w = fmaxf(fmaf(m1[i + 3], al.w, be.w), 0.f);
-          *reinterpret_cast<float4*>(dst + i) = o;
+        if (warp == 0) {
+          if (elect_one_sync()) {
+            tc_fence_after_sync();
+            mma_3xtf32_ts(t_d1, t_a1h, t_a1l, sw1bh, sw1bl, kCout, kHidden / 8, idesc1, false);
+            mma_commit(&bars[1]);
+          }
+          __syncwarp();
         }
       }
+      pending = true; pend_valid = valid; pend_r = cur.r;
+      if (kLayers == 1) finish_pending();
     }
+    // ---- rotate the prefetch pipeline ----
+    cur = nxt;
+    if (have_nn) decode(nn_list, nn_raw, nxt);
+    buf ^= 1;
   }
+  if (pending) finish_pending();
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
@@ -446,15 +554,18 @@ umma_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg,
     tc_fence_before_sync();
     __syncthreads();
   }
-  if (tid == 0) {
-    tc_fence_after_sync();
-    if (mode == 0)
-      mma_3xtf32(tmem, smem_u32(ah), smem_u32(al), kGroup, smem_u32(bh), smem_u32(bl), (uint32_t)N, K / 8,
-                 idesc_tf32_m128((uint32_t)N), false);
-    else
-      mma_3xtf32_ts(tmem, tmem + 64, tmem + 96, smem_u32(bh), smem_u32(bl), (uint32_t)N, K / 8,
-                    idesc_tf32_m128((uint32_t)N), false);
-    mma_commit(&bar);
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      tc_fence_after_sync();
+      if (mode == 0)
+        mma_3xtf32(tmem, smem_u32(ah), smem_u32(al), kGroup, smem_u32(bh), smem_u32(bl), (uint32_t)N, K / 8,
+                   idesc_tf32_m128((uint32_t)N), false);
+      else
+        mma_3xtf32_ts(tmem, tmem + 64, tmem + 96, smem_u32(bh), smem_u32(bl), (uint32_t)N, K / 8,
+                      idesc_tf32_m128((uint32_t)N), false);
+      mma_commit(&bar);
+    }
+    __syncwarp();
   }
   mbar_wait(&bar, 0);
   tc_fence_after_sync();
@@ -463,6 +574,60 @@ umma_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg,
     tmem_ld16(tmem + lane_base + c0, v);
 #pragma unroll
     for (int i = 0; i < 16; ++i) Cg[row * N + c0 + i] = v[i];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// micro-benchmark (diagnostic): cycles of `reps` back-to-back 3xTF32 groups of `ksteps` K steps (3 MMAs each),
+// issue -> commit -> mbarrier wait, measured with clock64 by the issuing thread.  Operands are whatever is in
+// shared / tensor memory (timing only).  out[0] = cycles, out[1] = cycles of an empty commit + wait.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+umma_cycles_kernel(int mode, int n, int ksteps, int reps, long long* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ah = reinterpret_cast<float*>(smem_raw);
+  float* al = ah + 64 * kGroup;
+  float* bh = al + 64 * kGroup;
+  float* bl = bh + 64 * 64;
+  __shared__ alignas(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 2 * 64 * kGroup + 2 * 64 * 64; i += 128) ah[i] = 0.f;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base, 128);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  if (warp == 0 && elect_one_sync()) {
+    uint32_t phase = 0;
+    const uint32_t idesc = idesc_tf32_m128((uint32_t)n);
+    // warm-up
+    mma_3xtf32(tmem, smem_u32(ah), smem_u32(al), kGroup, smem_u32(bh), smem_u32(bl), (uint32_t)n, 1, idesc, false);
+    mma_commit(&bar);
+    mbar_wait(&bar, phase); phase ^= 1;
+    long long t0 = clock64();
+    mma_commit(&bar);
+    mbar_wait(&bar, phase); phase ^= 1;
+    long long t1 = clock64();
+    out[1] = t1 - t0;
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (mode == 0)
+        mma_3xtf32(tmem, smem_u32(ah), smem_u32(al), kGroup, smem_u32(bh), smem_u32(bl), (uint32_t)n, ksteps, idesc, false);
+      else
+        mma_3xtf32_ts(tmem, tmem + 64, tmem + 96, smem_u32(bh), smem_u32(bl), (uint32_t)n, ksteps, idesc, false);
+    }
+    long long t_issue = clock64();
+    mma_commit(&bar);
+    mbar_wait(&bar, phase); phase ^= 1;
+    t1 = clock64();
+    out[0] = t1 - t0;
+    out[2] = t_issue - t0;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -492,6 +657,17 @@ extern "C" int pcp_selftest_umma_ts(const float* a, const float* b, int32_t k, i
   return selftest(a, b, k, n, 1, c, stream_);
 }
 
+extern "C" int pcp_selftest_umma_cycles(int32_t mode, int32_t n, int32_t ksteps, int32_t reps, long long* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(out && (n == 32 || n == 64) && ksteps >= 1 && ksteps <= (mode ? 4 : 8) && reps >= 0, PCP_E_INVALID,
+              "pcp_selftest_umma_cycles: bad argument");
+  const size_t smem = sizeof(float) * (2 * 64 * kGroup + 2 * 64 * 64);
+  PCP_CUDA(cudaFuncSetAttribute(umma_cycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_cycles_kernel<<<1, 128, smem, stream>>>(mode, n, ksteps, reps, out);
+  PCP_LAUNCH_CHECK("umma_cycles_kernel");
+  return 0;
+}
+
 // launched from pfn.cu
 namespace pcp {
 
@@ -501,7 +677,7 @@ static int launch_cfg(const TcArgs& a, int64_t n_points, cudaStream_t stream) {
   PCP_CUDA(cudaFuncSetAttribute(pfn_slot_kernel<kLayers, kCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP.total_bytes));
   // upper bound of the group count: every list may end in a partial group
   const int64_t groups = n_points / kGroup + kNumLists;
-  const unsigned blocks = (unsigned)(groups < 148 * 3 ? groups : 148 * 3);
+  const unsigned blocks = (unsigned)(groups < 148 * 2 ? groups : 148 * 2);
   pfn_slot_kernel<kLayers, kCfg><<<blocks, kTcThreads, SP.total_bytes, stream>>>(a);
   PCP_LAUNCH_CHECK("pfn_slot_kernel");
   return 0;

@@ -56,7 +56,7 @@ struct TcArgs {
   const int32_t* hdr;
   const int32_t* seg_off;
   const int32_t* sorted_idx;
-  const int32_t* lists;
+  const unsigned long long* lists;
   ListOffsets lo;
   const int4* seg_table;
   const float4* long_mean;

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t ny,
                   unsigned long long* __restrict__ state, int32_t* __restrict__ hdr,
                   int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
-                  int32_t* __restrict__ pillar_count, int32_t* __restrict__ lists, const ListOffsets lo,
+                  int32_t* __restrict__ pillar_count, unsigned long long* __restrict__ lists, const ListOffsets lo,
                   int4* __restrict__ long_table, int64_t scan_tiles) {
   __shared__ int s_tile;
   __shared__ int s_cls[kNumClasses], s_cls_base[kNumClasses];
@@ -178,11 +178,12 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
   }
   __syncthreads();
   unsigned long long excl = s_prefix + warp_excl + (incl - mine);
-  int my_rank[kScanItems], my_slot[kScanItems];   // pillar rank and (class << 16 | slot inside this tile's class batch)
+  unsigned long long my_ent[kScanItems];          // packed list entry
+  int my_slot[kScanItems];                        // class << 16 | slot inside this tile's class batch
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     const int64_t idx = base + j;
-    my_rank[j] = -1; my_slot[j] = -1;
+    my_ent[j] = 0ull; my_slot[j] = -1;
     if (idx < cells) {
       if (c[j] > 0) {
         const int32_t r = (int32_t)(excl & 0xffffffffull);
@@ -197,7 +198,7 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
         cell[idx] = r;
         if (c[j] <= kSegRows) {
           const int k = class_of(c[j]);
-          my_rank[j] = r;
+          my_ent[j] = pack_entry(r, off, c[j]);
           my_slot[j] = (k << 16) | atomicAdd(&s_cls[k], 1);
         } else {
           // long pillar: reserve its segments; sort_long_kernel fills the segment table
@@ -220,7 +221,7 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
   for (int j = 0; j < kScanItems; ++j) {
     if (my_slot[j] >= 0) {
       const int k = my_slot[j] >> 16;
-      lists[lo.off[k] + s_cls_base[k] + (my_slot[j] & 0xffff)] = my_rank[j];
+      lists[lo.off[k] + s_cls_base[k] + (my_slot[j] & 0xffff)] = my_ent[j];
     }
   }
 }
@@ -258,8 +259,8 @@ __device__ __forceinline__ void cswap(int32_t& a, int32_t& b) {
 
 // classes 1..5 (2..8 points): one thread per pillar, 19-comparator network in registers
 __global__ void __launch_bounds__(256)
-sort_short_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
-                  const int32_t* __restrict__ lists, const ListOffsets lo, const int32_t* __restrict__ hdr) {
+sort_short_kernel(int32_t* __restrict__ sorted_idx, const unsigned long long* __restrict__ lists, const ListOffsets lo,
+                  const int32_t* __restrict__ hdr) {
   int pre[6];
   pre[0] = 0;
 #pragma unroll
@@ -268,8 +269,8 @@ sort_short_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sor
     int k = 1;
 #pragma unroll
     for (int q = 1; q < 5; ++q) k += (w >= pre[q]) ? 1 : 0;
-    const int32_t r = __ldg(lists + lo.off[k] + (w - pre[k - 1]));
-    const int32_t off = __ldg(seg_off + r), n = __ldg(seg_off + r + 1) - off;
+    int r, off, n;
+    unpack_entry(__ldg(lists + lo.off[k] + (w - pre[k - 1])), r, off, n);
     int32_t v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
@@ -289,8 +290,8 @@ sort_short_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sor
 
 // classes 6..9 (9..32 points): one warp per pillar, rank by counting
 __global__ void __launch_bounds__(256)
-sort_mid_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorted_idx,
-                const int32_t* __restrict__ lists, const ListOffsets lo, const int32_t* __restrict__ hdr) {
+sort_mid_kernel(int32_t* __restrict__ sorted_idx, const unsigned long long* __restrict__ lists, const ListOffsets lo,
+                const int32_t* __restrict__ hdr) {
   int pre[5];
   pre[0] = 0;
 #pragma unroll
@@ -300,8 +301,8 @@ sort_mid_kernel(const int32_t* __restrict__ seg_off, int32_t* __restrict__ sorte
     int q = 0;
 #pragma unroll
     for (int t = 1; t < 4; ++t) q += (w >= pre[t]) ? 1 : 0;
-    const int32_t r = __ldg(lists + lo.off[6 + q] + (w - pre[q]));
-    const int32_t off = __ldg(seg_off + r), n = __ldg(seg_off + r + 1) - off;
+    int r, off, n;
+    unpack_entry(__ldg(lists + lo.off[6 + q] + (w - pre[q])), r, off, n);
     const int32_t v = (lane < n) ? sorted_idx[off + lane] : 0x7fffffff;
     int rank = 0;
     for (int i = 0; i < n; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
@@ -406,7 +407,7 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
                             int64_t pillar_capacity, int32_t* counts_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PCP_REQUIRE(grid && workspace && voxel_coords_out && counts_out, PCP_E_INVALID, "pcp_voxelize: null argument");
-  PCP_REQUIRE(n_points >= 0 && n_points < (1ll << 30), PCP_E_INVALID, "pcp_voxelize: n_points out of range");
+  PCP_REQUIRE(n_points >= 0 && n_points < (1ll << 29), PCP_E_INVALID, "pcp_voxelize: n_points out of range (< 2^29)");
   PCP_REQUIRE(n_points == 0 || points, PCP_E_INVALID, "pcp_voxelize: null points");
   PCP_REQUIRE(row_stride >= 3, PCP_E_INVALID, "pcp_voxelize: row_stride < 3");
   PCP_REQUIRE(max_frames > 0 && grid->nx > 0 && grid->ny > 0, PCP_E_INVALID, "pcp_voxelize: bad grid");
@@ -446,11 +447,11 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   if (n_points > 0) {
     const int64_t want = (n_points / 2 + 255) / 256;
     const unsigned blocks = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
-    sort_short_kernel<<<blocks, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.lists, L.lo, W.hdr);
+    sort_short_kernel<<<blocks, 256, 0, stream>>>(W.sorted_idx, W.lists, L.lo, W.hdr);
     PCP_LAUNCH_CHECK("sort_short_kernel");
     const int64_t want_mid = (n_points / 9 + 7) / 8;
     const unsigned blocks_mid = (unsigned)(want_mid < 148 * 8 ? (want_mid > 0 ? want_mid : 1) : 148 * 8);
-    sort_mid_kernel<<<blocks_mid, 256, 0, stream>>>(W.seg_off, W.sorted_idx, W.lists, L.lo, W.hdr);
+    sort_mid_kernel<<<blocks_mid, 256, 0, stream>>>(W.sorted_idx, W.lists, L.lo, W.hdr);
     PCP_LAUNCH_CHECK("sort_mid_kernel");
     const int64_t want_long = n_points / (kSegRows + 1);
     if (want_long > 0) {
