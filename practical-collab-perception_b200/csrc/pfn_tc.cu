@@ -34,18 +34,26 @@ namespace pcp {
 using namespace umma;
 
 constexpr int kTcThreads = 256;     // threads of the self-test kernels
-constexpr int kWorkers = 256;       // epilogue / feature threads of the PFN kernel: (pillar p, column half h)
-constexpr int kPfnThreads = kWorkers + 32;   // + one warp that only issues tensor-core instructions
-constexpr int kMmaWarp = kWorkers / 32;
-constexpr int kTmemCols = 256;
-// tensor-memory column map of one CTA
-constexpr uint32_t kColD0 = 0;      // layer-0 accumulator (32 columns; 64 for a single-layer PFN)
-constexpr uint32_t kColD1 = 64;     // layer-1 / hoist accumulator (64 columns)
-constexpr uint32_t kColA0h = 128;   // layer-0 A operand (features), TF32 hi part, k0 <= 24 columns
-constexpr uint32_t kColA0l = 160;   //                               lo part
-constexpr uint32_t kColA1h = 192;   // layer-1 A operand (x0, later max0), hi part, 32 columns
-constexpr uint32_t kColA1l = 224;   //                                     lo part
+// ---- roles of the PFN kernel (one persistent CTA per SM) ----
+constexpr int kEpiThreads = 512;    // epilogue threads: (pillar p = tid & 127, column quarter q = tid >> 7)
+constexpr int kProdThreads = 128;   // producers: one thread per pillar (TMEM lane) of the group
+constexpr int kProdWarp0 = kEpiThreads / 32;                   // 16
+constexpr int kMmaWarp = kProdWarp0 + kProdThreads / 32;      // 20
+constexpr int kPfnThreads = (kMmaWarp + 1) * 32;              // 672
+constexpr int kTmemCols = 512;
+// tensor-memory column map (everything double buffered: operand / accumulator b of op c is c & 1)
+constexpr uint32_t kColD0 = 0;      // layer-0 accumulators   [b * 64, +32)  (+64 for a single-layer PFN)
+constexpr uint32_t kColD1 = 128;    // layer-1 / hoist accumulators [128 + b * 64, +64)
+constexpr uint32_t kColA0 = 256;    // layer-0 A operand (features): hi at 256 + b * 64, lo 32 columns further (k0 <= 24)
+constexpr uint32_t kColA1 = 384;    // layer-1 A operand (x0 / max0): hi at 384 + b * 64, lo 32 columns further
 constexpr int kOutLd = 68;          // padded row of the output staging tile (conflict-free 16-byte accesses)
+constexpr int kIdxBufs = 3;         // row-number buffers: group g (in use), g + 1 (mean prefetch), g + 2 (cp.async in flight)
+constexpr int kRowRing = 8;         // ring of per-group output-row tables (producer runs a few groups ahead of the output)
+// mbarrier indices
+constexpr int kBarA0 = 0;           // [2] features staged in TMEM        (128 producer arrivals)
+constexpr int kBarA1 = 2;           // [2] x0 / max0 staged in TMEM       (512 epilogue arrivals)
+constexpr int kBarD0 = 4;           // [2] layer-0 accumulator ready      (tcgen05.commit)
+constexpr int kBarD1 = 6;           // [2] layer-1 / hoist accumulator ready
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -78,47 +86,25 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers) {
     S.prm_a1 = o; o += kCout;
     S.prm_b1 = o; o += kCout;
   }
-  S.idx = o; o += 2 * kSegRows * kGroup;     // row numbers of the current and the next group, [buffer][slot][pillar]
-  S.out = o; o += kGroup * kOutLd;           // output staging tile (coalesced pillar_features rows)
-  S.rows = o; o += 2 * kGroup;               // output row (pillar rank) / long-pillar index of each lane, [group parity][pillar]
-  S.ints = o; o += 64;                       // 4 mbarriers | tmem base | group prefix | list counts | list offsets
+  S.idx = o; o += kIdxBufs * kSegRows * kGroup;   // row numbers, [buffer][slot][pillar]
+  S.out = o; o += kGroup * kOutLd;                // output staging tile (coalesced pillar_features rows)
+  S.rows = o; o += kRowRing * kGroup;             // output row (pillar rank) / long-pillar index of each lane
+  S.ints = o; o += 80;                            // 8 mbarriers | tmem base | group prefix | list counts | list offsets
   S.total_bytes = o * 4;
   return S;
 }
 
-#ifdef PCP_PFN_TIMING
-__device__ long long g_pfn_timing[8192];
-}  // namespace pcp
-extern "C" int pcp_debug_read_timing(long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, pcp::g_pfn_timing, sizeof(long long) * 8192);
-}
-namespace pcp {
-#define PCP_T(id)                                                                             \
-  do {                                                                                        \
-    if (blockIdx.x == 7 && (tid == 0 || tid == 200) && dbg_n < 1000) {                        \
-      g_pfn_timing[(tid ? 4096 : 0) + dbg_n * 4 + 0] = (id);                                  \
-      g_pfn_timing[(tid ? 4096 : 0) + dbg_n * 4 + 1] = clock64();                             \
-      dbg_n++;                                                                                \
-    }                                                                                         \
-  } while (0)
-#else
-#define PCP_T(id) do {} while (0)
-#endif
-
-struct Work {        // one thread's pillar (or long-pillar segment) of a group
-  int r, off, len, li;
-  bool valid;
-};
-
-// Roles (no __syncthreads inside the main loop; everything is ordered by mbarriers):
-//   workers, threads 0..255 = (pillar p = tid & 127, column half h = tid >> 7)
-//     h == 0 also gathers the pillar's rows, computes its mean and writes the A0 operand (features) to TMEM
-//     both halves run the epilogues E0 / E1 on their half of the accumulator columns and keep the running maxima
-//   MMA warp, threads 256..287: waits for "operand staged" barriers, issues the tcgen05.mma groups, commits them to
-//     the "accumulator ready" barriers.  The tensor pipe back-pressures its issuer, so issuing from a worker would
-//     stall the whole CTA for the duration of every MMA group (measured: 500-1000 cycles per slot).
+// Persistent, warp-specialised kernel.  Three roles talk only through mbarriers:
+//   producers (4 warps, thread = pillar lane): prefetch the work-list entries and row numbers (cp.async), compute the
+//       pillar mean, gather each slot's row, build the feature vector and write its TF32 hi / lo parts to TMEM (A0);
+//   MMA warp: waits for "operand staged", issues the tcgen05.mma groups (layer 0 of the NEXT slot is queued in front
+//       of layer 1 of the current one, so the tensor pipe has work while the epilogue runs), commits to "accumulator ready";
+//   epilogue (16 warps, thread = pillar lane x column quarter): layer-0 epilogue (BN + ReLU, running max0, x0 back to
+//       TMEM as layer 1's A operand), layer-1 epilogue (running max), the per-pillar hoist and the output rows.
+// The issuing thread of a tcgen05.mma is back-pressured by the tensor pipe (measured 30-60 cycles per MMA), which is
+// why it owns a warp; shared-memory traffic is limited to the weight panels the MMAs read and the output staging tile.
 template <int kLayers, int kCfg>
-__global__ void __launch_bounds__(kPfnThreads, 2)
+__global__ void __launch_bounds__(kPfnThreads, 1)
 pfn_slot_kernel(const TcArgs A) {
   extern __shared__ __align__(128) float smem[];
   constexpr int N0 = (kLayers == 2) ? kHidden : kCout;
@@ -129,19 +115,14 @@ pfn_slot_kernel(const TcArgs A) {
   const bool with_dist = kCfg ? false : (A.with_distance != 0);
   const SmemPlan SP = smem_plan(k0, kLayers);
   const int tid = threadIdx.x, warp = tid >> 5;
-#ifdef PCP_PFN_TIMING
-  int dbg_n = 0;
-#endif
-  const int p = tid & (kGroup - 1);      // pillar of the group == TMEM lane
-  const int h = (tid >> 7) & 1;          // which half of the accumulator columns
   int* const s_idx = reinterpret_cast<int*>(smem + SP.idx);
   float* const s_out = smem + SP.out;
   int* const s_rows = reinterpret_cast<int*>(smem + SP.rows);
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + SP.ints);   // 0: a0 staged, 1: a1 staged, 2: d0 ready, 3: d1 ready
-  uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 8);
-  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 12);      // [kNumLists + 1] group prefix, processing order
-  int* const s_cnt = reinterpret_cast<int*>(smem + SP.ints + 28);      // [kNumLists] entries per list
-  long long* const s_loff = reinterpret_cast<long long*>(smem + SP.ints + 40);   // [kNumLists] list offsets
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + SP.ints);
+  uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 16);
+  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 20);      // [kNumLists + 1] group prefix, processing order
+  int* const s_cnt = reinterpret_cast<int*>(smem + SP.ints + 36);      // [kNumLists] entries per list
+  long long* const s_loff = reinterpret_cast<long long*>(smem + SP.ints + 48);   // [kNumLists] list offsets
 
   // ---- one-time setup: parameters -> smem, barriers, TMEM, work prefix ----
   {
@@ -159,10 +140,12 @@ pfn_slot_kernel(const TcArgs A) {
         smem[SP.prm_b1 + i] = A.params[PL.b1 + i];
       }
     if (tid == 0) {
-      mbar_init(&bars[0], kGroup);      // A0 staged: one arrival per pillar (the h == 0 workers)
-      mbar_init(&bars[1], kWorkers);    // A1 staged: every worker
-      mbar_init(&bars[2], 1);           // D0 ready: tcgen05.commit
-      mbar_init(&bars[3], 1);           // D1 ready: tcgen05.commit
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars[kBarA0 + b], kProdThreads);
+        mbar_init(&bars[kBarA1 + b], kEpiThreads);
+        mbar_init(&bars[kBarD0 + b], 1);
+        mbar_init(&bars[kBarD1 + b], 1);
+      }
       fence_mbar_init();
       int acc = 0;
       for (int q = 0; q < kNumLists; ++q) {                     // processing order: segments, then classes 9 .. 0
@@ -182,8 +165,6 @@ pfn_slot_kernel(const TcArgs A) {
     tc_fence_after_sync();
   }
   const uint32_t tmem = *s_tmem;
-  const uint32_t t_d0 = tmem + kColD0, t_d1 = tmem + kColD1;
-  const uint32_t t_a0h = tmem + kColA0h, t_a0l = tmem + kColA0l, t_a1h = tmem + kColA1h, t_a1l = tmem + kColA1l;
   const int total = s_pre[kNumLists];
   const int G = gridDim.x;
   auto list_of = [&](int w, int& q) {
@@ -192,57 +173,67 @@ pfn_slot_kernel(const TcArgs A) {
     for (int t = 1; t < kNumLists; ++t) q += (w >= s_pre[t]) ? 1 : 0;
     return kNumLists - 1 - q;
   };
+  auto slots_of = [&](int w, bool& is_seg) {
+    int q;
+    const int list = list_of(w, q);
+    is_seg = (list == kSegList);
+    return is_seg ? kSegRows : class_slots(list);
+  };
 
   if (warp == kMmaWarp) {
     // =====================================================================================================
     // MMA warp
     // =====================================================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     const uint32_t sw0h = smem_u32(smem + SP.w0h), sw0l = smem_u32(smem + SP.w0l);
     const uint32_t sw1ah = smem_u32(smem + SP.w1ah), sw1al = smem_u32(smem + SP.w1al);
     const uint32_t sw1bh = smem_u32(smem + SP.w1bh), sw1bl = smem_u32(smem + SP.w1bl);
     const uint32_t idesc0 = idesc_tf32_m128(N0), idesc1 = idesc_tf32_m128(kCout);
-    uint32_t pa0 = 0, pa1 = 0;
+    uint32_t c0 = 0, c1 = 0;      // layer-0 ops / layer-1-type ops issued so far
+    auto issue_m0 = [&]() {
+      const uint32_t b = c0 & 1;
+      mbar_wait(&bars[kBarA0 + b], (c0 >> 1) & 1);
+      if (kLayers == 1 && c0 >= 2) mbar_wait(&bars[kBarA1 + b], ((c0 - 2) >> 1) & 1);   // D0[b] consumed by the epilogue
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
+        mma_3xtf32_ts(tmem + kColD0 + b * 64, tmem + kColA0 + b * 64, tmem + kColA0 + b * 64 + 32, sw0h, sw0l, N0, k0 / 8,
+                      idesc0, false);
+        mma_commit(&bars[kBarD0 + b]);
+      }
+      __syncwarp();
+      ++c0;
+    };
+    auto issue_m1 = [&](uint32_t wh, uint32_t wl) {
+      const uint32_t b = c1 & 1;
+      mbar_wait(&bars[kBarA1 + b], (c1 >> 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
+        mma_3xtf32_ts(tmem + kColD1 + b * 64, tmem + kColA1 + b * 64, tmem + kColA1 + b * 64 + 32, wh, wl, kCout, kHidden / 8,
+                      idesc1, false);
+        mma_commit(&bars[kBarD1 + b]);
+      }
+      __syncwarp();
+      ++c1;
+    };
+    if ((int)blockIdx.x < total) issue_m0();
     for (int w = blockIdx.x; w < total; w += G) {
-      int q;
-      const int list = list_of(w, q);
-      const bool is_seg = (list == kSegList);
-      const int slots = is_seg ? kSegRows : class_slots(list);
+      bool is_seg;
+      const int slots = slots_of(w, is_seg);
+      const bool more_groups = (w + G) < total;
       for (int j = 0; j < slots; ++j) {
-        mbar_wait(&bars[0], pa0); pa0 ^= 1;
-        tc_fence_after_sync();
-        if (elect_one_sync()) {
-          mma_3xtf32_ts(t_d0, t_a0h, t_a0l, sw0h, sw0l, N0, k0 / 8, idesc0, false);
-          mma_commit(&bars[2]);
-        }
-        __syncwarp();
-        if (kLayers == 2) {
-          mbar_wait(&bars[1], pa1); pa1 ^= 1;
-          tc_fence_after_sync();
-          if (elect_one_sync()) {
-            mma_3xtf32_ts(t_d1, t_a1h, t_a1l, sw1ah, sw1al, kCout, kHidden / 8, idesc1, false);
-            mma_commit(&bars[3]);
-          }
-          __syncwarp();
-        }
+        if (j + 1 < slots || more_groups) issue_m0();          // the NEXT slot's layer 0 goes in front of this slot's layer 1
+        if (kLayers == 2) issue_m1(sw1ah, sw1al);
       }
-      if (kLayers == 2 && !is_seg) {
-        // hoist: max0 . W1[:, 32:]^T once per pillar
-        mbar_wait(&bars[1], pa1); pa1 ^= 1;
-        tc_fence_after_sync();
-        if (elect_one_sync()) {
-          mma_3xtf32_ts(t_d1, t_a1h, t_a1l, sw1bh, sw1bl, kCout, kHidden / 8, idesc1, false);
-          mma_commit(&bars[3]);
-        }
-        __syncwarp();
-      }
+      if (kLayers == 2 && !is_seg) issue_m1(sw1bh, sw1bl);     // hoist: max0 . W1[:, 32:]^T once per pillar
     }
-  } else {
+  } else if (warp >= kProdWarp0) {
     // =====================================================================================================
-    // workers
+    // producers (register budget raised with what the other roles gave back to the CTA pool)
     // =====================================================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int p = tid - kEpiThreads;                       // pillar of the group == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t pd0 = 0, pd1 = 0;
-    // raw 16-byte descriptor of this thread's pillar in group w (loads only; decoded later so they stay in flight)
+    struct Ent { int r, off, len, li; bool valid; };
     auto fetch = [&](int w, int4& raw) {
       int q;
       const int list = list_of(w, q);
@@ -258,154 +249,113 @@ pfn_slot_kernel(const TcArgs A) {
         }
       }
     };
-    auto decode = [&](const int4& raw, Work& W) {
-      W.valid = raw.w >= 0;
-      W.r = -1; W.off = 0; W.len = 0; W.li = -1;
-      if (raw.w == 1) { W.off = raw.x; W.len = raw.y; W.li = raw.z; }
-      else if (raw.w == 0) unpack_entry(((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x, W.r, W.off, W.len);
+    auto decode = [&](const int4& raw, Ent& E) {
+      E.valid = raw.w >= 0;
+      E.r = -1; E.off = 0; E.len = 0; E.li = -1;
+      if (raw.w == 1) { E.off = raw.x; E.len = raw.y; E.li = raw.z; }
+      else if (raw.w == 0) unpack_entry(((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x, E.r, E.off, E.len);
     };
-    // row numbers of every slot of a group -> s_idx[b] (cp.async: no registers, lands while the previous group computes)
-    auto issue_idx = [&](const Work& W, int slots, int b) {
-      if (W.valid) {
+    auto issue_idx = [&](const Ent& E, int w, int b) {
+      if (E.valid) {
+        bool sg;
+        const int slots = slots_of(w, sg);
         int* dst = s_idx + b * (kSegRows * kGroup) + p;
-        for (int j = 0; j < slots; ++j) cp_async4(dst + j * kGroup, A.sorted_idx + W.off + min(j, W.len - 1));
+        for (int j = 0; j < slots; ++j) cp_async4(dst + j * kGroup, A.sorted_idx + E.off + min(j, E.len - 1));
       }
     };
-    auto slots_of = [&](int w) {
-      int q;
-      const int list = list_of(w, q);
-      return list == kSegList ? kSegRows : class_slots(list);
-    };
-
-    Work cur, nxt;
-    cur.valid = false; cur.r = -1; cur.off = 0; cur.len = 0; cur.li = -1;
-    nxt = cur;
-    if (h == 0) {
-      int4 raw;
-      if ((int)blockIdx.x < total) { fetch(blockIdx.x, raw); decode(raw, cur); issue_idx(cur, slots_of(blockIdx.x), 0); }
-      cp_async_commit();
-      if ((int)blockIdx.x + G < total) { fetch(blockIdx.x + G, raw); decode(raw, nxt); }
-    }
-    int buf = 0;
-    bool pending = false;      // a finished group whose hoist MMA is in flight / whose output is not yet written
-    int pend_par = 0;
-    float max0[16];            // layer-0 running max, this thread's 16 channels (two layers only)
-    float m1[32];              // last-layer running max of the raw accumulators, this thread's 32 channels
-
-    // ======== OUT of a finished group: h = max0 . W1[:, 32:]^T landed in D1; BN(eval) + ReLU once per pillar; the tile is
-    // staged in shared memory so that every pillar_features row leaves as 256 contiguous bytes =========================
-    auto finish_pending = [&]() {
-      if (kLayers == 2) {
-        mbar_wait(&bars[3], pd1); pd1 ^= 1;
-        tc_fence_after_sync();
+    // xyz of up to 8 rows of a pillar (loads only: summed later, in ascending row order)
+    auto load_xyz8 = [&](const Ent& E, const int* idx, int j0, float (&vx)[8], float (&vy)[8], float (&vz)[8]) {
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          uint32_t rr[16];
-          tmem_ld16_nowait(t_d1 + lane_base + 32 * h + 16 * part, rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) m1[part * 16 + i] = __fadd_rn(m1[part * 16 + i], __uint_as_float(rr[i]));
-        }
-        tc_fence_before_sync();
-      }
-      {
-        const float* pa = smem + (kLayers == 2 ? SP.prm_a1 : SP.prm_a0) + 32 * h;
-        const float* pb = smem + (kLayers == 2 ? SP.prm_b1 : SP.prm_b0) + 32 * h;
-        float* dst = s_out + p * kOutLd + 32 * h;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 al = ld4(pa + i), be = ld4(pb + i);
-          float4 o;
-          o.x = fmaxf(fmaf(m1[i + 0], al.x, be.x), 0.f);
-          o.y = fmaxf(fmaf(m1[i + 1], al.y, be.y), 0.f);
-          o.z = fmaxf(fmaf(m1[i + 2], al.z, be.z), 0.f);
-          o.w = fmaxf(fmaf(m1[i + 3], al.w, be.w), 0.f);
-          *reinterpret_cast<float4*>(dst + i) = o;
-        }
-      }
-      named_bar_sync(1, kWorkers);
-      const int* rows = s_rows + pend_par * kGroup;
-#pragma unroll
-      for (int t = 0; t < (kGroup * kCout / 4) / kWorkers; ++t) {
-        const int item = t * kWorkers + tid;
-        const int row = item >> 4, c4 = item & 15;
-        const int r = rows[row];
-        if (r >= 0) *reinterpret_cast<float4*>(A.out + (int64_t)r * kCout + c4 * 4) = ld4(s_out + row * kOutLd + c4 * 4);
-      }
-      pending = false;
-    };
-
-    int par = 0;
-    for (int w = blockIdx.x; w < total; w += G, par ^= 1) {
-      int q;
-      const int list = list_of(w, q);
-      const bool is_seg = (list == kSegList);
-      const int slots = is_seg ? kSegRows : class_slots(list);
-      PCP_T(100 + slots);
-      const int* my_idx = s_idx + buf * (kSegRows * kGroup) + p;
-      int4 nn_raw = make_int4(0, 0, 0, -1);
-      const bool have_nn = (w + 2 * G) < total;
-      float mean_x = 0.f, mean_y = 0.f, mean_z = 0.f;
-      const bool valid = cur.valid;
-      const int len = cur.len;
-      if (h == 0) {
-        // ---- prefetch: row numbers of the next group, descriptor of the one after ----
-        if (w + G < total) issue_idx(nxt, slots_of(w + G), buf ^ 1);
-        cp_async_commit();
-        if (have_nn) fetch(w + 2 * G, nn_raw);
-        cp_async_wait<1>();                               // this thread's copies of the current group have landed
-        s_rows[par * kGroup + p] = is_seg ? cur.li : cur.r;
-        // ---- pillar mean: scatter_mean = sum in ascending row order / count (dynamic_pillar_vfe.py:110) ----
-        if (valid) {
-          if (is_seg) {
-            const float4 m = __ldg(A.long_mean + cur.li);
-            mean_x = m.x; mean_y = m.y; mean_z = m.z;
+      for (int t = 0; t < 8; ++t) {
+        if (E.valid && j0 + t < E.len) {
+          const float* row = A.points + (int64_t)idx[(j0 + t) * kGroup] * A.stride;
+          if (kCfg == 1) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+            vx[t] = v.y; vy[t] = v.z; vz[t] = v.w;
           } else {
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            for (int j0 = 0; j0 < len; j0 += 8) {
-              float vx[8], vy[8], vz[8];
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                if (j0 + t < len) {
-                  const float* row = A.points + (int64_t)my_idx[(j0 + t) * kGroup] * A.stride;
-                  if (kCfg == 1) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(row));
-                    vx[t] = v.y; vy[t] = v.z; vz[t] = v.w;
-                  } else {
-                    vx[t] = __ldg(row + 1); vy[t] = __ldg(row + 2); vz[t] = __ldg(row + 3);
-                  }
-                }
-              }
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                if (j0 + t < len) { sx = __fadd_rn(sx, vx[t]); sy = __fadd_rn(sy, vy[t]); sz = __fadd_rn(sz, vz[t]); }
-              }
-            }
-            const float cnt = (float)len;
-            mean_x = __fdiv_rn(sx, cnt); mean_y = __fdiv_rn(sy, cnt); mean_z = __fdiv_rn(sz, cnt);
-            if (A.mean_out) {
-              float* m = A.mean_out + (int64_t)cur.r * 3;
-              m[0] = mean_x; m[1] = mean_y; m[2] = mean_z;
-            }
+            vx[t] = __ldg(row + 1); vy[t] = __ldg(row + 2); vz[t] = __ldg(row + 3);
           }
         }
       }
-      PCP_T(103);
-      // the previous group's hoist MMA ran while the loads above were in flight
-      if (pending) finish_pending();
-      PCP_T(105);
-
+    };
+    // scatter_mean = sum in ascending row order / count (dynamic_pillar_vfe.py:110); first 8 rows already in registers
+    auto finish_mean = [&](const Ent& E, const int* idx, bool is_seg, const float (&vx)[8], const float (&vy)[8],
+                           const float (&vz)[8], float& mx, float& my, float& mz) {
+      mx = my = mz = 0.f;
+      if (!E.valid) return;
+      if (is_seg) {
+        const float4 m = __ldg(A.long_mean + E.li);
+        mx = m.x; my = m.y; mz = m.z;
+        return;
+      }
+      float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) max0[i] = 0.f;
+      for (int t = 0; t < 8; ++t)
+        if (t < E.len) { sx = __fadd_rn(sx, vx[t]); sy = __fadd_rn(sy, vy[t]); sz = __fadd_rn(sz, vz[t]); }
+      for (int j0 = 8; j0 < E.len; j0 += 8) {
+        float wx[8], wy[8], wz[8];
+        load_xyz8(E, idx, j0, wx, wy, wz);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
+        for (int t = 0; t < 8; ++t)
+          if (j0 + t < E.len) { sx = __fadd_rn(sx, wx[t]); sy = __fadd_rn(sy, wy[t]); sz = __fadd_rn(sz, wz[t]); }
+      }
+      const float cnt = (float)E.len;
+      mx = __fdiv_rn(sx, cnt); my = __fdiv_rn(sy, cnt); mz = __fdiv_rn(sz, cnt);
+      if (A.mean_out) {
+        float* m = A.mean_out + (int64_t)E.r * 3;
+        m[0] = mx; m[1] = my; m[2] = mz;
+      }
+    };
 
-      // ---- row fetch (registers; issued one slot ahead) and A0 = TF32 hi / lo features -> tensor memory (h == 0) ----
-      float rw[NREG];
-      const float* rowp = A.points;
-      auto load_row = [&](int j) {
-        if (!valid) return;
-        rowp = A.points + (int64_t)my_idx[j * kGroup] * A.stride;
+    // ---- prime the prefetch pipeline: entries of groups 0..2, row numbers of groups 0..1, mean of group 0 ----
+    Ent cur, nxt, nn;
+    cur.valid = nxt.valid = nn.valid = false;
+    cur.r = nxt.r = nn.r = -1; cur.off = nxt.off = nn.off = 0; cur.len = nxt.len = nn.len = 0; cur.li = nxt.li = nn.li = -1;
+    const int w0 = blockIdx.x;
+    {
+      int4 raw;
+      if (w0 < total) { fetch(w0, raw); decode(raw, cur); issue_idx(cur, w0, 0); }
+      cp_async_commit();
+      if (w0 + G < total) { fetch(w0 + G, raw); decode(raw, nxt); issue_idx(nxt, w0 + G, 1); }
+      cp_async_commit();
+      if (w0 + 2 * G < total) { fetch(w0 + 2 * G, raw); decode(raw, nn); }
+    }
+    float mean_x = 0.f, mean_y = 0.f, mean_z = 0.f;
+    if (w0 < total) {
+      cp_async_wait<1>();
+      bool sg;
+      slots_of(w0, sg);
+      float vx[8], vy[8], vz[8];
+      load_xyz8(cur, s_idx + p, 0, vx, vy, vz);
+      finish_mean(cur, s_idx + p, sg, vx, vy, vz, mean_x, mean_y, mean_z);
+    }
+    uint32_t c0 = 0;
+    int ib = 0;                 // row-number buffer of the current group
+    int gi = 0;                 // group counter (ring index of s_rows)
+    float rw[NREG];
+    const float* rowp = A.points;
+    for (int w = w0; w < total; w += G, ++gi) {
+      bool is_seg, nseg = false;
+      const int slots = slots_of(w, is_seg);
+      const bool have_next = (w + G) < total;
+      if (have_next) slots_of(w + G, nseg);
+      const int* my_idx = s_idx + ib * (kSegRows * kGroup) + p;
+      const int ib1 = (ib + 1) % kIdxBufs, ib2 = (ib + 2) % kIdxBufs;
+      const int* nx_idx = s_idx + ib1 * (kSegRows * kGroup) + p;
+      const bool valid = cur.valid;
+      s_rows[(gi % kRowRing) * kGroup + p] = is_seg ? cur.li : cur.r;
+      // ---- prefetch for the following groups (all in flight while this group's slots are built) ----
+      int4 raw3 = make_int4(0, 0, 0, -1);
+      if (w + 2 * G < total) issue_idx(nn, w + 2 * G, ib2);       // row numbers of group g + 2
+      cp_async_commit();
+      if (w + 3 * G < total) fetch(w + 3 * G, raw3);              // entry of group g + 3
+      cp_async_wait<1>();                                         // row numbers of group g + 1 have landed
+      float vx[8], vy[8], vz[8];
+      if (have_next && !nseg) load_xyz8(nxt, nx_idx, 0, vx, vy, vz);   // rows of group g + 1 for its mean
+
+      auto load_row = [&](const int* idx, int j, bool ok) {
+        if (!ok) return;
+        rowp = A.points + (int64_t)idx[j * kGroup] * A.stride;
         if (kCfg == 1) {
           const float4 v0 = __ldg(reinterpret_cast<const float4*>(rowp));
           const float4 v1 = __ldg(reinterpret_cast<const float4*>(rowp) + 1);
@@ -418,7 +368,10 @@ pfn_slot_kernel(const TcArgs A) {
           }
         }
       };
-      auto build_a0 = [&]() {
+      if (w == w0) load_row(my_idx, 0, valid);                    // later groups: fetched at the end of the previous group
+
+      for (int j = 0; j < slots; ++j) {
+        // ---- features of this slot's row (dynamic_pillar_vfe.py:111-126) ----
         float x = 0.f, y = 0.f, z = 0.f;
         if (valid) {
           if (kCfg) { x = rw[1]; y = rw[2]; z = rw[3]; }
@@ -435,14 +388,17 @@ pfn_slot_kernel(const TcArgs A) {
         ed[5] = __fsub_rn(z, A.g.z_offset);
         ed[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
         const int n_feat = n_raw + (with_dist ? 7 : 6);
-        const uint32_t dh = t_a0h + lane_base, dl = t_a0l + lane_base;
+        // A0[c0 & 1] is free once the layer-0 MMA that read it two ops ago has completed
+        const uint32_t b = c0 & 1;
+        if (c0 >= 2) { mbar_wait(&bars[kBarD0 + b], ((c0 - 2) >> 1) & 1); tc_fence_after_sync(); }
+        const uint32_t dh = tmem + kColA0 + b * 64 + lane_base, dl = dh + 32;
 #pragma unroll
-        for (int c0 = 0; c0 < kMaxCin; c0 += 8) {
-          if (c0 < k0) {
+        for (int cc = 0; cc < kMaxCin; cc += 8) {
+          if (cc < k0) {
             float hi[8], lo[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              const int f = c0 + t;
+              const int f = cc + t;
               float val = 0.f;
               if (valid) {
                 if (f < n_raw) {
@@ -455,119 +411,197 @@ pfn_slot_kernel(const TcArgs A) {
               }
               split_tf32(val, hi[t], lo[t]);
             }
-            tmem_st8(dh + c0, hi);
-            tmem_st8(dl + c0, lo);
+            tmem_st8(dh + cc, hi);
+            tmem_st8(dl + cc, lo);
           }
         }
         tmem_st_wait();
         tc_fence_before_sync();
-        mbar_arrive(&bars[0]);
-      };
-
-      if (h == 0) {
-        load_row(0);
-        build_a0();
-        if (slots > 1) load_row(1);
+        mbar_arrive(&bars[kBarA0 + b]);
+        ++c0;
+        // ---- next row: this group's next slot, or slot 0 of the next group ----
+        if (j + 1 < slots) load_row(my_idx, j + 1, valid);
+        else if (have_next) load_row(nx_idx, 0, nxt.valid);
       }
-      PCP_T(108);
+      // ---- rotate: mean of the next group from the rows fetched above ----
+      if (have_next) finish_mean(nxt, nx_idx, nseg, vx, vy, vz, mean_x, mean_y, mean_z);
+      cur = nxt; nxt = nn;
+      decode(raw3, nn);
+      ib = ib1;
+    }
+  } else {
+    // =====================================================================================================
+    // epilogue
+    // =====================================================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int p = tid & (kGroup - 1);
+    const int q = tid >> 7;                                  // column quarter
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t c0 = 0, c1 = 0;   // layer-0 accumulators consumed / layer-1-type ops staged
+    float max0[8];             // layer-0 running max, this thread's 8 channels (two layers only)
+    float m1[16];              // last-layer running max of the raw accumulators, this thread's 16 channels
+    bool pend_fin = false;     // a finished group whose hoist result / output rows are still outstanding
+    uint32_t pend_k = 0;       // its hoist op
+    int pend_gi = 0;
+    uint32_t e1_k = 0;         // op whose accumulator the next E1 reads
 
-      for (int j = 0; j < slots; ++j) {
-        PCP_T(1);
-        mbar_wait(&bars[2], pd0); pd0 ^= 1;
-        tc_fence_after_sync();
-        PCP_T(2);
-        if (kLayers == 2) {
-          // ================= E0: BN+ReLU, running max0, x0 -> TMEM as the A operand of layer 1 =================
-          {
-            uint32_t rr[16];
-            tmem_ld16_nowait(t_d0 + lane_base + 16 * h, rr);
-            tmem_ld_wait();
-            float hi[16], lo[16];
-            const float* pa = smem + SP.prm_a0 + 16 * h;
-            const float* pb = smem + SP.prm_b0 + 16 * h;
+    auto e0 = [&]() {          // BN + ReLU, running max0, x0 -> TMEM as the A operand of layer 1
+      const uint32_t b = c0 & 1;
+      mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t rr[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
+                   : "r"(tmem + kColD0 + b * 64 + lane_base + 8 * q)
+                   : "memory");
+      tmem_ld_wait();
+      float hi[8], lo[8];
+      const float4 al0 = ld4(smem + SP.prm_a0 + 8 * q), al1 = ld4(smem + SP.prm_a0 + 8 * q + 4);
+      const float4 be0 = ld4(smem + SP.prm_b0 + 8 * q), be1 = ld4(smem + SP.prm_b0 + 8 * q + 4);
+      const float a8[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
+      const float b8[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 al = ld4(pa + i), be = ld4(pb + i);
-              const float a4[4] = {al.x, al.y, al.z, al.w}, b4[4] = {be.x, be.y, be.z, be.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float xv = fmaxf(fmaf(__uint_as_float(rr[i + t]), a4[t], b4[t]), 0.f);
-                max0[i + t] = fmaxf(max0[i + t], xv);
-                split_tf32(xv, hi[i + t], lo[i + t]);
-              }
-            }
-            tmem_st16(t_a1h + lane_base + 16 * h, hi);
-            tmem_st16(t_a1l + lane_base + 16 * h, lo);
-            tmem_st_wait();
-          }
-          tc_fence_before_sync();
-          mbar_arrive(&bars[1]);
-          PCP_T(3);
-          // ================= next slot's A0 goes in behind M1 =================
-          if (h == 0 && j + 1 < slots) {
-            build_a0();
-            if (j + 2 < slots) load_row(j + 2);
-          }
-          PCP_T(6);
-          mbar_wait(&bars[3], pd1); pd1 ^= 1;
-          tc_fence_after_sync();
-          PCP_T(8);
-        }
-        // ================= E1: running max of the raw last-layer accumulators =================
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          uint32_t rr[16];
-          tmem_ld16_nowait((kLayers == 2 ? t_d1 : t_d0) + lane_base + 32 * h + 16 * part, rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) m1[part * 16 + i] = fmaxf(m1[part * 16 + i], __uint_as_float(rr[i]));
-        }
-        tc_fence_before_sync();
-        PCP_T(9);
-        if (kLayers == 1) {
-          // single layer: D0 is free again only now; the A1 barrier doubles as "D0 consumed" for the MMA warp
-          if (j + 1 < slots) {
-            named_bar_sync(1, kWorkers);
-            if (h == 0) { build_a0(); if (j + 2 < slots) load_row(j + 2); }
-          }
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float xv = fmaxf(fmaf(__uint_as_float(rr[i]), a8[i], b8[i]), 0.f);
+        max0[i] = fmaxf(max0[i], xv);
+        split_tf32(xv, hi[i], lo[i]);
       }
+      const uint32_t b1 = c1 & 1;
+      tmem_st8(tmem + kColA1 + b1 * 64 + lane_base + 8 * q, hi);
+      tmem_st8(tmem + kColA1 + b1 * 64 + 32 + lane_base + 8 * q, lo);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars[kBarA1 + b1]);
+      ++c0; ++c1;
+    };
+    auto ld_acc16 = [&](uint32_t k, uint32_t (&rr)[16]) {       // this thread's 16 columns of layer-1-type op k
+      const uint32_t b = k & 1;
+      mbar_wait(&bars[kBarD1 + b], (k >> 1) & 1);
+      tc_fence_after_sync();
+      tmem_ld16_nowait(tmem + kColD1 + b * 64 + lane_base + 16 * q, rr);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+    };
+    auto e1 = [&]() {          // running max of the raw last-layer accumulators
+      uint32_t rr[16];
+      ld_acc16(e1_k, rr);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m1[i] = fmaxf(m1[i], __uint_as_float(rr[i]));
+    };
+    // OUT: BN(eval) + ReLU once per pillar; the tile is staged in shared memory so that every pillar_features row
+    // leaves as 256 contiguous bytes
+    auto write_out = [&](int gi) {
+      const float* pa = smem + (kLayers == 2 ? SP.prm_a1 : SP.prm_a0) + 16 * q;
+      const float* pb = smem + (kLayers == 2 ? SP.prm_b1 : SP.prm_b0) + 16 * q;
+      float* dst = s_out + p * kOutLd + 16 * q;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 al = ld4(pa + i), be = ld4(pb + i);
+        float4 o;
+        o.x = fmaxf(fmaf(m1[i + 0], al.x, be.x), 0.f);
+        o.y = fmaxf(fmaf(m1[i + 1], al.y, be.y), 0.f);
+        o.z = fmaxf(fmaf(m1[i + 2], al.z, be.z), 0.f);
+        o.w = fmaxf(fmaf(m1[i + 3], al.w, be.w), 0.f);
+        *reinterpret_cast<float4*>(dst + i) = o;
+      }
+      named_bar_sync(1, kEpiThreads);
+      const int* rows = s_rows + (gi % kRowRing) * kGroup;
+#pragma unroll
+      for (int t = 0; t < (kGroup * kCout / 4) / kEpiThreads; ++t) {
+        const int item = t * kEpiThreads + tid;
+        const int row = item >> 4, c4 = item & 15;
+        const int r = rows[row];
+        if (r >= 0) *reinterpret_cast<float4*>(A.out + (int64_t)r * kCout + c4 * 4) = ld4(s_out + row * kOutLd + c4 * 4);
+      }
+      named_bar_sync(2, kEpiThreads);
+    };
+    auto finish_group = [&]() {   // hoist result + output of the pending group
+      if (kLayers == 2) {
+        uint32_t rr[16];
+        ld_acc16(pend_k, rr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m1[i] = __fadd_rn(m1[i], __uint_as_float(rr[i]));
+      }
+      write_out(pend_gi);
+      pend_fin = false;
+    };
 
-      if (is_seg) {
-        // ---- long pillar segment: partial maxima -> the pillar's accumulator ----
-        const int li = s_rows[par * kGroup + p];
-        if (li >= 0) {
-          unsigned* acc = A.long_acc + (int64_t)li * 96;
-          if (kLayers == 2) {
+    int gi = 0;
+    for (int w = blockIdx.x; w < total; w += G, ++gi) {
+      bool is_seg;
+      const int slots = slots_of(w, is_seg);
+      if (kLayers == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicMax(acc + 16 * h + i, ord_enc(max0[i]));
+        for (int i = 0; i < 8; ++i) max0[i] = 0.f;
+        for (int j = 0; j < slots; ++j) {
+          e0();                                       // stages op c1 - 1
+          if (j == 0) {
+            if (pend_fin) finish_group();             // previous group: its hoist ran behind our first layer-0 epilogue
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m1[i] = -INFINITY;
+          } else {
+            e1();                                     // previous slot
           }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) atomicMax(acc + 32 + 32 * h + i, ord_enc(m1[i]));
+          e1_k = c1 - 1;
         }
-        if (kLayers == 1) named_bar_sync(1, kWorkers);   // D0 consumed before the next group's first MMA
-      } else {
-        if (kLayers == 2) {
-          // ============ H: max0 -> A1; the MMA warp multiplies by W1[:, 32:]^T; collected by finish_pending() ============
-          float hi[16], lo[16];
+        if (!is_seg) {
+          // hoist: max0 -> A1; the MMA warp multiplies by W1[:, 32:]^T
+          float hi[8], lo[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_tf32(max0[i], hi[i], lo[i]);
-          tmem_st16(t_a1h + lane_base + 16 * h, hi);
-          tmem_st16(t_a1l + lane_base + 16 * h, lo);
+          for (int i = 0; i < 8; ++i) split_tf32(max0[i], hi[i], lo[i]);
+          const uint32_t b1 = c1 & 1;
+          tmem_st8(tmem + kColA1 + b1 * 64 + lane_base + 8 * q, hi);
+          tmem_st8(tmem + kColA1 + b1 * 64 + 32 + lane_base + 8 * q, lo);
           tmem_st_wait();
           tc_fence_before_sync();
-          mbar_arrive(&bars[1]);
+          mbar_arrive(&bars[kBarA1 + b1]);
+          pend_k = c1;
+          ++c1;
         }
-        pending = true; pend_par = par;
-        if (kLayers == 1) { finish_pending(); named_bar_sync(1, kWorkers); }
+        e1();                                         // last slot
+        if (is_seg) {
+          // long pillar segment: partial maxima -> the pillar's accumulator
+          const int li = s_rows[(gi % kRowRing) * kGroup + p];
+          if (li >= 0) {
+            unsigned* acc = A.long_acc + (int64_t)li * 96;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicMax(acc + 8 * q + i, ord_enc(max0[i]));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicMax(acc + 32 + 16 * q + i, ord_enc(m1[i]));
+          }
+        } else {
+          pend_fin = true; pend_gi = gi;
+        }
+      } else {
+        // single layer: D0 (64 columns) is the last-layer accumulator
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m1[i] = -INFINITY;
+        for (int j = 0; j < slots; ++j) {
+          const uint32_t b = c0 & 1;
+          mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
+          tc_fence_after_sync();
+          uint32_t rr[16];
+          tmem_ld16_nowait(tmem + kColD0 + b * 64 + lane_base + 16 * q, rr);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          mbar_arrive(&bars[kBarA1 + b]);             // "D0[b] consumed"
+          ++c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m1[i] = fmaxf(m1[i], __uint_as_float(rr[i]));
+        }
+        if (is_seg) {
+          const int li = s_rows[(gi % kRowRing) * kGroup + p];
+          if (li >= 0) {
+            unsigned* acc = A.long_acc + (int64_t)li * 96;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicMax(acc + 32 + 16 * q + i, ord_enc(m1[i]));
+          }
+        } else {
+          write_out(gi);
+        }
       }
-      PCP_T(110);
-      // ---- rotate the prefetch pipeline ----
-      cur = nxt;
-      if (h == 0 && have_nn) decode(nn_raw, nxt);
-      buf ^= 1;
     }
-    if (pending) finish_pending();
+    if (pend_fin) finish_group();
   }
   // ---- teardown ----
   tc_fence_before_sync();
@@ -751,7 +785,7 @@ static int launch_cfg(const TcArgs& a, int64_t n_points, cudaStream_t stream) {
   PCP_CUDA(cudaFuncSetAttribute(pfn_slot_kernel<kLayers, kCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP.total_bytes));
   // upper bound of the group count: every list may end in a partial group
   const int64_t groups = n_points / kGroup + kNumLists;
-  const unsigned blocks = (unsigned)(groups < 148 * 2 ? groups : 148 * 2);
+  const unsigned blocks = (unsigned)(groups < 148 ? groups : 148);
   pfn_slot_kernel<kLayers, kCfg><<<blocks, kPfnThreads, SP.total_bytes, stream>>>(a);
   PCP_LAUNCH_CHECK("pfn_slot_kernel");
   return 0;
