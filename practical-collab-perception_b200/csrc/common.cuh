@@ -76,8 +76,9 @@ __host__ __device__ inline int class_of(int n) {
 //   seg_off    int32[cap+1]     first sorted position of each pillar (exclusive scan of counts)
 //   sorted_idx int32[N]         input row numbers grouped by pillar, ascending inside a pillar
 //   lists      uint64[...]      per length class: packed pillar descriptors (list k at list_off[k], capacity
-//                               N / min_len + 1): bits [0,29) pillar rank, [29,58) first sorted position, [58,63) rows - 1
-//   seg_table  int4[N/16+2]     long-pillar segments {first sorted position, rows, long index, 0}
+//                               N / min_len + 1): bits [0,29) pillar rank, [29,58) first sorted position, [58,63) rows - 1;
+//                               the last list holds the long-pillar SEGMENTS (same packing, long index instead of rank)
+//   mean       float4[cap+1]    per-pillar mean xyz (sequential fp32 sum in ascending row order / count), by pillar rank
 //   long_table int4[N/33+1]     long pillars {pillar rank, first sorted position, rows, first segment}
 //   long_mean  float4[N/33+1]   mean xyz of each long pillar (sequential fp32 sum in ascending row order)
 //   long_acc   uint32[96*(N/33+1)] per long pillar: ordered-int running max of layer-0 (32) and layer-1 (64) values
@@ -103,7 +104,7 @@ __host__ __device__ inline void unpack_entry(unsigned long long e, int& r, int& 
 }
 
 struct WsLayout {
-  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, lists, seg_table, long_table, long_mean, long_acc, total;
+  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, lists, mean, long_table, long_mean, long_acc, total;
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
   int64_t cells, cap, scan_tiles, seg_cap, long_cap;
   ListOffsets lo;
@@ -135,9 +136,10 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
     if (c > L.cap + 1) c = L.cap + 1;
     lo += (c + 63) / 64 * 64;
   }
-  L.lo.off[kSegList] = lo;   // the segment "list" is the identity (entry e = segment e): no storage
+  L.lo.off[kSegList] = lo;   // long-pillar segments, written by pillar_prep_kernel
+  lo += (L.seg_cap + 63) / 64 * 64;
   o = align_up(o + sizeof(unsigned long long) * (size_t)(lo + 64), 256);
-  L.seg_table = o;   o = align_up(o + 16 * (size_t)L.seg_cap, 256);
+  L.mean = o;        o = align_up(o + 16 * (size_t)(L.cap + 1), 256);
   L.long_table = o;  o = align_up(o + 16 * (size_t)L.long_cap, 256);
   L.long_mean = o;   o = align_up(o + 16 * (size_t)L.long_cap, 256);
   L.long_acc = o;    o = align_up(o + sizeof(uint32_t) * 96 * (size_t)L.long_cap, 256);
@@ -154,7 +156,7 @@ struct WsView {
   int32_t* seg_off;
   int32_t* sorted_idx;
   unsigned long long* lists;
-  int4* seg_table;
+  float4* mean;
   int4* long_table;
   float4* long_mean;
   unsigned* long_acc;
@@ -171,7 +173,7 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.seg_off = reinterpret_cast<int32_t*>(p + L.seg_off);
   v.sorted_idx = reinterpret_cast<int32_t*>(p + L.sorted_idx);
   v.lists = reinterpret_cast<unsigned long long*>(p + L.lists);
-  v.seg_table = reinterpret_cast<int4*>(p + L.seg_table);
+  v.mean = reinterpret_cast<float4*>(p + L.mean);
   v.long_table = reinterpret_cast<int4*>(p + L.long_table);
   v.long_mean = reinterpret_cast<float4*>(p + L.long_mean);
   v.long_acc = reinterpret_cast<unsigned*>(p + L.long_acc);

@@ -89,9 +89,18 @@ __global__ void __launch_bounds__(256)
 pfn_finish_long_kernel(const int32_t* __restrict__ hdr, const int4* __restrict__ long_table, unsigned* __restrict__ long_acc,
                        const float4* __restrict__ long_mean, const float* __restrict__ params, int c_in, int num_layers,
                        float* __restrict__ out, float* __restrict__ mean_out) {
+  __shared__ float s_w[kHidden][kCout + 1];     // W1[:, 32:] transposed: s_w[k][n], lanes read consecutive n
   const ParamLayout P = param_layout(c_in, num_layers);
   const int nlong = hdr[kHdrLongCount];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  if ((int)(blockIdx.x * wpb) >= nlong) return;
+  if (num_layers == 2) {
+    for (int i = threadIdx.x; i < kCout * kHidden; i += blockDim.x) s_w[i % kHidden][i / kHidden] = __ldg(params + P.w1b_f32 + i);
+  }
+  __syncthreads();
+  const int pa = num_layers == 2 ? P.a1 : P.a0, pb = num_layers == 2 ? P.b1 : P.b0;
+  const float sa0 = __ldg(params + pa + lane), sa1 = __ldg(params + pa + 32 + lane);
+  const float sb0 = __ldg(params + pb + lane), sb1 = __ldg(params + pb + 32 + lane);
   for (int li = blockIdx.x * wpb + (threadIdx.x >> 5); li < nlong; li += gridDim.x * wpb) {
     const int r = long_table[li].x;
     if (mean_out && lane == 0) {
@@ -105,17 +114,15 @@ pfn_finish_long_kernel(const int32_t* __restrict__ hdr, const int4* __restrict__
     acc[lane] = kAccInit; acc[32 + lane] = kAccInit; acc[64 + lane] = kAccInit;
     float ha = 0.f, hb = 0.f;
     if (num_layers == 2) {
-      const float* wa = params + P.w1b_f32 + lane * kHidden;
-      const float* wb = params + P.w1b_f32 + (lane + 32) * kHidden;
+#pragma unroll
       for (int k = 0; k < kHidden; ++k) {
         const float xk = __shfl_sync(0xffffffffu, x0, k);
-        ha = fmaf(xk, __ldg(wa + k), ha);
-        hb = fmaf(xk, __ldg(wb + k), hb);
+        ha = fmaf(xk, s_w[k][lane], ha);
+        hb = fmaf(xk, s_w[k][lane + 32], hb);
       }
     }
-    const int pa = num_layers == 2 ? P.a1 : P.a0, pb = num_layers == 2 ? P.b1 : P.b0;
-    out[(int64_t)r * kCout + lane] = fmaxf(fmaf(__fadd_rn(ma, ha), params[pa + lane], params[pb + lane]), 0.f);
-    out[(int64_t)r * kCout + 32 + lane] = fmaxf(fmaf(__fadd_rn(mb, hb), params[pa + 32 + lane], params[pb + 32 + lane]), 0.f);
+    out[(int64_t)r * kCout + lane] = fmaxf(fmaf(__fadd_rn(ma, ha), sa0, sb0), 0.f);
+    out[(int64_t)r * kCout + 32 + lane] = fmaxf(fmaf(__fadd_rn(mb, hb), sa1, sb1), 0.f);
   }
 }
 
@@ -221,17 +228,17 @@ extern "C" int pcp_pfn(const float* points, int64_t row_stride, int64_t n_points
   const WsView W = ws_view(const_cast<void*>(workspace), L);
   TcArgs t;
   t.points = points; t.stride = row_stride; t.g = *grid; t.c_in = c_in;
-  t.raw_col0 = desc->use_absolute_xyz ? 1 : 4;
+  t.raw_col0 = desc->use_absolute_xyz ? 1 : 4; t.c_raw = desc->c_raw;
   t.n_raw = desc->use_absolute_xyz ? desc->c_raw : desc->c_raw - 3;
   t.with_distance = desc->with_distance; t.k0 = pfn_k0(c_in); t.num_layers = desc->num_layers;
   t.params = packed_params;
   t.hdr = W.hdr; t.seg_off = W.seg_off; t.sorted_idx = W.sorted_idx; t.lists = W.lists; t.lo = L.lo;
-  t.seg_table = W.seg_table; t.long_mean = W.long_mean; t.long_acc = W.long_acc; t.long_table = W.long_table;
+  t.mean = W.mean; t.long_mean = W.long_mean; t.long_acc = W.long_acc; t.long_table = W.long_table;
   t.out = pillar_features_out; t.mean_out = pillar_mean_out;
   if (int rc = launch_pfn_tc(t, n_points, stream)) return rc;
   if (n_points > kSegRows) {
     const int64_t want = (n_points / (kSegRows + 1) + 7) / 8;
-    const unsigned blocks = (unsigned)(want < 148 ? (want > 0 ? want : 1) : 148);
+    const unsigned blocks = (unsigned)(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4);
     pfn_finish_long_kernel<<<blocks, 256, 0, stream>>>(W.hdr, W.long_table, W.long_acc, W.long_mean, packed_params, c_in,
                                                        desc->num_layers, pillar_features_out, pillar_mean_out);
     PCP_LAUNCH_CHECK("pfn_finish_long_kernel");

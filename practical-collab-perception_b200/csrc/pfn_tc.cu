@@ -47,8 +47,8 @@ constexpr uint32_t kColD1 = 128;    // layer-1 / hoist accumulators [128 + b * 6
 constexpr uint32_t kColA0 = 256;    // layer-0 A operand (features): hi at 256 + b * 64, lo 32 columns further (k0 <= 24)
 constexpr uint32_t kColA1 = 384;    // layer-1 A operand (x0 / max0): hi at 384 + b * 64, lo 32 columns further
 constexpr int kOutLd = 68;          // padded row of the output staging tile (conflict-free 16-byte accesses)
-constexpr int kIdxBufs = 3;         // row-number buffers: group g (in use), g + 1 (mean prefetch), g + 2 (cp.async in flight)
 constexpr int kRowRing = 8;         // ring of per-group output-row tables (producer runs a few groups ahead of the output)
+constexpr int kEntRing = 32;        // ring of per-group work-list entries (the entry cursor runs up to 3 * depth groups ahead)
 // mbarrier indices
 constexpr int kBarA0 = 0;           // [2] features staged in TMEM        (128 producer arrivals)
 constexpr int kBarA1 = 2;           // [2] x0 / max0 staged in TMEM       (512 epilogue arrivals)
@@ -60,14 +60,15 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 // kCfg: 0 = any layout (scalar loads, run-time feature map)
 //       1 = car / early-fusion rows: c_raw 5, absolute xyz, no distance, row stride % 4 == 0, 16-byte aligned
 //       2 = ego (lately fusion) rows: c_raw 11, absolute xyz, no distance, even row stride, 8-byte aligned
-template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 1; };
-template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8; };
-template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12; };
+//   nreg  = floats of a row staged per slot, depth = rows in flight per producer thread (cp.async ring of depth + 1 stages)
+template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 24, depth = 3; };
+template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8, depth = 7; };
+template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12, depth = 7; };
 
 struct SmemPlan {   // float offsets into dynamic shared memory
-  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, idx, out, rows, ints, total_bytes;
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, row, out, rows, ints, total_bytes;
 };
-__host__ __device__ inline SmemPlan smem_plan(int k0, int layers) {
+__host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int depth) {
   SmemPlan S{};
   const int n0 = layers == 2 ? kHidden : kCout;
   int o = 0;
@@ -86,7 +87,9 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers) {
     S.prm_a1 = o; o += kCout;
     S.prm_b1 = o; o += kCout;
   }
-  S.idx = o; o += kIdxBufs * kSegRows * kGroup;   // row numbers, [buffer][slot][pillar]
+  S.ent = o; o += kEntRing * kGroup * 2;          // work-list entries, [group ring][pillar] (8 bytes each)
+  S.idx = o; o += (depth + 1) * kGroup;           // row numbers, [slot ring][pillar]
+  S.row = o; o += (depth + 1) * nreg * kGroup;    // staged rows, [slot ring][16/8/4-byte chunk][pillar]
   S.out = o; o += kGroup * kOutLd;                // output staging tile (coalesced pillar_features rows)
   S.rows = o; o += kRowRing * kGroup;             // output row (pillar rank) / long-pillar index of each lane
   S.ints = o; o += 80;                            // 8 mbarriers | tmem base | group prefix | list counts | list offsets
@@ -113,7 +116,7 @@ pfn_slot_kernel(const TcArgs A) {
   const int n_raw = kCfg ? RowCfg<kCfg>::n_raw : A.n_raw;
   const int raw_col0 = kCfg ? 1 : A.raw_col0;
   const bool with_dist = kCfg ? false : (A.with_distance != 0);
-  const SmemPlan SP = smem_plan(k0, kLayers);
+  const SmemPlan SP = smem_plan(k0, kLayers, NREG, RowCfg<kCfg>::depth);
   const int tid = threadIdx.x, warp = tid >> 5;
   int* const s_idx = reinterpret_cast<int*>(smem + SP.idx);
   float* const s_out = smem + SP.out;
@@ -229,206 +232,206 @@ pfn_slot_kernel(const TcArgs A) {
   } else if (warp >= kProdWarp0) {
     // =====================================================================================================
     // producers (register budget raised with what the other roles gave back to the CTA pool)
+    //
+    // A producer thread owns TMEM lane p, i.e. pillar p of every group of this CTA, and walks the CTA's slots in
+    // order.  Everything it needs arrives through a software pipeline of cp.async copies that it issues itself and
+    // that only it reads back (no cross-thread synchronisation), DEPTH slots apart per stage:
+    //   cursor A  work-list entry of a group             -> s_ent   (DEPTH + 1 groups ahead of cursor B)
+    //   cursor B  row number of slot t + 2 * DEPTH       -> s_idx   (needs its group's entry)
+    //   cursor C  point row of slot t + DEPTH            -> s_row   (needs its row number)
+    //   cursor D  slot t: features -> TF32 hi / lo -> tensor memory (A operand of layer 0)
+    // One commit group per slot and a single cp.async.wait_group<DEPTH - 1> make everything issued DEPTH or more
+    // iterations ago visible, which is exactly what cursors B, C and D read.  DEPTH rows (32 bytes each) are in
+    // flight per thread, 128 threads per SM: enough outstanding gathers to cover HBM latency.
     // =====================================================================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    constexpr int DEPTH = RowCfg<kCfg>::depth;
+    constexpr int STAGES = DEPTH + 1;
     const int p = tid - kEpiThreads;                       // pillar of the group == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    struct Ent { int r, off, len, li; bool valid; };
-    auto fetch = [&](int w, int4& raw) {
-      int q;
-      const int list = list_of(w, q);
-      const int e = (w - s_pre[q]) * kGroup + p;
-      raw = make_int4(0, 0, 0, -1);
-      if (e < s_cnt[list]) {
-        if (list == kSegList) {
-          raw = __ldg(A.seg_table + e);
-          raw.w = 1;
-        } else {
-          const unsigned long long v = __ldg(A.lists + s_loff[list] + e);
-          raw.x = (int)(v & 0xffffffffull); raw.y = (int)(v >> 32); raw.w = 0;
-        }
-      }
-    };
-    auto decode = [&](const int4& raw, Ent& E) {
-      E.valid = raw.w >= 0;
-      E.r = -1; E.off = 0; E.len = 0; E.li = -1;
-      if (raw.w == 1) { E.off = raw.x; E.len = raw.y; E.li = raw.z; }
-      else if (raw.w == 0) unpack_entry(((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x, E.r, E.off, E.len);
-    };
-    auto issue_idx = [&](const Ent& E, int w, int b) {
-      if (E.valid) {
-        bool sg;
-        const int slots = slots_of(w, sg);
-        int* dst = s_idx + b * (kSegRows * kGroup) + p;
-        for (int j = 0; j < slots; ++j) cp_async4(dst + j * kGroup, A.sorted_idx + E.off + min(j, E.len - 1));
-      }
-    };
-    // xyz of up to 8 rows of a pillar (loads only: summed later, in ascending row order)
-    auto load_xyz8 = [&](const Ent& E, const int* idx, int j0, float (&vx)[8], float (&vy)[8], float (&vz)[8]) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        if (E.valid && j0 + t < E.len) {
-          const float* row = A.points + (int64_t)idx[(j0 + t) * kGroup] * A.stride;
-          if (kCfg == 1) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(row));
-            vx[t] = v.y; vy[t] = v.z; vz[t] = v.w;
-          } else {
-            vx[t] = __ldg(row + 1); vy[t] = __ldg(row + 2); vz[t] = __ldg(row + 3);
-          }
-        }
-      }
-    };
-    // scatter_mean = sum in ascending row order / count (dynamic_pillar_vfe.py:110); first 8 rows already in registers
-    auto finish_mean = [&](const Ent& E, const int* idx, bool is_seg, const float (&vx)[8], const float (&vy)[8],
-                           const float (&vz)[8], float& mx, float& my, float& mz) {
-      mx = my = mz = 0.f;
-      if (!E.valid) return;
-      if (is_seg) {
-        const float4 m = __ldg(A.long_mean + E.li);
-        mx = m.x; my = m.y; mz = m.z;
-        return;
-      }
-      float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        if (t < E.len) { sx = __fadd_rn(sx, vx[t]); sy = __fadd_rn(sy, vy[t]); sz = __fadd_rn(sz, vz[t]); }
-      for (int j0 = 8; j0 < E.len; j0 += 8) {
-        float wx[8], wy[8], wz[8];
-        load_xyz8(E, idx, j0, wx, wy, wz);
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (j0 + t < E.len) { sx = __fadd_rn(sx, wx[t]); sy = __fadd_rn(sy, wy[t]); sz = __fadd_rn(sz, wz[t]); }
-      }
-      const float cnt = (float)E.len;
-      mx = __fdiv_rn(sx, cnt); my = __fdiv_rn(sy, cnt); mz = __fdiv_rn(sz, cnt);
-      if (A.mean_out) {
-        float* m = A.mean_out + (int64_t)E.r * 3;
-        m[0] = mx; m[1] = my; m[2] = mz;
-      }
-    };
+    unsigned long long* const s_ent = reinterpret_cast<unsigned long long*>(smem + SP.ent);
+    float* const s_row = smem + SP.row;
+    constexpr unsigned long long kNoEntry = ~0ull;
+    const int n_cols = kCfg ? NREG : A.c_raw;              // generic layout: columns 1 .. c_raw are staged
 
-    // ---- prime the prefetch pipeline: entries of groups 0..2, row numbers of groups 0..1, mean of group 0 ----
-    Ent cur, nxt, nn;
-    cur.valid = nxt.valid = nn.valid = false;
-    cur.r = nxt.r = nn.r = -1; cur.off = nxt.off = nn.off = 0; cur.len = nxt.len = nn.len = 0; cur.li = nxt.li = nn.li = -1;
-    const int w0 = blockIdx.x;
-    {
-      int4 raw;
-      if (w0 < total) { fetch(w0, raw); decode(raw, cur); issue_idx(cur, w0, 0); }
-      cp_async_commit();
-      if (w0 + G < total) { fetch(w0 + G, raw); decode(raw, nxt); issue_idx(nxt, w0 + G, 1); }
-      cp_async_commit();
-      if (w0 + 2 * G < total) { fetch(w0 + 2 * G, raw); decode(raw, nn); }
-    }
-    float mean_x = 0.f, mean_y = 0.f, mean_z = 0.f;
-    if (w0 < total) {
-      cp_async_wait<1>();
+    struct Cursor { int w, j, slots, gi; };               // work item, slot inside it, its slot count, group counter
+    auto cur_init = [&](Cursor& c) {
+      c.w = blockIdx.x; c.j = 0; c.gi = 0;
       bool sg;
-      slots_of(w0, sg);
-      float vx[8], vy[8], vz[8];
-      load_xyz8(cur, s_idx + p, 0, vx, vy, vz);
-      finish_mean(cur, s_idx + p, sg, vx, vy, vz, mean_x, mean_y, mean_z);
-    }
-    uint32_t c0 = 0;
-    int ib = 0;                 // row-number buffer of the current group
-    int gi = 0;                 // group counter (ring index of s_rows)
-    float rw[NREG];
-    const float* rowp = A.points;
-    for (int w = w0; w < total; w += G, ++gi) {
-      bool is_seg, nseg = false;
-      const int slots = slots_of(w, is_seg);
-      const bool have_next = (w + G) < total;
-      if (have_next) slots_of(w + G, nseg);
-      const int* my_idx = s_idx + ib * (kSegRows * kGroup) + p;
-      const int ib1 = (ib + 1) % kIdxBufs, ib2 = (ib + 2) % kIdxBufs;
-      const int* nx_idx = s_idx + ib1 * (kSegRows * kGroup) + p;
-      const bool valid = cur.valid;
-      s_rows[(gi % kRowRing) * kGroup + p] = is_seg ? cur.li : cur.r;
-      // ---- prefetch for the following groups (all in flight while this group's slots are built) ----
-      int4 raw3 = make_int4(0, 0, 0, -1);
-      if (w + 2 * G < total) issue_idx(nn, w + 2 * G, ib2);       // row numbers of group g + 2
-      cp_async_commit();
-      if (w + 3 * G < total) fetch(w + 3 * G, raw3);              // entry of group g + 3
-      cp_async_wait<1>();                                         // row numbers of group g + 1 have landed
-      float vx[8], vy[8], vz[8];
-      if (have_next && !nseg) load_xyz8(nxt, nx_idx, 0, vx, vy, vz);   // rows of group g + 1 for its mean
+      c.slots = (c.w < total) ? slots_of(c.w, sg) : 1;
+    };
+    auto cur_next = [&](Cursor& c) -> bool {              // advance one slot; true when a new group starts
+      if (++c.j < c.slots) return false;
+      c.j = 0; c.w += G; ++c.gi;
+      bool sg;
+      c.slots = (c.w < total) ? slots_of(c.w, sg) : 1;
+      return true;
+    };
+    auto issue_entry = [&](int w, int gi) {               // cursor A
+      unsigned long long* dst = s_ent + (gi & (kEntRing - 1)) * kGroup + p;
+      bool ok = false;
+      if (w < total) {
+        int q;
+        const int list = list_of(w, q);
+        const int e = (w - s_pre[q]) * kGroup + p;
+        if (e < s_cnt[list]) { cp_async8(dst, A.lists + s_loff[list] + e); ok = true; }
+      }
+      if (!ok) *dst = kNoEntry;
+    };
+    auto entry_of = [&](int gi) { return s_ent[(gi & (kEntRing - 1)) * kGroup + p]; };
 
-      auto load_row = [&](const int* idx, int j, bool ok) {
-        if (!ok) return;
-        rowp = A.points + (int64_t)idx[j * kGroup] * A.stride;
+    // ---- prologue: fill the pipeline (entries, then row numbers, then rows), each stage after the previous landed ----
+    int ga_w = blockIdx.x, ga_gi = 0;                      // cursor A
+    Cursor cb, cc, cd;
+    cur_init(cb); cur_init(cc); cur_init(cd);
+    unsigned long long eb = kNoEntry, ec = kNoEntry, ed = kNoEntry;   // cached entries of the cursors' groups
+    // Cursor A stays DEPTH + 1 groups ahead of cursor B's group: an entry requested in the iteration after B entered
+    // group Y - DEPTH - 1 is committed DEPTH iterations before B can enter group Y (every group has at least one slot).
+    auto step_a = [&](int b_gi) {
+      while (ga_gi <= b_gi + DEPTH + 1) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
+    };
+    auto step_b = [&](int slot) {                          // row number of cursor B's slot -> s_idx[slot ring]
+      if (eb != kNoEntry) {
+        int r, off, len;
+        unpack_entry(eb, r, off, len);
+        cp_async4(s_idx + (slot % STAGES) * kGroup + p, A.sorted_idx + off + min(cb.j, len - 1));
+      }
+      if (cur_next(cb)) eb = entry_of(cb.gi);
+    };
+    auto step_c = [&](int slot) {                          // row of cursor C's slot -> s_row[slot ring]
+      if (ec != kNoEntry) {
+        const int idx = s_idx[(slot % STAGES) * kGroup + p];
+        const float* row = A.points + (int64_t)idx * A.stride;
+        float* dst = s_row + (slot % STAGES) * (NREG * kGroup);
         if (kCfg == 1) {
-          const float4 v0 = __ldg(reinterpret_cast<const float4*>(rowp));
-          const float4 v1 = __ldg(reinterpret_cast<const float4*>(rowp) + 1);
+          cp_async16(dst + p * 4, row);
+          cp_async16(dst + 4 * kGroup + p * 4, row + 4);
+        } else if (kCfg == 2) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) cp_async8(dst + c * 2 * kGroup + p * 2, row + 2 * c);
+        } else {
+          for (int c = 0; c < n_cols; ++c) cp_async4(dst + c * kGroup + p, row + 1 + c);
+        }
+      }
+      if (cur_next(cc)) ec = entry_of(cc.gi);
+    };
+    int sb = 0, sc = 0;                                    // absolute slot numbers of cursors B and C
+    // entries of the first 2 * DEPTH + 2 groups (everything cursor B can reach during the prologue) - one round trip
+    while (ga_gi < 2 * DEPTH + 2) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
+    cp_async_commit();
+    cp_async_wait<0>();
+    eb = entry_of(0); ec = eb; ed = eb;
+    for (int t = 0; t < DEPTH; ++t) step_b(sb++);          // row numbers of slots 0 .. DEPTH - 1 - one round trip
+    cp_async_commit();
+    cp_async_wait<0>();
+    // rows of slots 0 .. DEPTH - 1 and row numbers of slots DEPTH .. 2 * DEPTH - 1, one commit group per slot: cursor D
+    // is at slot 0, C at DEPTH, B at 2 * DEPTH, with DEPTH commit groups pending exactly as in the steady state
+    // (at most DEPTH + 1 row numbers are live, which is the size of their ring)
+    for (int t = 0; t < DEPTH; ++t) { step_b(sb++); step_c(sc++); cp_async_commit(); }
+
+    auto mean_of = [&](unsigned long long e, bool is_seg) -> float4 {
+      if (e == kNoEntry) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r = (int)(e & 0x1fffffffull);
+      return __ldg((is_seg ? A.long_mean : A.mean) + r);
+    };
+    auto seg_of = [&](int w) { bool sg = false; if (w < total) slots_of(w, sg); return sg; };
+    // pillar means: this group's, the next group's and the one after (register prefetch, two groups ahead)
+    float4 m0 = mean_of(ed, seg_of(cd.w));
+    float4 m1 = mean_of(entry_of(1), seg_of(cd.w + G));
+    float4 m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t c0 = 0;
+    int sd = 0;                                            // absolute slot number of cursor D
+    bool new_group = true;
+    const int n_feat = n_raw + (with_dist ? 7 : 6);
+    while (cd.w < total) {
+      // ---- pipeline upkeep: one entry / row number / row request per slot ----
+      cp_async_wait<DEPTH - 1>();                          // everything issued DEPTH or more slots ago has landed
+      step_a(cb.gi);
+      step_b(sb++);
+      step_c(sc++);
+      cp_async_commit();
+      const bool valid = ed != kNoEntry;
+      if (new_group) {
+        // entries of the next two groups were requested at least 2 * DEPTH slots ago
+        const bool is_seg = seg_of(cd.w);
+        m2 = mean_of(entry_of(cd.gi + 2), seg_of(cd.w + 2 * G));
+        const int r = valid ? (int)(ed & 0x1fffffffull) : -1;
+        s_rows[(cd.gi % kRowRing) * kGroup + p] = r;      // pillar rank, or long-pillar index of a segment
+        if (A.mean_out && valid && !is_seg) {
+          float* m = A.mean_out + (int64_t)r * 3;
+          m[0] = m0.x; m[1] = m0.y; m[2] = m0.z;
+        }
+      }
+      // ---- this slot's row: shared memory -> registers ----
+      float rw[NREG];
+      {
+        const float* src = s_row + (sd % STAGES) * (NREG * kGroup);
+        if (kCfg == 1) {
+          const float4 v0 = ld4(src + p * 4), v1 = ld4(src + 4 * kGroup + p * 4);
           rw[0] = v0.x; rw[1] = v0.y; rw[2] = v0.z; rw[3] = v0.w; rw[4] = v1.x; rw[5] = v1.y; rw[6] = v1.z; rw[7] = v1.w;
         } else if (kCfg == 2) {
 #pragma unroll
           for (int c = 0; c < 6; ++c) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(rowp) + c);
+            const float2 v = *reinterpret_cast<const float2*>(src + c * 2 * kGroup + p * 2);
             rw[2 * c] = v.x; rw[2 * c + 1] = v.y;
           }
         }
-      };
-      if (w == w0) load_row(my_idx, 0, valid);                    // later groups: fetched at the end of the previous group
-
-      for (int j = 0; j < slots; ++j) {
-        // ---- features of this slot's row (dynamic_pillar_vfe.py:111-126) ----
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (valid) {
-          if (kCfg) { x = rw[1]; y = rw[2]; z = rw[3]; }
-          else { x = __ldg(rowp + 1); y = __ldg(rowp + 2); z = __ldg(rowp + 3); }
-        }
-        float ed[7];
-        ed[0] = __fsub_rn(x, mean_x);                                              // f_cluster (:111)
-        ed[1] = __fsub_rn(y, mean_y);
-        ed[2] = __fsub_rn(z, mean_z);
-        const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
-        const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
-        ed[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
-        ed[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
-        ed[5] = __fsub_rn(z, A.g.z_offset);
-        ed[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
-        const int n_feat = n_raw + (with_dist ? 7 : 6);
-        // A0[c0 & 1] is free once the layer-0 MMA that read it two ops ago has completed
-        const uint32_t b = c0 & 1;
-        if (c0 >= 2) { mbar_wait(&bars[kBarD0 + b], ((c0 - 2) >> 1) & 1); tc_fence_after_sync(); }
-        const uint32_t dh = tmem + kColA0 + b * 64 + lane_base, dl = dh + 32;
-#pragma unroll
-        for (int cc = 0; cc < kMaxCin; cc += 8) {
-          if (cc < k0) {
-            float hi[8], lo[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int f = cc + t;
-              float val = 0.f;
-              if (valid) {
-                if (f < n_raw) {
-                  if (kCfg) val = rw[(1 + f) < NREG ? (1 + f) : (NREG - 1)];
-                  else val = __ldg(rowp + raw_col0 + f);
-                } else if (f < n_feat) {
-                  const int d = f - n_raw;
-                  val = d == 0 ? ed[0] : d == 1 ? ed[1] : d == 2 ? ed[2] : d == 3 ? ed[3] : d == 4 ? ed[4] : d == 5 ? ed[5] : ed[6];
-                }
-              }
-              split_tf32(val, hi[t], lo[t]);
-            }
-            tmem_st8(dh + cc, hi);
-            tmem_st8(dl + cc, lo);
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive(&bars[kBarA0 + b]);
-        ++c0;
-        // ---- next row: this group's next slot, or slot 0 of the next group ----
-        if (j + 1 < slots) load_row(my_idx, j + 1, valid);
-        else if (have_next) load_row(nx_idx, 0, nxt.valid);
       }
-      // ---- rotate: mean of the next group from the rows fetched above ----
-      if (have_next) finish_mean(nxt, nx_idx, nseg, vx, vy, vz, mean_x, mean_y, mean_z);
-      cur = nxt; nxt = nn;
-      decode(raw3, nn);
-      ib = ib1;
+      const float* gsrc = s_row + (sd % STAGES) * (NREG * kGroup) + p;   // generic layout: column c at gsrc[(c - 1) * kGroup]
+      // ---- features of this slot's row (dynamic_pillar_vfe.py:111-126) ----
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (valid) {
+        if (kCfg) { x = rw[1]; y = rw[2]; z = rw[3]; }
+        else { x = gsrc[0]; y = gsrc[kGroup]; z = gsrc[2 * kGroup]; }
+      }
+      float ed_[7];
+      ed_[0] = __fsub_rn(x, m0.x);                                               // f_cluster (:111)
+      ed_[1] = __fsub_rn(y, m0.y);
+      ed_[2] = __fsub_rn(z, m0.z);
+      const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
+      const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
+      ed_[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
+      ed_[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
+      ed_[5] = __fsub_rn(z, A.g.z_offset);
+      ed_[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
+      // A0[c0 & 1] is free once the layer-0 MMA that read it two ops ago has completed
+      const uint32_t b = c0 & 1;
+      if (c0 >= 2) { mbar_wait(&bars[kBarD0 + b], ((c0 - 2) >> 1) & 1); tc_fence_after_sync(); }
+      const uint32_t dh = tmem + kColA0 + b * 64 + lane_base, dl = dh + 32;
+#pragma unroll
+      for (int cc8 = 0; cc8 < kMaxCin; cc8 += 8) {
+        if (cc8 < k0) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int f = cc8 + t;
+            float val = 0.f;
+            if (valid) {
+              if (f < n_raw) {
+                if (kCfg) val = rw[(1 + f) < NREG ? (1 + f) : (NREG - 1)];
+                else val = gsrc[(raw_col0 - 1 + f) * kGroup];
+              } else if (f < n_feat) {
+                const int d = f - n_raw;
+                val = d == 0 ? ed_[0] : d == 1 ? ed_[1] : d == 2 ? ed_[2] : d == 3 ? ed_[3] : d == 4 ? ed_[4] : d == 5 ? ed_[5] : ed_[6];
+              }
+            }
+            split_tf32(val, hi[t], lo[t]);
+          }
+          tmem_st8(dh + cc8, hi);
+          tmem_st8(dl + cc8, lo);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars[kBarA0 + b]);
+      ++c0; ++sd;
+      new_group = cur_next(cd);
+      if (new_group) {
+        ed = entry_of(cd.gi);
+        m0 = m1; m1 = m2;
+      }
     }
+    cp_async_wait<0>();
   } else {
     // =====================================================================================================
     // epilogue
@@ -781,7 +784,7 @@ namespace pcp {
 
 template <int kLayers, int kCfg>
 static int launch_cfg(const TcArgs& a, int64_t n_points, cudaStream_t stream) {
-  const SmemPlan SP = smem_plan(kCfg ? RowCfg<kCfg>::k0 : a.k0, kLayers);
+  const SmemPlan SP = smem_plan(kCfg ? RowCfg<kCfg>::k0 : a.k0, kLayers, RowCfg<kCfg>::nreg, RowCfg<kCfg>::depth);
   PCP_CUDA(cudaFuncSetAttribute(pfn_slot_kernel<kLayers, kCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP.total_bytes));
   // upper bound of the group count: every list may end in a partial group
   const int64_t groups = n_points / kGroup + kNumLists;

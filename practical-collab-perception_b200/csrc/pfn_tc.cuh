@@ -51,14 +51,14 @@ struct TcArgs {
   const float* points;
   int64_t stride;
   pcp_grid g;
-  int c_in, n_raw, raw_col0, with_distance, k0, num_layers;
+  int c_in, c_raw, n_raw, raw_col0, with_distance, k0, num_layers;
   const float* params;
   const int32_t* hdr;
   const int32_t* seg_off;
   const int32_t* sorted_idx;
   const unsigned long long* lists;
   ListOffsets lo;
-  const int4* seg_table;
+  const float4* mean;
   const float4* long_mean;
   unsigned* long_acc;
   const int4* long_table;

@@ -10,10 +10,11 @@
 //                       the first sorted position of its points, voxel_coords and the counts;
 //                       and bins the pillars by length into the work lists the PFN kernel consumes;
 //   3. place          : counting-sort scatter of the row numbers + the point->pillar map (unq_inv);
-//   4. sort_*         : row numbers inside each pillar are put in ascending order so that every
-//                       later per-pillar sum runs in the reference CPU path's order (deterministic);
-//                       launched on the dense per-class lists (thread / warp / CTA per pillar);
-//                       long pillars also get their mean and their segment table here.
+//   4. pillar_prep    : row numbers inside each pillar are put in ascending order so that every
+//                       per-pillar sum runs in the reference CPU path's order (deterministic), and the
+//                       pillar mean (scatter_mean, :110) is evaluated in that order; one launch over the
+//                       dense per-class lists (thread / warp / CTA per pillar); long pillars also get
+//                       their segment entries here.
 // No kernel synchronises with the host; the only data-dependent size (P) is read back by the caller.
 #include "common.cuh"
 
@@ -250,145 +251,214 @@ place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within
 }
 
 // ------------------------------------------------------------------------------------------------
-// 4. ascending row order inside every pillar, on the dense per-class lists
+// 4. pillar preparation: ascending row order inside every pillar + the pillar mean, ONE launch.
+//    Row numbers inside a pillar arrive in atomic order; they are put in ascending order so that every
+//    per-pillar sum runs in the reference CPU path's order (index_add_ walks the rows sequentially), which
+//    makes scatter_mean (dynamic_pillar_vfe.py:110) bit-reproducible.  The mean is evaluated here - one
+//    sequential fp32 sum per pillar, divided by the count - so that the PFN kernel streams each row once.
+//    Every CTA walks three work lists in turn (longest items first):
+//      long  pillars (> kSegRows rows)  : one CTA per pillar, rank-by-counting / bitonic sort in shared memory;
+//                                         also emits the pillar's segment entries and arms its max accumulator
+//      mid   pillars (9 .. 32 rows)     : one warp per pillar, rank by counting through shuffles
+//      short pillars (1 .. 8 rows)      : one thread per pillar, 19-comparator network in registers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cswap(int32_t& a, int32_t& b) {
   const int32_t lo = min(a, b), hi = max(a, b);
   a = lo; b = hi;
 }
 
-// classes 1..5 (2..8 points): one thread per pillar, 19-comparator network in registers
-__global__ void __launch_bounds__(256)
-sort_short_kernel(int32_t* __restrict__ sorted_idx, const unsigned long long* __restrict__ lists, const ListOffsets lo,
-                  const int32_t* __restrict__ hdr) {
-  int pre[6];
-  pre[0] = 0;
-#pragma unroll
-  for (int k = 1; k <= 5; ++k) pre[k] = pre[k - 1] + hdr[kHdrListCount + k];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < pre[5]; w += gridDim.x * blockDim.x) {
-    int k = 1;
-#pragma unroll
-    for (int q = 1; q < 5; ++q) k += (w >= pre[q]) ? 1 : 0;
-    int r, off, n;
-    unpack_entry(__ldg(lists + lo.off[k] + (w - pre[k - 1])), r, off, n);
-    int32_t v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
-    // optimal 8-input sorting network (19 compare-exchanges)
-    cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
-    cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
-    cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
-    cswap(v[1], v[5]); cswap(v[2], v[6]);
-    cswap(v[1], v[4]); cswap(v[3], v[6]);
-    cswap(v[2], v[4]); cswap(v[3], v[5]);
-    cswap(v[3], v[4]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < n) sorted_idx[off + j] = v[j];
+template <bool kVec4>
+__device__ __forceinline__ void load_xyz(const float* __restrict__ points, int64_t stride, int32_t idx, float& x, float& y,
+                                         float& z) {
+  const float* row = points + (int64_t)idx * stride;
+  if (kVec4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+    x = v.y; y = v.z; z = v.w;
+  } else {
+    x = __ldg(row + 1); y = __ldg(row + 2); z = __ldg(row + 3);
   }
 }
 
-// classes 6..9 (9..32 points): one warp per pillar, rank by counting
-__global__ void __launch_bounds__(256)
-sort_mid_kernel(int32_t* __restrict__ sorted_idx, const unsigned long long* __restrict__ lists, const ListOffsets lo,
-                const int32_t* __restrict__ hdr) {
-  int pre[5];
-  pre[0] = 0;
-#pragma unroll
-  for (int k = 6; k <= 9; ++k) pre[k - 5] = pre[k - 6] + hdr[kHdrListCount + k];
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < pre[4]; w += gridDim.x * wpb) {
-    int q = 0;
-#pragma unroll
-    for (int t = 1; t < 4; ++t) q += (w >= pre[t]) ? 1 : 0;
-    int r, off, n;
-    unpack_entry(__ldg(lists + lo.off[6 + q] + (w - pre[q])), r, off, n);
-    const int32_t v = (lane < n) ? sorted_idx[off + lane] : 0x7fffffff;
-    int rank = 0;
-    for (int i = 0; i < n; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
-    __syncwarp();
-    if (lane < n) sorted_idx[off + rank] = v;
-  }
-}
+constexpr int kPrepThreads = 256;
+constexpr int kCountSortMax = 1024;   // long pillars up to this size are ranked by counting, larger ones by a bitonic network
 
-// long pillars (> kSegRows points): one CTA per pillar.  Bitonic index sort in shared memory (<= kBigSegMax
-// rows; larger pillars keep their arrival order: their sums stay within tolerance but are not order-canonical),
-// the pillar mean (sequential fp32 sum in ascending row order for <= kBigSegMax rows, dynamic_pillar_vfe.py:110),
-// its segment table entries and its running-max accumulator.
-__global__ void __launch_bounds__(256)
-sort_long_kernel(const float* __restrict__ points, int64_t stride, const int32_t* __restrict__ hdr,
-                 const int4* __restrict__ long_table, int32_t* __restrict__ sorted_idx, int4* __restrict__ seg_table,
-                 float4* __restrict__ long_mean, unsigned* __restrict__ long_acc) {
+template <bool kVec4>
+__global__ void __launch_bounds__(kPrepThreads)
+pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32_t* __restrict__ hdr,
+                   unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
+                   int32_t* __restrict__ sorted_idx, float4* __restrict__ mean, float4* __restrict__ long_mean,
+                   unsigned* __restrict__ long_acc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* s = reinterpret_cast<int32_t*>(smem_raw);                  // [kBigSegMax]
-  float* sx = reinterpret_cast<float*>(smem_raw) + kBigSegMax;         // [3][kBigSegMax]
+  int32_t* s = reinterpret_cast<int32_t*>(smem_raw);                  // [kBigSegMax] row numbers
+  float* sx = reinterpret_cast<float*>(smem_raw) + kBigSegMax;         // [3][kBigSegMax] xyz (first used as sort scratch)
   __shared__ float s_red[3][8];
+  __shared__ int32_t s_warp[kPrepThreads / 32][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---------------- long pillars ----------------
   const int nlong = hdr[kHdrLongCount];
-  const int tid = threadIdx.x;
   for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
     const int4 e = long_table[li];
-    const int32_t off = e.y, n = e.z, sb = e.w;
+    const int32_t r = e.x, off = e.y, n = e.z, sb = e.w;
     const int nseg = (n + kSegRows - 1) / kSegRows;
-    for (int i = tid; i < nseg; i += blockDim.x)
-      seg_table[sb + i] = make_int4(off + i * kSegRows, min(kSegRows, n - i * kSegRows), li, 0);
-    for (int i = tid; i < 96; i += blockDim.x) long_acc[(int64_t)li * 96 + i] = kAccInit;
+    for (int i = tid; i < nseg; i += kPrepThreads)
+      lists[lo.off[kSegList] + sb + i] = pack_entry(li, off + i * kSegRows, min(kSegRows, n - i * kSegRows));
+    for (int i = tid; i < 96; i += kPrepThreads) long_acc[(int64_t)li * 96 + i] = kAccInit;
     float mx, my, mz;
     if (n <= kBigSegMax) {
-      int m = 64;
-      while (m < n) m <<= 1;
-      for (int i = tid; i < m; i += blockDim.x) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
-      __syncthreads();
-      for (int k = 2; k <= m; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = tid; i < m; i += blockDim.x) {
-            const int p = i ^ j;
-            if (p > i) {
-              const int32_t a = s[i], b = s[p];
-              const bool up = (i & k) == 0;
-              if ((a > b) == up) { s[i] = b; s[p] = a; }
-            }
+      if (n <= kCountSortMax) {
+        int32_t* s2 = reinterpret_cast<int32_t*>(sx);
+        const int n4 = (n + 3) & ~3;
+        for (int i = tid; i < n4; i += kPrepThreads) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+        __syncthreads();
+        for (int i = tid; i < n; i += kPrepThreads) {
+          const int32_t v = s[i];
+          int rank = 0;
+          for (int j = 0; j < n4; j += 4) {
+            const int4 t = *reinterpret_cast<const int4*>(s + j);
+            rank += (t.x < v) + (t.y < v) + (t.z < v) + (t.w < v);
           }
-          __syncthreads();
+          s2[rank] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += kPrepThreads) s[i] = s2[i];
+        __syncthreads();
+      } else {
+        int m = 2048;
+        while (m < n) m <<= 1;
+        for (int i = tid; i < m; i += kPrepThreads) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1) {
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < m; i += kPrepThreads) {
+              const int p = i ^ j;
+              if (p > i) {
+                const int32_t a = s[i], b = s[p];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { s[i] = b; s[p] = a; }
+              }
+            }
+            __syncthreads();
+          }
         }
       }
-      for (int i = tid; i < n; i += blockDim.x) {
+      for (int i = tid; i < n; i += kPrepThreads) {
         const int32_t idx = s[i];
         sorted_idx[off + i] = idx;
-        const float* row = points + (int64_t)idx * stride;
-        sx[i] = __ldg(row + 1); sx[kBigSegMax + i] = __ldg(row + 2); sx[2 * kBigSegMax + i] = __ldg(row + 3);
+        float x, y, z;
+        load_xyz<kVec4>(points, stride, idx, x, y, z);
+        sx[i] = x; sx[kBigSegMax + i] = y; sx[2 * kBigSegMax + i] = z;
       }
       __syncthreads();
-      if (tid < 3) {
-        const float* v = sx + tid * kBigSegMax;
+      if (tid < 96 && lane == 0) {
+        const float* v = sx + warp * kBigSegMax;          // warps 0, 1, 2: x, y, z
         float acc = 0.f;
         for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, v[i]);
-        s_red[tid][0] = __fdiv_rn(acc, (float)n);
+        s_red[warp][0] = __fdiv_rn(acc, (float)n);
       }
       __syncthreads();
       mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
     } else {
-      // giant pillar: strided partial sums + tree (deterministic for a given row order)
+      // giant pillar: arrival order, strided partial sums + tree (within tolerance, not order-canonical)
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-      for (int i = tid; i < n; i += blockDim.x) {
-        const float* row = points + (int64_t)sorted_idx[off + i] * stride;
-        a0 += __ldg(row + 1); a1 += __ldg(row + 2); a2 += __ldg(row + 3);
+      for (int i = tid; i < n; i += kPrepThreads) {
+        float x, y, z;
+        load_xyz<kVec4>(points, stride, sorted_idx[off + i], x, y, z);
+        a0 += x; a1 += y; a2 += z;
       }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d); a2 += __shfl_xor_sync(0xffffffffu, a2, d);
       }
-      if ((tid & 31) == 0) { s_red[0][tid >> 5] = a0; s_red[1][tid >> 5] = a1; s_red[2][tid >> 5] = a2; }
+      if (lane == 0) { s_red[0][warp] = a0; s_red[1][warp] = a1; s_red[2][warp] = a2; }
       __syncthreads();
       if (tid < 3) {
         float acc = 0.f;
-        for (int w = 0; w < 8; ++w) acc += s_red[tid][w];
+        for (int w = 0; w < kPrepThreads / 32; ++w) acc += s_red[tid][w];
         s_red[tid][0] = __fdiv_rn(acc, (float)n);
       }
       __syncthreads();
       mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
     }
-    if (tid == 0) long_mean[li] = make_float4(mx, my, mz, 0.f);
+    if (tid == 0) {
+      long_mean[li] = make_float4(mx, my, mz, 0.f);
+      mean[r] = make_float4(mx, my, mz, 0.f);
+    }
     __syncthreads();
+  }
+
+  // ---------------- mid pillars: classes 6..9 (9..32 rows), one warp per pillar ----------------
+  {
+    int pre[5];
+    pre[0] = 0;
+#pragma unroll
+    for (int k = 6; k <= 9; ++k) pre[k - 5] = pre[k - 6] + hdr[kHdrListCount + k];
+    constexpr int wpb = kPrepThreads / 32;
+    for (int w = blockIdx.x * wpb + warp; w < pre[4]; w += gridDim.x * wpb) {
+      int q = 0;
+#pragma unroll
+      for (int t = 1; t < 4; ++t) q += (w >= pre[t]) ? 1 : 0;
+      int r, off, n;
+      unpack_entry(__ldg(lists + lo.off[6 + q] + (w - pre[q])), r, off, n);
+      const int32_t v = (lane < n) ? sorted_idx[off + lane] : 0x7fffffff;
+      int rank = 0;
+      for (int i = 0; i < n; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
+      if (lane < n) { sorted_idx[off + rank] = v; s_warp[warp][rank] = v; }
+      __syncwarp();
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (lane < n) load_xyz<kVec4>(points, stride, s_warp[warp][lane], x, y, z);
+      // lanes 0, 1, 2 run the sequential sums of x, y, z
+      float mine = 0.f;
+      for (int i = 0; i < n; ++i) {
+        const float vx = __shfl_sync(0xffffffffu, x, i), vy = __shfl_sync(0xffffffffu, y, i), vz = __shfl_sync(0xffffffffu, z, i);
+        mine = __fadd_rn(mine, lane == 0 ? vx : (lane == 1 ? vy : vz));
+      }
+      mine = __fdiv_rn(mine, (float)n);
+      const float my = __shfl_sync(0xffffffffu, mine, 1), mz = __shfl_sync(0xffffffffu, mine, 2);
+      if (lane == 0) mean[r] = make_float4(mine, my, mz, 0.f);
+      __syncwarp();
+    }
+  }
+
+  // ---------------- short pillars: classes 0..5 (1..8 rows), one thread per pillar ----------------
+  {
+    int pre[7];
+    pre[0] = 0;
+#pragma unroll
+    for (int k = 0; k <= 5; ++k) pre[k + 1] = pre[k] + hdr[kHdrListCount + k];
+    for (int w = blockIdx.x * kPrepThreads + tid; w < pre[6]; w += gridDim.x * kPrepThreads) {
+      int k = 0;
+#pragma unroll
+      for (int q = 1; q <= 5; ++q) k += (w >= pre[q]) ? 1 : 0;
+      int r, off, n;
+      unpack_entry(__ldg(lists + lo.off[k] + (w - pre[k])), r, off, n);
+      int32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
+      if (n > 1) {
+        // optimal 8-input sorting network (19 compare-exchanges)
+        cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
+        cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
+        cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
+        cswap(v[1], v[5]); cswap(v[2], v[6]);
+        cswap(v[1], v[4]); cswap(v[3], v[6]);
+        cswap(v[2], v[4]); cswap(v[3], v[5]);
+        cswap(v[3], v[4]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < n) sorted_idx[off + j] = v[j];
+      }
+      float x[8], y[8], z[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < n) load_xyz<kVec4>(points, stride, v[j], x[j], y[j], z[j]);
+      float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < n) { ax = __fadd_rn(ax, x[j]); ay = __fadd_rn(ay, y[j]); az = __fadd_rn(az, z[j]); }
+      const float cnt = (float)n;
+      mean[r] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 0.f);
+    }
   }
 }
 
@@ -445,23 +515,20 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
     PCP_LAUNCH_CHECK("place_kernel");
   }
   if (n_points > 0) {
-    const int64_t want = (n_points / 2 + 255) / 256;
-    const unsigned blocks = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
-    sort_short_kernel<<<blocks, 256, 0, stream>>>(W.sorted_idx, W.lists, L.lo, W.hdr);
-    PCP_LAUNCH_CHECK("sort_short_kernel");
-    const int64_t want_mid = (n_points / 9 + 7) / 8;
-    const unsigned blocks_mid = (unsigned)(want_mid < 148 * 8 ? (want_mid > 0 ? want_mid : 1) : 148 * 8);
-    sort_mid_kernel<<<blocks_mid, 256, 0, stream>>>(W.sorted_idx, W.lists, L.lo, W.hdr);
-    PCP_LAUNCH_CHECK("sort_mid_kernel");
-    const int64_t want_long = n_points / (kSegRows + 1);
-    if (want_long > 0) {
-      const size_t smem = sizeof(int32_t) * kBigSegMax * 4;
-      PCP_CUDA(cudaFuncSetAttribute(sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const unsigned blocks_long = (unsigned)(want_long < 296 ? want_long : 296);
-      sort_long_kernel<<<blocks_long, 256, smem, stream>>>(points, row_stride, W.hdr, W.long_table, W.sorted_idx,
-                                                           W.seg_table, W.long_mean, W.long_acc);
-      PCP_LAUNCH_CHECK("sort_long_kernel");
+    const size_t smem = sizeof(int32_t) * kBigSegMax * 4;
+    const int64_t want = (n_points + kPrepThreads - 1) / kPrepThreads;
+    const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    const bool vec4 = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    if (vec4) {
+      PCP_CUDA(cudaFuncSetAttribute(pillar_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pillar_prep_kernel<true><<<blocks, kPrepThreads, smem, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
+                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc);
+    } else {
+      PCP_CUDA(cudaFuncSetAttribute(pillar_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pillar_prep_kernel<false><<<blocks, kPrepThreads, smem, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
+                                                                       W.sorted_idx, W.mean, W.long_mean, W.long_acc);
     }
+    PCP_LAUNCH_CHECK("pillar_prep_kernel");
   }
   return 0;
 }
