@@ -55,6 +55,25 @@ constexpr int kBarA1 = 2;           // [2] x0 / max0 staged in TMEM       (512 e
 constexpr int kBarD0 = 4;           // [2] layer-0 accumulator ready      (tcgen05.commit)
 constexpr int kBarD1 = 6;           // [2] layer-1 / hoist accumulator ready
 
+// ---- optional per-role event trace of CTA 0 (debug build only: make dbg; tools/pfn_timing.py) ----
+#ifdef PCP_PFN_TIMING
+constexpr int kTraceCap = 8192;
+__device__ long long g_trace[3][kTraceCap][2];
+__device__ int g_trace_n[3];
+#define TRACE_DECL(cond) const bool trace_on_ = (blockIdx.x == 0) && (cond); int trace_cnt_ = 0;
+#define TRACE(role, id)                                                                          \
+  do {                                                                                           \
+    if (trace_on_ && trace_cnt_ < kTraceCap) {                                                   \
+      g_trace[role][trace_cnt_][0] = (id); g_trace[role][trace_cnt_][1] = clock64(); ++trace_cnt_; \
+    }                                                                                            \
+  } while (0)
+#define TRACE_END(role) do { if (trace_on_) g_trace_n[role] = trace_cnt_; } while (0)
+#else
+#define TRACE_DECL(cond)
+#define TRACE(role, id)
+#define TRACE_END(role)
+#endif
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // kCfg: 0 = any layout (scalar loads, run-time feature map)
@@ -193,9 +212,12 @@ pfn_slot_kernel(const TcArgs A) {
     const uint32_t sw1bh = smem_u32(smem + SP.w1bh), sw1bl = smem_u32(smem + SP.w1bl);
     const uint32_t idesc0 = idesc_tf32_m128(N0), idesc1 = idesc_tf32_m128(kCout);
     uint32_t c0 = 0, c1 = 0;      // layer-0 ops / layer-1-type ops issued so far
+    TRACE_DECL((tid & 31) == 0)
     auto issue_m0 = [&]() {
       const uint32_t b = c0 & 1;
+      TRACE(0, 20);
       mbar_wait(&bars[kBarA0 + b], (c0 >> 1) & 1);
+      TRACE(0, 21);
       if (kLayers == 1 && c0 >= 2) mbar_wait(&bars[kBarA1 + b], ((c0 - 2) >> 1) & 1);   // D0[b] consumed by the epilogue
       tc_fence_after_sync();
       if (elect_one_sync()) {
@@ -208,7 +230,9 @@ pfn_slot_kernel(const TcArgs A) {
     };
     auto issue_m1 = [&](uint32_t wh, uint32_t wl) {
       const uint32_t b = c1 & 1;
+      TRACE(0, 22);
       mbar_wait(&bars[kBarA1 + b], (c1 >> 1) & 1);
+      TRACE(0, 23);
       tc_fence_after_sync();
       if (elect_one_sync()) {
         mma_3xtf32_ts(tmem + kColD1 + b * 64, tmem + kColA1 + b * 64, tmem + kColA1 + b * 64 + 32, wh, wl, kCout, kHidden / 8,
@@ -228,7 +252,9 @@ pfn_slot_kernel(const TcArgs A) {
         if (kLayers == 2) issue_m1(sw1ah, sw1al);
       }
       if (kLayers == 2 && !is_seg) issue_m1(sw1bh, sw1bl);     // hoist: max0 . W1[:, 32:]^T once per pillar
+      TRACE(0, 24);
     }
+    TRACE_END(0);
   } else if (warp >= kProdWarp0) {
     // =====================================================================================================
     // producers (register budget raised with what the other roles gave back to the CTA pool)
@@ -343,9 +369,13 @@ pfn_slot_kernel(const TcArgs A) {
     int sd = 0;                                            // absolute slot number of cursor D
     bool new_group = true;
     const int n_feat = n_raw + (with_dist ? 7 : 6);
+    TRACE_DECL(p == 0)
+    TRACE(1, 9);
     while (cd.w < total) {
       // ---- pipeline upkeep: one entry / row number / row request per slot ----
-      cp_async_wait<DEPTH - 1>();                          // everything issued DEPTH or more slots ago has landed
+      TRACE(1, new_group ? 13 : 10);
+      cp_async_wait<DEPTH - 1>();
+      TRACE(1, 14);                          // everything issued DEPTH or more slots ago has landed
       step_a(cb.gi);
       step_b(sb++);
       step_c(sc++);
@@ -396,7 +426,9 @@ pfn_slot_kernel(const TcArgs A) {
       ed_[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
       // A0[c0 & 1] is free once the layer-0 MMA that read it two ops ago has completed
       const uint32_t b = c0 & 1;
+      TRACE(1, 11);
       if (c0 >= 2) { mbar_wait(&bars[kBarD0 + b], ((c0 - 2) >> 1) & 1); tc_fence_after_sync(); }
+      TRACE(1, 12);
       const uint32_t dh = tmem + kColA0 + b * 64 + lane_base, dl = dh + 32;
 #pragma unroll
       for (int cc8 = 0; cc8 < kMaxCin; cc8 += 8) {
@@ -432,6 +464,7 @@ pfn_slot_kernel(const TcArgs A) {
       }
     }
     cp_async_wait<0>();
+    TRACE_END(1);
   } else {
     // =====================================================================================================
     // epilogue
@@ -448,9 +481,12 @@ pfn_slot_kernel(const TcArgs A) {
     int pend_gi = 0;
     uint32_t e1_k = 0;         // op whose accumulator the next E1 reads
 
+    TRACE_DECL(tid == 0)
     auto e0 = [&]() {          // BN + ReLU, running max0, x0 -> TMEM as the A operand of layer 1
       const uint32_t b = c0 & 1;
+      TRACE(2, 30);
       mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
+      TRACE(2, 31);
       tc_fence_after_sync();
       uint32_t rr[8];
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -475,11 +511,14 @@ pfn_slot_kernel(const TcArgs A) {
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(&bars[kBarA1 + b1]);
+      TRACE(2, 32);
       ++c0; ++c1;
     };
     auto ld_acc16 = [&](uint32_t k, uint32_t (&rr)[16]) {       // this thread's 16 columns of layer-1-type op k
       const uint32_t b = k & 1;
+      TRACE(2, 33);
       mbar_wait(&bars[kBarD1 + b], (k >> 1) & 1);
+      TRACE(2, 34);
       tc_fence_after_sync();
       tmem_ld16_nowait(tmem + kColD1 + b * 64 + lane_base + 16 * q, rr);
       tmem_ld_wait();
@@ -525,7 +564,9 @@ pfn_slot_kernel(const TcArgs A) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) m1[i] = __fadd_rn(m1[i], __uint_as_float(rr[i]));
       }
+      TRACE(2, 37);
       write_out(pend_gi);
+      TRACE(2, 38);
       pend_fin = false;
     };
 
@@ -605,6 +646,7 @@ pfn_slot_kernel(const TcArgs A) {
       }
     }
     if (pend_fin) finish_group();
+    TRACE_END(2);
   }
   // ---- teardown ----
   tc_fence_before_sync();
@@ -778,6 +820,16 @@ extern "C" int pcp_selftest_umma_cycles(int32_t mode, int32_t n, int32_t ksteps,
   PCP_LAUNCH_CHECK("umma_cycles_kernel");
   return 0;
 }
+
+#ifdef PCP_PFN_TIMING
+// debug: copies the event trace of CTA 0 (3 roles x kTraceCap x (id, clock)) and the 3 event counts to host memory
+extern "C" int pcp_debug_read_timing(long long* trace_host, int* counts_host) {
+  PCP_CUDA(cudaDeviceSynchronize());
+  PCP_CUDA(cudaMemcpyFromSymbol(trace_host, g_trace, sizeof(long long) * 3 * kTraceCap * 2));
+  PCP_CUDA(cudaMemcpyFromSymbol(counts_host, g_trace_n, sizeof(int) * 3));
+  return 0;
+}
+#endif
 
 // launched from pfn.cu
 namespace pcp {

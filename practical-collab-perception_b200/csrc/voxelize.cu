@@ -280,34 +280,117 @@ __device__ __forceinline__ void load_xyz(const float* __restrict__ points, int64
 }
 
 constexpr int kPrepThreads = 256;
-constexpr int kCountSortMax = 1024;   // long pillars up to this size are ranked by counting, larger ones by a bitonic network
+constexpr int kPrepWarps = kPrepThreads / 32;
+constexpr int kWarpLongMax = 128;     // long pillars up to this size are handled by ONE WARP (no CTA barrier)
+constexpr int kCountSortMax = 1024;   // CTA path: ranked by counting up to this size, bitonic network above
+constexpr int kSumChunk = 256;        // CTA path: rows staged per step of the sequential sum
+
+// Shared memory of a CTA (24 KB, static): either 8 per-warp regions of 3 x 256 words (warp path), or the CTA path's
+// row-number array [kBigSegMax] followed by 2048 words of scratch (counting-sort output / double-buffered xyz chunks).
+struct PrepSmem {
+  union {
+    int32_t warp_words[kPrepWarps][3][kWarpLongMax];
+    struct { int32_t s[kBigSegMax]; int32_t scratch[2048]; } cta;
+  };
+};
 
 template <bool kVec4>
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, 5)
 pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32_t* __restrict__ hdr,
                    unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
                    int32_t* __restrict__ sorted_idx, float4* __restrict__ mean, float4* __restrict__ long_mean,
                    unsigned* __restrict__ long_acc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* s = reinterpret_cast<int32_t*>(smem_raw);                  // [kBigSegMax] row numbers
-  float* sx = reinterpret_cast<float*>(smem_raw) + kBigSegMax;         // [3][kBigSegMax] xyz (first used as sort scratch)
+  __shared__ __align__(16) PrepSmem sm;
   __shared__ float s_red[3][8];
-  __shared__ int32_t s_warp[kPrepThreads / 32][32];
+  __shared__ int s_big[64];             // long pillars of this CTA's share that need the whole CTA
+  __shared__ int s_nbig;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_nbig = 0;
+  __syncthreads();
 
-  // ---------------- long pillars ----------------
+  // ---------------- long pillars, warp path (33 .. kWarpLongMax rows): one warp per pillar ----------------
   const int nlong = hdr[kHdrLongCount];
-  for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+  for (int li = blockIdx.x * kPrepWarps + warp; li < nlong; li += gridDim.x * kPrepWarps) {
     const int4 e = long_table[li];
     const int32_t r = e.x, off = e.y, n = e.z, sb = e.w;
     const int nseg = (n + kSegRows - 1) / kSegRows;
-    for (int i = tid; i < nseg; i += kPrepThreads)
+    for (int i = lane; i < nseg; i += 32)
       lists[lo.off[kSegList] + sb + i] = pack_entry(li, off + i * kSegRows, min(kSegRows, n - i * kSegRows));
-    for (int i = tid; i < 96; i += kPrepThreads) long_acc[(int64_t)li * 96 + i] = kAccInit;
+    for (int i = lane; i < 96; i += 32) long_acc[(int64_t)li * 96 + i] = kAccInit;
+    if (n > kWarpLongMax) {
+      if (lane == 0) { const int k = atomicAdd(&s_nbig, 1); if (k < 64) s_big[k] = li; }
+      continue;
+    }
+    int32_t* s0 = sm.warp_words[warp][0];
+    int32_t* s1 = sm.warp_words[warp][1];
+    const int n4 = (n + 3) & ~3;
+    int32_t v[kWarpLongMax / 32];
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      v[k] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+      if (i < n4) s0[i] = v[k];
+    }
+    __syncwarp();
+    int rank[kWarpLongMax / 32];
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) rank[k] = 0;
+    for (int j = 0; j < n4; j += 4) {
+      const int4 t = *reinterpret_cast<const int4*>(s0 + j);
+#pragma unroll
+      for (int k = 0; k < kWarpLongMax / 32; ++k)
+        rank[k] += (t.x < v[k]) + (t.y < v[k]) + (t.z < v[k]) + (t.w < v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k)
+      if (k * 32 + lane < n) s1[rank[k]] = v[k];
+    __syncwarp();
+    float* fx = reinterpret_cast<float*>(sm.warp_words[warp][0]);
+    float* fy = reinterpret_cast<float*>(sm.warp_words[warp][2]);
+    float x[kWarpLongMax / 32], y[kWarpLongMax / 32], z[kWarpLongMax / 32];
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      if (i < n) {
+        const int32_t idx = s1[i];
+        sorted_idx[off + i] = idx;
+        load_xyz<kVec4>(points, stride, idx, x[k], y[k], z[k]);
+      }
+    }
+    __syncwarp();                       // every lane has read its sorted row numbers: s1 can be reused for z
+    float* fz = reinterpret_cast<float*>(sm.warp_words[warp][1]);
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      if (i < n) { fx[i] = x[k]; fy[i] = y[k]; fz[i] = z[k]; }
+    }
+    __syncwarp();
+    float acc = 0.f;
+    if (lane < 3) {
+      const float* src = lane == 0 ? fx : (lane == 1 ? fy : fz);
+      for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, src[i]);
+      acc = __fdiv_rn(acc, (float)n);
+    }
+    const float my = __shfl_sync(0xffffffffu, acc, 1), mz = __shfl_sync(0xffffffffu, acc, 2);
+    if (lane == 0) {
+      long_mean[li] = make_float4(acc, my, mz, 0.f);
+      mean[r] = make_float4(acc, my, mz, 0.f);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---------------- long pillars, CTA path (> kWarpLongMax rows) ----------------
+  const int nbig = min(s_nbig, 64);
+  for (int bi = 0; bi < nbig; ++bi) {
+    const int li = s_big[bi];
+    const int4 e = long_table[li];
+    const int32_t r = e.x, off = e.y, n = e.z;
+    int32_t* s = sm.cta.s;
     float mx, my, mz;
     if (n <= kBigSegMax) {
       if (n <= kCountSortMax) {
-        int32_t* s2 = reinterpret_cast<int32_t*>(sx);
+        int32_t* s2 = sm.cta.scratch;
         const int n4 = (n + 3) & ~3;
         for (int i = tid; i < n4; i += kPrepThreads) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
         __syncthreads();
@@ -342,20 +425,27 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
           }
         }
       }
-      for (int i = tid; i < n; i += kPrepThreads) {
-        const int32_t idx = s[i];
-        sorted_idx[off + i] = idx;
-        float x, y, z;
-        load_xyz<kVec4>(points, stride, idx, x, y, z);
-        sx[i] = x; sx[kBigSegMax + i] = y; sx[2 * kBigSegMax + i] = z;
+      // sequential sums in ascending row order, rows staged kSumChunk at a time (double buffered: one barrier per chunk)
+      float* ch = reinterpret_cast<float*>(sm.cta.scratch);      // [2][3][kSumChunk]
+      float acc = 0.f;
+      for (int c0 = 0; c0 < n; c0 += kSumChunk) {
+        float* buf = ch + ((c0 / kSumChunk) & 1) * (3 * kSumChunk);
+        const int i = c0 + tid;
+        if (i < n) {
+          const int32_t idx = s[i];
+          sorted_idx[off + i] = idx;
+          float x, y, z;
+          load_xyz<kVec4>(points, stride, idx, x, y, z);
+          buf[tid] = x; buf[kSumChunk + tid] = y; buf[2 * kSumChunk + tid] = z;
+        }
+        __syncthreads();
+        if (warp < 3 && lane == 0) {
+          const float* src = buf + warp * kSumChunk;
+          const int m = min(kSumChunk, n - c0);
+          for (int q = 0; q < m; ++q) acc = __fadd_rn(acc, src[q]);
+        }
       }
-      __syncthreads();
-      if (tid < 96 && lane == 0) {
-        const float* v = sx + warp * kBigSegMax;          // warps 0, 1, 2: x, y, z
-        float acc = 0.f;
-        for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, v[i]);
-        s_red[warp][0] = __fdiv_rn(acc, (float)n);
-      }
+      if (warp < 3 && lane == 0) s_red[warp][0] = __fdiv_rn(acc, (float)n);
       __syncthreads();
       mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
     } else {
@@ -374,7 +464,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
       __syncthreads();
       if (tid < 3) {
         float acc = 0.f;
-        for (int w = 0; w < kPrepThreads / 32; ++w) acc += s_red[tid][w];
+        for (int w = 0; w < kPrepWarps; ++w) acc += s_red[tid][w];
         s_red[tid][0] = __fdiv_rn(acc, (float)n);
       }
       __syncthreads();
@@ -393,7 +483,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
     pre[0] = 0;
 #pragma unroll
     for (int k = 6; k <= 9; ++k) pre[k - 5] = pre[k - 6] + hdr[kHdrListCount + k];
-    constexpr int wpb = kPrepThreads / 32;
+    constexpr int wpb = kPrepWarps;
     for (int w = blockIdx.x * wpb + warp; w < pre[4]; w += gridDim.x * wpb) {
       int q = 0;
 #pragma unroll
@@ -403,10 +493,11 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
       const int32_t v = (lane < n) ? sorted_idx[off + lane] : 0x7fffffff;
       int rank = 0;
       for (int i = 0; i < n; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
-      if (lane < n) { sorted_idx[off + rank] = v; s_warp[warp][rank] = v; }
+      int32_t* sw = sm.warp_words[warp][0];
+      if (lane < n) { sorted_idx[off + rank] = v; sw[rank] = v; }
       __syncwarp();
       float x = 0.f, y = 0.f, z = 0.f;
-      if (lane < n) load_xyz<kVec4>(points, stride, s_warp[warp][lane], x, y, z);
+      if (lane < n) load_xyz<kVec4>(points, stride, sw[lane], x, y, z);
       // lanes 0, 1, 2 run the sequential sums of x, y, z
       float mine = 0.f;
       for (int i = 0; i < n; ++i) {
@@ -515,19 +606,15 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
     PCP_LAUNCH_CHECK("place_kernel");
   }
   if (n_points > 0) {
-    const size_t smem = sizeof(int32_t) * kBigSegMax * 4;
     const int64_t want = (n_points + kPrepThreads - 1) / kPrepThreads;
-    const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    const unsigned blocks = (unsigned)(want < 148 * 5 ? want : 148 * 5);
     const bool vec4 = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
-    if (vec4) {
-      PCP_CUDA(cudaFuncSetAttribute(pillar_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      pillar_prep_kernel<true><<<blocks, kPrepThreads, smem, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
-                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc);
-    } else {
-      PCP_CUDA(cudaFuncSetAttribute(pillar_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      pillar_prep_kernel<false><<<blocks, kPrepThreads, smem, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
-                                                                       W.sorted_idx, W.mean, W.long_mean, W.long_acc);
-    }
+    if (vec4)
+      pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
+                                                                   W.sorted_idx, W.mean, W.long_mean, W.long_acc);
+    else
+      pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
+                                                                    W.sorted_idx, W.mean, W.long_mean, W.long_acc);
     PCP_LAUNCH_CHECK("pillar_prep_kernel");
   }
   return 0;

@@ -1,4 +1,8 @@
-"""Debug: per-phase clock64 trace of one CTA of the PFN kernel (needs `make -C csrc dbg`: libpcp_b200_dbg.so)."""
+"""Debug: per-role event trace (clock64) of CTA 0 of the PFN kernel.  Needs `make -C .../csrc dbg` (libpcp_b200_dbg.so).
+    python tools/pfn_timing.py [first_event] [n_events]
+Event ids - MMA warp: 20/21 before/after wait A0 (layer-0 operand), 22/23 before/after wait A1, 24 group done;
+producer: 13/10 slot start (13 = first slot of a group), 14 rows landed, 11/12 before/after wait for the A0 buffer;
+epilogue: 30/31 before/after wait D0, 32 layer-0 epilogue done, 33/34 before/after wait D1, 37 hoist added, 38 rows written."""
 import ctypes as C
 import os
 import sys
@@ -27,25 +31,30 @@ for _ in range(3):
     fe.voxelize(pts, 8, out, want_point_pillar=False)
     fe.pfn(pts, out)
 torch.cuda.synchronize()
-buf = (C.c_longlong * 8192)()
+CAP = 8192
+buf = np.zeros((3, CAP, 2), dtype=np.int64)
+cnt = np.zeros(3, dtype=np.int32)
 lib = _lib.load()
-lib.pcp_debug_read_timing.argtypes = [C.c_void_p]
-print("rc", lib.pcp_debug_read_timing(buf))
-a = np.frombuffer(buf, dtype=np.int64).reshape(2, 1024, 4)
+lib.pcp_debug_read_timing.argtypes = [C.c_void_p, C.c_void_p]
+print("rc", lib.pcp_debug_read_timing(buf.ctypes.data, cnt.ctypes.data), "events", cnt)
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-for t in range(2):
-    ev = a[t]
-    ev = ev[ev[:, 1] > 0]
-    print(f"thread {'0' if t == 0 else '200'}: {len(ev)} events, total {int(ev[-1,1]-ev[0,1])} cycles")
-    prev = None
+n_ev = int(sys.argv[2]) if len(sys.argv) > 2 else 120
+t0 = min(int(buf[r, 0, 1]) for r in range(3) if cnt[r] > 0)
+names = ["mma", "producer", "epilogue"]
+for r in range(3):
+    ev = buf[r, :min(int(cnt[r]), CAP)]
+    if len(ev) == 0:
+        continue
+    print(f"== {names[r]}: {len(ev)} events, span {int(ev[-1, 1] - ev[0, 1])} cycles")
+    # time spent between consecutive events, summed by (from id -> to id)
+    agg = {}
+    for i in range(1, len(ev)):
+        k = (int(ev[i - 1, 0]), int(ev[i, 0]))
+        a = agg.setdefault(k, [0, 0])
+        a[0] += int(ev[i, 1] - ev[i - 1, 1]); a[1] += 1
+    for k, (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"   {k[0]:3d} -> {k[1]:3d}: total {tot:9d} cycles over {n:5d} = {tot / n:8.1f} each")
     line = []
-    for i in range(len(ev)):
-        sid, clk = int(ev[i, 0]), int(ev[i, 1])
-        d = 0 if prev is None else clk - prev
-        prev = clk
-        if sid >= 100 and sid not in (101, 102, 103, 104, 105, 106, 107, 108, 110) or sid == 1:
-            if line and i > first and i < first + 400:
-                print(" ".join(line))
-            line = []
-        line.append(f"[{sid}]+{d}")
+    for i in range(first, min(first + n_ev, len(ev))):
+        line.append(f"[{int(ev[i, 0])}]@{int(ev[i, 1]) - t0}")
     print(" ".join(line))
