@@ -88,6 +88,8 @@ constexpr int kHdrInts = 64;
 constexpr int kHdrScanTicket = 16;   // dynamic tile id of the scan
 constexpr int kHdrListCount = 32;    // [32, 32 + kNumLists): entries in each list
 constexpr int kHdrLongCount = 48;    // long pillars
+constexpr int kHdrBigCount = 49;     // long pillars above kWarpLongMax rows (handled by a whole CTA in pillar_prep_kernel)
+constexpr int kWarpLongMax = 128;    // long pillars up to this size are ordered by ONE warp
 constexpr int kScanTileCells = 2048; // cells per scan tile (256 threads x 8)
 constexpr unsigned kAccInit = 0x007fffffu;   // ordered-int encoding of -inf
 
@@ -104,7 +106,7 @@ __host__ __device__ inline void unpack_entry(unsigned long long e, int& r, int& 
 }
 
 struct WsLayout {
-  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, lists, mean, long_table, long_mean, long_acc, total;
+  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, lists, mean, long_table, big_list, long_mean, long_acc, total;
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
   int64_t cells, cap, scan_tiles, seg_cap, long_cap;
   ListOffsets lo;
@@ -141,6 +143,7 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   o = align_up(o + sizeof(unsigned long long) * (size_t)(lo + 64), 256);
   L.mean = o;        o = align_up(o + 16 * (size_t)(L.cap + 1), 256);
   L.long_table = o;  o = align_up(o + 16 * (size_t)L.long_cap, 256);
+  L.big_list = o;    o = align_up(o + 4 * (size_t)L.long_cap, 256);
   L.long_mean = o;   o = align_up(o + 16 * (size_t)L.long_cap, 256);
   L.long_acc = o;    o = align_up(o + sizeof(uint32_t) * 96 * (size_t)L.long_cap, 256);
   L.total = o;
@@ -158,6 +161,7 @@ struct WsView {
   unsigned long long* lists;
   float4* mean;
   int4* long_table;
+  int32_t* big_list;
   float4* long_mean;
   unsigned* long_acc;
 };
@@ -175,6 +179,7 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.lists = reinterpret_cast<unsigned long long*>(p + L.lists);
   v.mean = reinterpret_cast<float4*>(p + L.mean);
   v.long_table = reinterpret_cast<int4*>(p + L.long_table);
+  v.big_list = reinterpret_cast<int32_t*>(p + L.big_list);
   v.long_mean = reinterpret_cast<float4*>(p + L.long_mean);
   v.long_acc = reinterpret_cast<unsigned*>(p + L.long_acc);
   return v;

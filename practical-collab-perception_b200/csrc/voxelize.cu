@@ -16,6 +16,8 @@
 //                       dense per-class lists (thread / warp / CTA per pillar); long pillars also get
 //                       their segment entries here.
 // No kernel synchronises with the host; the only data-dependent size (P) is read back by the caller.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pcp {
@@ -79,7 +81,7 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
                   unsigned long long* __restrict__ state, int32_t* __restrict__ hdr,
                   int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
                   int32_t* __restrict__ pillar_count, unsigned long long* __restrict__ lists, const ListOffsets lo,
-                  int4* __restrict__ long_table, int64_t scan_tiles) {
+                  int4* __restrict__ long_table, int32_t* __restrict__ big_list, int64_t scan_tiles) {
   __shared__ int s_tile;
   __shared__ int s_cls[kNumClasses], s_cls_base[kNumClasses];
   __shared__ unsigned long long s_warp[kScanThreads / 32];
@@ -207,6 +209,7 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
           const int li = atomicAdd(&hdr[kHdrLongCount], 1);
           const int sb = atomicAdd(&hdr[kHdrListCount + kSegList], nseg);
           long_table[li] = make_int4(r, off, c[j], sb);
+          if (c[j] > kWarpLongMax) big_list[atomicAdd(&hdr[kHdrBigCount], 1)] = li;
         }
         excl += ((unsigned long long)(uint32_t)c[j] << 32) | 1ull;
       } else {
@@ -281,7 +284,7 @@ __device__ __forceinline__ void load_xyz(const float* __restrict__ points, int64
 
 constexpr int kPrepThreads = 256;
 constexpr int kPrepWarps = kPrepThreads / 32;
-constexpr int kWarpLongMax = 128;     // long pillars up to this size are handled by ONE WARP (no CTA barrier)
+
 constexpr int kCountSortMax = 1024;   // CTA path: ranked by counting up to this size, bitonic network above
 constexpr int kSumChunk = 256;        // CTA path: rows staged per step of the sequential sum
 
@@ -298,94 +301,23 @@ template <bool kVec4>
 __global__ void __launch_bounds__(kPrepThreads, 5)
 pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32_t* __restrict__ hdr,
                    unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
-                   int32_t* __restrict__ sorted_idx, float4* __restrict__ mean, float4* __restrict__ long_mean,
-                   unsigned* __restrict__ long_acc) {
+                   const int32_t* __restrict__ big_list, int32_t* __restrict__ sorted_idx, float4* __restrict__ mean,
+                   float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, int phase_mask) {
   __shared__ __align__(16) PrepSmem sm;
   __shared__ float s_red[3][8];
-  __shared__ int s_big[64];             // long pillars of this CTA's share that need the whole CTA
-  __shared__ int s_nbig;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_nbig = 0;
-  __syncthreads();
-
-  // ---------------- long pillars, warp path (33 .. kWarpLongMax rows): one warp per pillar ----------------
   const int nlong = hdr[kHdrLongCount];
-  for (int li = blockIdx.x * kPrepWarps + warp; li < nlong; li += gridDim.x * kPrepWarps) {
+
+  // ---------------- long pillars, CTA path (> kWarpLongMax rows) ----------------
+  const int nbig = (phase_mask & 1) ? hdr[kHdrBigCount] : 0;
+  for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+    const int li = big_list[bi];
     const int4 e = long_table[li];
     const int32_t r = e.x, off = e.y, n = e.z, sb = e.w;
     const int nseg = (n + kSegRows - 1) / kSegRows;
-    for (int i = lane; i < nseg; i += 32)
+    for (int i = tid; i < nseg; i += kPrepThreads)
       lists[lo.off[kSegList] + sb + i] = pack_entry(li, off + i * kSegRows, min(kSegRows, n - i * kSegRows));
-    for (int i = lane; i < 96; i += 32) long_acc[(int64_t)li * 96 + i] = kAccInit;
-    if (n > kWarpLongMax) {
-      if (lane == 0) { const int k = atomicAdd(&s_nbig, 1); if (k < 64) s_big[k] = li; }
-      continue;
-    }
-    int32_t* s0 = sm.warp_words[warp][0];
-    int32_t* s1 = sm.warp_words[warp][1];
-    const int n4 = (n + 3) & ~3;
-    int32_t v[kWarpLongMax / 32];
-#pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k) {
-      const int i = k * 32 + lane;
-      v[k] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
-      if (i < n4) s0[i] = v[k];
-    }
-    __syncwarp();
-    int rank[kWarpLongMax / 32];
-#pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k) rank[k] = 0;
-    for (int j = 0; j < n4; j += 4) {
-      const int4 t = *reinterpret_cast<const int4*>(s0 + j);
-#pragma unroll
-      for (int k = 0; k < kWarpLongMax / 32; ++k)
-        rank[k] += (t.x < v[k]) + (t.y < v[k]) + (t.z < v[k]) + (t.w < v[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k)
-      if (k * 32 + lane < n) s1[rank[k]] = v[k];
-    __syncwarp();
-    float* fx = reinterpret_cast<float*>(sm.warp_words[warp][0]);
-    float* fy = reinterpret_cast<float*>(sm.warp_words[warp][2]);
-    float x[kWarpLongMax / 32], y[kWarpLongMax / 32], z[kWarpLongMax / 32];
-#pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k) {
-      const int i = k * 32 + lane;
-      if (i < n) {
-        const int32_t idx = s1[i];
-        sorted_idx[off + i] = idx;
-        load_xyz<kVec4>(points, stride, idx, x[k], y[k], z[k]);
-      }
-    }
-    __syncwarp();                       // every lane has read its sorted row numbers: s1 can be reused for z
-    float* fz = reinterpret_cast<float*>(sm.warp_words[warp][1]);
-#pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k) {
-      const int i = k * 32 + lane;
-      if (i < n) { fx[i] = x[k]; fy[i] = y[k]; fz[i] = z[k]; }
-    }
-    __syncwarp();
-    float acc = 0.f;
-    if (lane < 3) {
-      const float* src = lane == 0 ? fx : (lane == 1 ? fy : fz);
-      for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, src[i]);
-      acc = __fdiv_rn(acc, (float)n);
-    }
-    const float my = __shfl_sync(0xffffffffu, acc, 1), mz = __shfl_sync(0xffffffffu, acc, 2);
-    if (lane == 0) {
-      long_mean[li] = make_float4(acc, my, mz, 0.f);
-      mean[r] = make_float4(acc, my, mz, 0.f);
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-
-  // ---------------- long pillars, CTA path (> kWarpLongMax rows) ----------------
-  const int nbig = min(s_nbig, 64);
-  for (int bi = 0; bi < nbig; ++bi) {
-    const int li = s_big[bi];
-    const int4 e = long_table[li];
-    const int32_t r = e.x, off = e.y, n = e.z;
+    for (int i = tid; i < 96; i += kPrepThreads) long_acc[(int64_t)li * 96 + i] = kAccInit;
     int32_t* s = sm.cta.s;
     float mx, my, mz;
     if (n <= kBigSegMax) {
@@ -477,6 +409,74 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
     __syncthreads();
   }
 
+  // ---------------- long pillars, warp path (33 .. kWarpLongMax rows): one warp per pillar ----------------
+  for (int li = blockIdx.x * kPrepWarps + warp; (phase_mask & 2) && li < nlong; li += gridDim.x * kPrepWarps) {
+    const int4 e = long_table[li];
+    const int32_t r = e.x, off = e.y, n = e.z, sb = e.w;
+    if (n > kWarpLongMax) continue;
+    const int nseg = (n + kSegRows - 1) / kSegRows;
+    for (int i = lane; i < nseg; i += 32)
+      lists[lo.off[kSegList] + sb + i] = pack_entry(li, off + i * kSegRows, min(kSegRows, n - i * kSegRows));
+    for (int i = lane; i < 96; i += 32) long_acc[(int64_t)li * 96 + i] = kAccInit;
+    int32_t* s0 = sm.warp_words[warp][0];
+    int32_t* s1 = sm.warp_words[warp][1];
+    const int n4 = (n + 3) & ~3;
+    int32_t v[kWarpLongMax / 32];
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      v[k] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+      if (i < n4) s0[i] = v[k];
+    }
+    __syncwarp();
+    int rank[kWarpLongMax / 32];
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) rank[k] = 0;
+    for (int j = 0; j < n4; j += 4) {
+      const int4 t = *reinterpret_cast<const int4*>(s0 + j);
+#pragma unroll
+      for (int k = 0; k < kWarpLongMax / 32; ++k)
+        rank[k] += (t.x < v[k]) + (t.y < v[k]) + (t.z < v[k]) + (t.w < v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k)
+      if (k * 32 + lane < n) s1[rank[k]] = v[k];
+    __syncwarp();
+    float* fx = reinterpret_cast<float*>(sm.warp_words[warp][0]);
+    float* fy = reinterpret_cast<float*>(sm.warp_words[warp][2]);
+    float x[kWarpLongMax / 32], y[kWarpLongMax / 32], z[kWarpLongMax / 32];
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      if (i < n) {
+        const int32_t idx = s1[i];
+        sorted_idx[off + i] = idx;
+        load_xyz<kVec4>(points, stride, idx, x[k], y[k], z[k]);
+      }
+    }
+    __syncwarp();                       // every lane has read its sorted row numbers: s1 can be reused for z
+    float* fz = reinterpret_cast<float*>(sm.warp_words[warp][1]);
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      if (i < n) { fx[i] = x[k]; fy[i] = y[k]; fz[i] = z[k]; }
+    }
+    __syncwarp();
+    float acc = 0.f;
+    if (lane < 3) {
+      const float* src = lane == 0 ? fx : (lane == 1 ? fy : fz);
+      for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, src[i]);
+      acc = __fdiv_rn(acc, (float)n);
+    }
+    const float my = __shfl_sync(0xffffffffu, acc, 1), mz = __shfl_sync(0xffffffffu, acc, 2);
+    if (lane == 0) {
+      long_mean[li] = make_float4(acc, my, mz, 0.f);
+      mean[r] = make_float4(acc, my, mz, 0.f);
+    }
+    __syncwarp();
+  }
+
+
   // ---------------- mid pillars: classes 6..9 (9..32 rows), one warp per pillar ----------------
   {
     int pre[5];
@@ -484,7 +484,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
 #pragma unroll
     for (int k = 6; k <= 9; ++k) pre[k - 5] = pre[k - 6] + hdr[kHdrListCount + k];
     constexpr int wpb = kPrepWarps;
-    for (int w = blockIdx.x * wpb + warp; w < pre[4]; w += gridDim.x * wpb) {
+    for (int w = blockIdx.x * wpb + warp; (phase_mask & 4) && w < pre[4]; w += gridDim.x * wpb) {
       int q = 0;
 #pragma unroll
       for (int t = 1; t < 4; ++t) q += (w >= pre[t]) ? 1 : 0;
@@ -517,7 +517,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
     pre[0] = 0;
 #pragma unroll
     for (int k = 0; k <= 5; ++k) pre[k + 1] = pre[k] + hdr[kHdrListCount + k];
-    for (int w = blockIdx.x * kPrepThreads + tid; w < pre[6]; w += gridDim.x * kPrepThreads) {
+    for (int w = blockIdx.x * kPrepThreads + tid; (phase_mask & 8) && w < pre[6]; w += gridDim.x * kPrepThreads) {
       int k = 0;
 #pragma unroll
       for (int q = 1; q <= 5; ++q) k += (w >= pre[q]) ? 1 : 0;
@@ -597,7 +597,7 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   }
   scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
       W.cell, L.cells, grid->nx, grid->ny, W.scan_state, W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
-      W.lists, L.lo, W.long_table, L.scan_tiles);
+      W.lists, L.lo, W.long_table, W.big_list, L.scan_tiles);
   PCP_LAUNCH_CHECK("scan_cells_kernel");
   {
     const unsigned blocks = (unsigned)((n_points + 255) / 256);
@@ -609,12 +609,17 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
     const int64_t want = (n_points + kPrepThreads - 1) / kPrepThreads;
     const unsigned blocks = (unsigned)(want < 148 * 5 ? want : 148 * 5);
     const bool vec4 = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
-    if (vec4)
-      pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
-                                                                   W.sorted_idx, W.mean, W.long_mean, W.long_acc);
-    else
-      pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table,
-                                                                    W.sorted_idx, W.mean, W.long_mean, W.long_acc);
+    // PCP_PREP_SPLIT=1 (diagnostic): one launch per phase so that a launch list shows each phase's time
+    static const bool split = getenv("PCP_PREP_SPLIT") != nullptr;
+    for (int ph = 0; ph < (split ? 4 : 1); ++ph) {
+      const int mask = split ? (1 << ph) : 15;
+      if (vec4)
+        pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                     W.sorted_idx, W.mean, W.long_mean, W.long_acc, mask);
+      else
+        pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc, mask);
+    }
     PCP_LAUNCH_CHECK("pillar_prep_kernel");
   }
   return 0;
