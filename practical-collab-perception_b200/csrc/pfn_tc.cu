@@ -8,9 +8,9 @@
 // belongs to pillar p, so the per-pillar max - the reference's scatter_max - is an ELEMENTWISE max between
 // successive accumulators inside the thread that owns lane p: no cross-lane traffic, no shared-memory
 // transpose, no atomics.  Per slot:
-//   A0   gather the slot's rows, features (f_cluster / f_center need the pillar mean, computed per group in
-//        ascending row order), TF32 hi/lo split -> A0 panels in shared memory
-//   M0   D0[128 x 32] = A0 . W0^T                      (tcgen05.mma kind::tf32, SS, 3 MMAs per K step)
+//   A0   the slot's rows (gathered by cp.async), features (f_cluster needs the pillar mean, f_center the pillar's
+//        cell - both per-pillar values prepared by pillar_prep_kernel), TF32 hi/lo split -> A0 in tensor memory
+//   M0   D0[128 x 32] = A0 . W0^T                      (tcgen05.mma kind::tf32, 3 MMAs per K step)
 //   E0   TMEM -> regs: BN(eval)+ReLU -> x0; running max0; hi/lo split -> written BACK TO TENSOR MEMORY as the
 //        A operand of layer 1 (tcgen05.st): the N' x 32 activation never touches shared memory or HBM
 //   M1   D1[128 x 64] = x0 . W1[:, :32]^T              (A from TMEM, B from smem)
@@ -34,32 +34,41 @@ namespace pcp {
 using namespace umma;
 
 constexpr int kTcThreads = 256;     // threads of the self-test kernels
-// ---- roles of the PFN kernel (one persistent CTA per SM) ----
-constexpr int kEpiThreads = 512;    // epilogue threads: (pillar p = tid & 127, column quarter q = tid >> 7)
-constexpr int kProdThreads = 128;   // producers: one thread per pillar (TMEM lane) of the group
-constexpr int kProdWarp0 = kEpiThreads / 32;                   // 16
-constexpr int kMmaWarp = kProdWarp0 + kProdThreads / 32;      // 20
-constexpr int kPfnThreads = (kMmaWarp + 1) * 32;              // 672
+// ---- roles of the PFN kernel (one persistent CTA per SM, 25 warps) ----
+//   warps  0.. 7  E0: layer-0 epilogue      (pillar p = tid & 127, column half h = (tid >> 7) & 1)
+//   warps  8..15  E1: last-layer epilogue   (same mapping) + the output rows
+//   warps 16..23  producers: two sets of 128 threads (one thread per pillar); set s builds the slots of parity s
+//   warp  24      MMA issue
+constexpr int kE0Threads = 256;
+constexpr int kE1Threads = 256;
+constexpr int kProdSets = 2;
+constexpr int kProdThreads = kGroup * kProdSets;
+constexpr int kE1Warp0 = kE0Threads / 32;                          // 8
+constexpr int kProdWarp0 = kE1Warp0 + kE1Threads / 32;             // 16
+constexpr int kMmaWarp = kProdWarp0 + kProdThreads / 32;          // 24
+constexpr int kPfnThreads = (kMmaWarp + 1) * 32;                  // 800
 constexpr int kTmemCols = 512;
 // tensor-memory column map (everything double buffered: operand / accumulator b of op c is c & 1)
 constexpr uint32_t kColD0 = 0;      // layer-0 accumulators   [b * 64, +32)  (+64 for a single-layer PFN)
 constexpr uint32_t kColD1 = 128;    // layer-1 / hoist accumulators [128 + b * 64, +64)
 constexpr uint32_t kColA0 = 256;    // layer-0 A operand (features): hi at 256 + b * 64, lo 32 columns further (k0 <= 24)
 constexpr uint32_t kColA1 = 384;    // layer-1 A operand (x0 / max0): hi at 384 + b * 64, lo 32 columns further
-constexpr int kOutLd = 68;          // padded row of the output staging tile (conflict-free 16-byte accesses)
-constexpr int kRowRing = 8;         // ring of per-group output-row tables (producer runs a few groups ahead of the output)
-constexpr int kEntRing = 32;        // ring of per-group work-list entries (the entry cursor runs up to 3 * depth groups ahead)
+constexpr int kRowRing = 16;        // ring of per-group output-row tables (producers run a few groups ahead of the output)
+constexpr int kEntRing = 32;        // per producer set: ring of per-group work-list entries
 // mbarrier indices
-constexpr int kBarA0 = 0;           // [2] features staged in TMEM        (128 producer arrivals)
-constexpr int kBarA1 = 2;           // [2] x0 / max0 staged in TMEM       (512 epilogue arrivals)
-constexpr int kBarD0 = 4;           // [2] layer-0 accumulator ready      (tcgen05.commit)
-constexpr int kBarD1 = 6;           // [2] layer-1 / hoist accumulator ready
+constexpr int kBarA0 = 0;           // [2] features staged in TMEM          (128 arrivals: the producer set of that parity)
+constexpr int kBarA1 = 2;           // [2] x0 / max0 staged in TMEM         (256 arrivals: E0)
+constexpr int kBarD0 = 4;           // [2] layer-0 accumulator ready        (tcgen05.commit)
+constexpr int kBarD1 = 6;           // [2] layer-1 / hoist accumulator ready (tcgen05.commit)
+constexpr int kBarF1 = 8;           // [2] layer-1 accumulator consumed     (256 arrivals: E1)
+constexpr int kNumBars = 10;
 
 // ---- optional per-role event trace of CTA 0 (debug build only: make dbg; tools/pfn_timing.py) ----
 #ifdef PCP_PFN_TIMING
 constexpr int kTraceCap = 8192;
-__device__ long long g_trace[3][kTraceCap][2];
-__device__ int g_trace_n[3];
+constexpr int kTraceRoles = 5;      // mma, producer set 0, E0, E1, producer set 1
+__device__ long long g_trace[kTraceRoles][kTraceCap][2];
+__device__ int g_trace_n[kTraceRoles];
 #define TRACE_DECL(cond) const bool trace_on_ = (blockIdx.x == 0) && (cond); int trace_cnt_ = 0;
 #define TRACE(role, id)                                                                          \
   do {                                                                                           \
@@ -75,17 +84,21 @@ __device__ int g_trace_n[3];
 #endif
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_global_f4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
 
-// kCfg: 0 = any layout (scalar loads, run-time feature map)
+// kCfg: 0 = any layout (4-byte copies, run-time feature map)
 //       1 = car / early-fusion rows: c_raw 5, absolute xyz, no distance, row stride % 4 == 0, 16-byte aligned
 //       2 = ego (lately fusion) rows: c_raw 11, absolute xyz, no distance, even row stride, 8-byte aligned
 //   nreg  = floats of a row staged per slot, depth = rows in flight per producer thread (cp.async ring of depth + 1 stages)
-template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 24, depth = 3; };
-template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8, depth = 7; };
-template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12, depth = 7; };
+template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 24, depth = 2; };
+template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8, depth = 4; };
+template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12, depth = 4; };
 
 struct SmemPlan {   // float offsets into dynamic shared memory
-  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, row, out, rows, ints, total_bytes;
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, mean, row, rows, ints, total_bytes;
+  int ent_set, idx_set, mean_set, row_set;   // floats per producer set
 };
 __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int depth) {
   SmemPlan S{};
@@ -106,25 +119,29 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int 
     S.prm_a1 = o; o += kCout;
     S.prm_b1 = o; o += kCout;
   }
-  S.ent = o; o += kEntRing * kGroup * 2;          // work-list entries, [group ring][pillar] (8 bytes each)
-  S.idx = o; o += (depth + 1) * kGroup;           // row numbers, [slot ring][pillar]
-  S.row = o; o += (depth + 1) * nreg * kGroup;    // staged rows, [slot ring][16/8/4-byte chunk][pillar]
-  S.out = o; o += kGroup * kOutLd;                // output staging tile (coalesced pillar_features rows)
+  S.ent_set = kEntRing * kGroup * 2;            // work-list entries, [group ring][pillar] (8 bytes each)
+  S.idx_set = (depth + 1) * kGroup;             // row numbers, [slot ring][pillar]
+  S.mean_set = (depth + 1) * kGroup * 4;        // per-pillar mean + cell, [slot ring][pillar] (16 bytes each)
+  S.row_set = (depth + 1) * nreg * kGroup;      // staged rows, [slot ring][16/8/4-byte chunk][pillar]
+  S.ent = o; o += kProdSets * S.ent_set;
+  S.idx = o; o += kProdSets * S.idx_set;
+  S.mean = o; o += kProdSets * S.mean_set;
+  S.row = o; o += kProdSets * S.row_set;
   S.rows = o; o += kRowRing * kGroup;             // output row (pillar rank) / long-pillar index of each lane
-  S.ints = o; o += 80;                            // 8 mbarriers | tmem base | group prefix | list counts | list offsets
+  S.ints = o; o += 96;                            // 10 mbarriers | tmem base | group prefix | list counts | list offsets
   S.total_bytes = o * 4;
   return S;
 }
 
-// Persistent, warp-specialised kernel.  Three roles talk only through mbarriers:
-//   producers (4 warps, thread = pillar lane): prefetch the work-list entries and row numbers (cp.async), compute the
-//       pillar mean, gather each slot's row, build the feature vector and write its TF32 hi / lo parts to TMEM (A0);
+// Persistent, warp-specialised kernel.  The roles talk only through mbarriers:
+//   producers (2 x 4 warps, thread = pillar lane): gather each slot's row through a cp.async pipeline, build the feature
+//       vector and write its TF32 hi / lo parts to tensor memory (A0); set s owns the slots of parity s == buffer s;
 //   MMA warp: waits for "operand staged", issues the tcgen05.mma groups (layer 0 of the NEXT slot is queued in front
-//       of layer 1 of the current one, so the tensor pipe has work while the epilogue runs), commits to "accumulator ready";
-//   epilogue (16 warps, thread = pillar lane x column quarter): layer-0 epilogue (BN + ReLU, running max0, x0 back to
-//       TMEM as layer 1's A operand), layer-1 epilogue (running max), the per-pillar hoist and the output rows.
-// The issuing thread of a tcgen05.mma is back-pressured by the tensor pipe (measured 30-60 cycles per MMA), which is
-// why it owns a warp; shared-memory traffic is limited to the weight panels the MMAs read and the output staging tile.
+//       of layer 1 of the current one, so the tensor pipe has work while the epilogues run), commits to "accumulator ready";
+//   E0 (8 warps): BN + ReLU of the layer-0 accumulator, running max0, x0 back to TMEM as layer 1's A operand, and once
+//       per group max0 as the operand of the hoist;
+//   E1 (8 warps): running max of the layer-1 accumulators, the hoist result, BN + ReLU and the output rows (each thread
+//       owns 32 consecutive channels of its pillar: 128 contiguous bytes of pillar_features).
 template <int kLayers, int kCfg>
 __global__ void __launch_bounds__(kPfnThreads, 1)
 pfn_slot_kernel(const TcArgs A) {
@@ -137,12 +154,10 @@ pfn_slot_kernel(const TcArgs A) {
   const bool with_dist = kCfg ? false : (A.with_distance != 0);
   const SmemPlan SP = smem_plan(k0, kLayers, NREG, RowCfg<kCfg>::depth);
   const int tid = threadIdx.x, warp = tid >> 5;
-  int* const s_idx = reinterpret_cast<int*>(smem + SP.idx);
-  float* const s_out = smem + SP.out;
   int* const s_rows = reinterpret_cast<int*>(smem + SP.rows);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + SP.ints);
-  uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 16);
-  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 20);      // [kNumLists + 1] group prefix, processing order
+  uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 20);
+  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 24);      // [kNumLists + 1] group prefix, processing order
   int* const s_cnt = reinterpret_cast<int*>(smem + SP.ints + 36);      // [kNumLists] entries per list
   long long* const s_loff = reinterpret_cast<long long*>(smem + SP.ints + 48);   // [kNumLists] list offsets
 
@@ -163,10 +178,11 @@ pfn_slot_kernel(const TcArgs A) {
       }
     if (tid == 0) {
       for (int b = 0; b < 2; ++b) {
-        mbar_init(&bars[kBarA0 + b], kProdThreads);
-        mbar_init(&bars[kBarA1 + b], kEpiThreads);
+        mbar_init(&bars[kBarA0 + b], kGroup);
+        mbar_init(&bars[kBarA1 + b], kE0Threads);
         mbar_init(&bars[kBarD0 + b], 1);
         mbar_init(&bars[kBarD1 + b], 1);
+        mbar_init(&bars[kBarF1 + b], kE1Threads);
       }
       fence_mbar_init();
       int acc = 0;
@@ -217,8 +233,8 @@ pfn_slot_kernel(const TcArgs A) {
       const uint32_t b = c0 & 1;
       TRACE(0, 20);
       mbar_wait(&bars[kBarA0 + b], (c0 >> 1) & 1);
+      if (kLayers == 1 && c0 >= 2) mbar_wait(&bars[kBarA1 + b], ((c0 - 2) >> 1) & 1);   // D0[b] consumed by E0
       TRACE(0, 21);
-      if (kLayers == 1 && c0 >= 2) mbar_wait(&bars[kBarA1 + b], ((c0 - 2) >> 1) & 1);   // D0[b] consumed by the epilogue
       tc_fence_after_sync();
       if (elect_one_sync()) {
         mma_3xtf32_ts(tmem + kColD0 + b * 64, tmem + kColA0 + b * 64, tmem + kColA0 + b * 64 + 32, sw0h, sw0l, N0, k0 / 8,
@@ -232,6 +248,7 @@ pfn_slot_kernel(const TcArgs A) {
       const uint32_t b = c1 & 1;
       TRACE(0, 22);
       mbar_wait(&bars[kBarA1 + b], (c1 >> 1) & 1);
+      if (c1 >= 2) mbar_wait(&bars[kBarF1 + b], ((c1 - 2) >> 1) & 1);                    // D1[b] consumed by E1
       TRACE(0, 23);
       tc_fence_after_sync();
       if (elect_one_sync()) {
@@ -242,6 +259,8 @@ pfn_slot_kernel(const TcArgs A) {
       __syncwarp();
       ++c1;
     };
+    // D0[b] is overwritten by the layer-0 MMA two slots later; that MMA is issued after the layer-1 MMA of the slot
+    // in between, which waited for A1, i.e. for E0 having read D0[b] (two-layer PFN).
     if ((int)blockIdx.x < total) issue_m0();
     for (int w = blockIdx.x; w < total; w += G) {
       bool is_seg;
@@ -257,41 +276,53 @@ pfn_slot_kernel(const TcArgs A) {
     TRACE_END(0);
   } else if (warp >= kProdWarp0) {
     // =====================================================================================================
-    // producers (register budget raised with what the other roles gave back to the CTA pool)
+    // producers
     //
-    // A producer thread owns TMEM lane p, i.e. pillar p of every group of this CTA, and walks the CTA's slots in
-    // order.  Everything it needs arrives through a software pipeline of cp.async copies that it issues itself and
-    // that only it reads back (no cross-thread synchronisation), DEPTH slots apart per stage:
-    //   cursor A  work-list entry of a group             -> s_ent   (DEPTH + 1 groups ahead of cursor B)
-    //   cursor B  row number of slot t + 2 * DEPTH       -> s_idx   (needs its group's entry)
-    //   cursor C  point row of slot t + DEPTH            -> s_row   (needs its row number)
-    //   cursor D  slot t: features -> TF32 hi / lo -> tensor memory (A operand of layer 0)
-    // One commit group per slot and a single cp.async.wait_group<DEPTH - 1> make everything issued DEPTH or more
-    // iterations ago visible, which is exactly what cursors B, C and D read.  DEPTH rows (32 bytes each) are in
-    // flight per thread, 128 threads per SM: enough outstanding gathers to cover HBM latency.
+    // A producer thread owns TMEM lane p, i.e. pillar p of every group of this CTA, and builds every second slot
+    // (set s: the slots of parity s, which live in operand buffer s).  Everything it needs arrives through a software
+    // pipeline of cp.async copies that it issues itself and that only it reads back (no cross-thread
+    // synchronisation); one iteration = one of its slots, the stages are DEPTH iterations apart:
+    //   cursor A  work-list entry of a group                    -> s_ent   (2 * DEPTH + 2 groups ahead of cursor B)
+    //   cursor B  row number of its slot i + 2 * DEPTH           -> s_idx   (needs its group's entry)
+    //   cursor C  point row + pillar mean of its slot i + DEPTH  -> s_row, s_mean (needs the row number)
+    //   cursor D  slot i: features -> TF32 hi / lo -> tensor memory (A operand of layer 0)
+    // One commit group per iteration and a single cp.async.wait_group<DEPTH - 1> make everything issued DEPTH or
+    // more iterations ago visible, which is exactly what cursors B, C and D read.
     // =====================================================================================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     constexpr int DEPTH = RowCfg<kCfg>::depth;
     constexpr int STAGES = DEPTH + 1;
-    const int p = tid - kEpiThreads;                       // pillar of the group == TMEM lane
+    constexpr int LEAD = 2 * DEPTH + 2;                    // cursor A's lead over cursor B, in groups
+    static_assert(4 * DEPTH + LEAD + 2 <= kEntRing, "entry ring too small");
+    const int set = (tid - kProdWarp0 * 32) >> 7;          // 0 / 1
+    const int p = tid & (kGroup - 1);                      // pillar of the group == TMEM lane (kProdWarp0 * 32 % 128 == 0)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    unsigned long long* const s_ent = reinterpret_cast<unsigned long long*>(smem + SP.ent);
-    float* const s_row = smem + SP.row;
+    unsigned long long* const s_ent = reinterpret_cast<unsigned long long*>(smem + SP.ent + set * SP.ent_set);
+    int* const s_idx = reinterpret_cast<int*>(smem + SP.idx + set * SP.idx_set);
+    float4* const s_mean = reinterpret_cast<float4*>(smem + SP.mean + set * SP.mean_set);
+    float* const s_row = smem + SP.row + set * SP.row_set;
     constexpr unsigned long long kNoEntry = ~0ull;
     const int n_cols = kCfg ? NREG : A.c_raw;              // generic layout: columns 1 .. c_raw are staged
 
-    struct Cursor { int w, j, slots, gi; };               // work item, slot inside it, its slot count, group counter
-    auto cur_init = [&](Cursor& c) {
-      c.w = blockIdx.x; c.j = 0; c.gi = 0;
-      bool sg;
-      c.slots = (c.w < total) ? slots_of(c.w, sg) : 1;
+    struct Cursor { int w, j, slots, gi; bool seg; };      // work item, slot inside it, its slot count, group counter
+    auto cur_load = [&](Cursor& c) {
+      c.seg = false;
+      c.slots = (c.w < total) ? slots_of(c.w, c.seg) : 1;
     };
     auto cur_next = [&](Cursor& c) -> bool {              // advance one slot; true when a new group starts
       if (++c.j < c.slots) return false;
       c.j = 0; c.w += G; ++c.gi;
-      bool sg;
-      c.slots = (c.w < total) ? slots_of(c.w, sg) : 1;
+      cur_load(c);
       return true;
+    };
+    auto cur_init = [&](Cursor& c) {                       // slot `set` of the CTA's slot sequence
+      c.w = blockIdx.x; c.j = 0; c.gi = 0;
+      cur_load(c);
+      if (set) cur_next(c);
+    };
+    auto cur_next2 = [&](Cursor& c) -> bool {             // advance to this set's next slot
+      const bool a = cur_next(c);
+      const bool b = cur_next(c);
+      return a || b;
     };
     auto issue_entry = [&](int w, int gi) {               // cursor A
       unsigned long long* dst = s_ent + (gi & (kEntRing - 1)) * kGroup + p;
@@ -306,29 +337,29 @@ pfn_slot_kernel(const TcArgs A) {
     };
     auto entry_of = [&](int gi) { return s_ent[(gi & (kEntRing - 1)) * kGroup + p]; };
 
-    // ---- prologue: fill the pipeline (entries, then row numbers, then rows), each stage after the previous landed ----
     int ga_w = blockIdx.x, ga_gi = 0;                      // cursor A
     Cursor cb, cc, cd;
     cur_init(cb); cur_init(cc); cur_init(cd);
     unsigned long long eb = kNoEntry, ec = kNoEntry, ed = kNoEntry;   // cached entries of the cursors' groups
-    // Cursor A stays DEPTH + 1 groups ahead of cursor B's group: an entry requested in the iteration after B entered
-    // group Y - DEPTH - 1 is committed DEPTH iterations before B can enter group Y (every group has at least one slot).
+    // An entry requested in the iteration after cursor B entered group Y - LEAD (or Y - LEAD + 1) is committed at
+    // least DEPTH iterations before B can enter group Y: B advances at most two groups per iteration.
     auto step_a = [&](int b_gi) {
-      while (ga_gi <= b_gi + DEPTH + 1) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
+      while (ga_gi <= b_gi + LEAD) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
     };
-    auto step_b = [&](int slot) {                          // row number of cursor B's slot -> s_idx[slot ring]
+    auto step_b = [&](int it) {                            // row number of cursor B's slot -> s_idx[ring]
       if (eb != kNoEntry) {
         int r, off, len;
         unpack_entry(eb, r, off, len);
-        cp_async4(s_idx + (slot % STAGES) * kGroup + p, A.sorted_idx + off + min(cb.j, len - 1));
+        cp_async4(s_idx + (it % STAGES) * kGroup + p, A.sorted_idx + off + min(cb.j, len - 1));
       }
-      if (cur_next(cb)) eb = entry_of(cb.gi);
+      if (cur_next2(cb)) eb = entry_of(cb.gi);
     };
-    auto step_c = [&](int slot) {                          // row of cursor C's slot -> s_row[slot ring]
+    auto step_c = [&](int it) {                            // row and pillar mean of cursor C's slot -> s_row / s_mean[ring]
       if (ec != kNoEntry) {
-        const int idx = s_idx[(slot % STAGES) * kGroup + p];
+        const int st = it % STAGES;
+        const int idx = s_idx[st * kGroup + p];
         const float* row = A.points + (int64_t)idx * A.stride;
-        float* dst = s_row + (slot % STAGES) * (NREG * kGroup);
+        float* dst = s_row + st * (NREG * kGroup);
         if (kCfg == 1) {
           cp_async16(dst + p * 4, row);
           cp_async16(dst + 4 * kGroup + p * 4, row + 4);
@@ -338,76 +369,63 @@ pfn_slot_kernel(const TcArgs A) {
         } else {
           for (int c = 0; c < n_cols; ++c) cp_async4(dst + c * kGroup + p, row + 1 + c);
         }
+        const int r = (int)(ec & 0x1fffffffull);
+        cp_async16(s_mean + st * kGroup + p, (cc.seg ? A.long_mean : A.mean) + r);
       }
-      if (cur_next(cc)) ec = entry_of(cc.gi);
+      if (cur_next2(cc)) ec = entry_of(cc.gi);
     };
-    int sb = 0, sc = 0;                                    // absolute slot numbers of cursors B and C
-    // entries of the first 2 * DEPTH + 2 groups (everything cursor B can reach during the prologue) - one round trip
-    while (ga_gi < 2 * DEPTH + 2) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
+    int ib = 0, ic = 0;                                    // iteration numbers of cursors B and C
+    // entries of the first 4 * DEPTH + LEAD + 2 groups (everything cursor B can reach during the prologue plus its lead)
+    while (ga_gi < 4 * DEPTH + LEAD + 2) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
     cp_async_commit();
     cp_async_wait<0>();
-    eb = entry_of(0); ec = eb; ed = eb;
-    for (int t = 0; t < DEPTH; ++t) step_b(sb++);          // row numbers of slots 0 .. DEPTH - 1 - one round trip
+    eb = entry_of(cb.gi); ec = eb; ed = eb;
+    for (int t = 0; t < DEPTH; ++t) step_b(ib++);          // row numbers of its slots 0 .. DEPTH - 1 - one round trip
     cp_async_commit();
     cp_async_wait<0>();
-    // rows of slots 0 .. DEPTH - 1 and row numbers of slots DEPTH .. 2 * DEPTH - 1, one commit group per slot: cursor D
-    // is at slot 0, C at DEPTH, B at 2 * DEPTH, with DEPTH commit groups pending exactly as in the steady state
-    // (at most DEPTH + 1 row numbers are live, which is the size of their ring)
-    for (int t = 0; t < DEPTH; ++t) { step_b(sb++); step_c(sc++); cp_async_commit(); }
+    // rows of its slots 0 .. DEPTH - 1 and row numbers of slots DEPTH .. 2 * DEPTH - 1, one commit group per slot:
+    // DEPTH commit groups pending exactly as in the steady state (at most DEPTH + 1 row numbers are live = their ring)
+    for (int t = 0; t < DEPTH; ++t) { step_b(ib++); step_c(ic++); cp_async_commit(); }
 
-    auto mean_of = [&](unsigned long long e, bool is_seg) -> float4 {
-      if (e == kNoEntry) return make_float4(0.f, 0.f, 0.f, 0.f);
-      const int r = (int)(e & 0x1fffffffull);
-      return __ldg((is_seg ? A.long_mean : A.mean) + r);
-    };
-    auto seg_of = [&](int w) { bool sg = false; if (w < total) slots_of(w, sg); return sg; };
-    // pillar means: this group's, the next group's and the one after (register prefetch, two groups ahead)
-    float4 m0 = mean_of(ed, seg_of(cd.w));
-    float4 m1 = mean_of(entry_of(1), seg_of(cd.w + G));
-    float4 m2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t c0 = 0;
-    int sd = 0;                                            // absolute slot number of cursor D
-    bool new_group = true;
+    uint32_t c0 = 0;                                       // this set's slots built so far
+    int id = 0;                                            // iteration number of cursor D
     const int n_feat = n_raw + (with_dist ? 7 : 6);
+    const uint32_t b = (uint32_t)set;                      // operand buffer == slot parity == set
     TRACE_DECL(p == 0)
-    TRACE(1, 9);
     while (cd.w < total) {
-      // ---- pipeline upkeep: one entry / row number / row request per slot ----
-      TRACE(1, new_group ? 13 : 10);
-      cp_async_wait<DEPTH - 1>();
-      TRACE(1, 14);                          // everything issued DEPTH or more slots ago has landed
+      // ---- pipeline upkeep: entries / one row number / one row request per iteration ----
+      TRACE(set ? 4 : 1, 10);
+      cp_async_wait<DEPTH - 1>();                          // everything issued DEPTH or more iterations ago has landed
       step_a(cb.gi);
-      step_b(sb++);
-      step_c(sc++);
+      step_b(ib++);
+      step_c(ic++);
       cp_async_commit();
+      TRACE(set ? 4 : 1, 14);
       const bool valid = ed != kNoEntry;
-      if (new_group) {
-        // entries of the next two groups were requested at least 2 * DEPTH slots ago
-        const bool is_seg = seg_of(cd.w);
-        m2 = mean_of(entry_of(cd.gi + 2), seg_of(cd.w + 2 * G));
+      const float4 m = s_mean[(id % STAGES) * kGroup + p];
+      if (cd.j == 0) {
+        // first slot of a group (built by exactly one of the two sets): publish the group's output rows
         const int r = valid ? (int)(ed & 0x1fffffffull) : -1;
         s_rows[(cd.gi % kRowRing) * kGroup + p] = r;      // pillar rank, or long-pillar index of a segment
-        if (A.mean_out && valid && !is_seg) {
-          float* m = A.mean_out + (int64_t)r * 3;
-          m[0] = m0.x; m[1] = m0.y; m[2] = m0.z;
+        if (A.mean_out && valid && !cd.seg) {
+          float* mo = A.mean_out + (int64_t)r * 3;
+          mo[0] = m.x; mo[1] = m.y; mo[2] = m.z;
         }
       }
       // ---- this slot's row: shared memory -> registers ----
       float rw[NREG];
-      {
-        const float* src = s_row + (sd % STAGES) * (NREG * kGroup);
-        if (kCfg == 1) {
-          const float4 v0 = ld4(src + p * 4), v1 = ld4(src + 4 * kGroup + p * 4);
-          rw[0] = v0.x; rw[1] = v0.y; rw[2] = v0.z; rw[3] = v0.w; rw[4] = v1.x; rw[5] = v1.y; rw[6] = v1.z; rw[7] = v1.w;
-        } else if (kCfg == 2) {
+      const float* src = s_row + (id % STAGES) * (NREG * kGroup);
+      if (kCfg == 1) {
+        const float4 v0 = ld4(src + p * 4), v1 = ld4(src + 4 * kGroup + p * 4);
+        rw[0] = v0.x; rw[1] = v0.y; rw[2] = v0.z; rw[3] = v0.w; rw[4] = v1.x; rw[5] = v1.y; rw[6] = v1.z; rw[7] = v1.w;
+      } else if (kCfg == 2) {
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            const float2 v = *reinterpret_cast<const float2*>(src + c * 2 * kGroup + p * 2);
-            rw[2 * c] = v.x; rw[2 * c + 1] = v.y;
-          }
+        for (int c = 0; c < 6; ++c) {
+          const float2 v = *reinterpret_cast<const float2*>(src + c * 2 * kGroup + p * 2);
+          rw[2 * c] = v.x; rw[2 * c + 1] = v.y;
         }
       }
-      const float* gsrc = s_row + (sd % STAGES) * (NREG * kGroup) + p;   // generic layout: column c at gsrc[(c - 1) * kGroup]
+      const float* gsrc = src + p;                         // generic layout: column c at gsrc[(c - 1) * kGroup]
       // ---- features of this slot's row (dynamic_pillar_vfe.py:111-126) ----
       float x = 0.f, y = 0.f, z = 0.f;
       if (valid) {
@@ -415,20 +433,20 @@ pfn_slot_kernel(const TcArgs A) {
         else { x = gsrc[0]; y = gsrc[kGroup]; z = gsrc[2 * kGroup]; }
       }
       float ed_[7];
-      ed_[0] = __fsub_rn(x, m0.x);                                               // f_cluster (:111)
-      ed_[1] = __fsub_rn(y, m0.y);
-      ed_[2] = __fsub_rn(z, m0.z);
-      const float cx = quantise(x, A.g.range_min_x, A.g.voxel_x);
-      const float cy = quantise(y, A.g.range_min_y, A.g.voxel_y);
+      ed_[0] = __fsub_rn(x, m.x);                                                // f_cluster (:111)
+      ed_[1] = __fsub_rn(y, m.y);
+      ed_[2] = __fsub_rn(z, m.z);
+      // the pillar's cell (same for all its points) was packed next to the mean: no per-point division (:98, :114-116)
+      const unsigned cell = __float_as_uint(m.w);
+      const float cx = (float)(cell & 0xffffu), cy = (float)(cell >> 16);
       ed_[3] = __fsub_rn(x, __fadd_rn(__fmul_rn(cx, A.g.voxel_x), A.g.x_offset));   // f_center (:114-116)
       ed_[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
       ed_[5] = __fsub_rn(z, A.g.z_offset);
       ed_[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
-      // A0[c0 & 1] is free once the layer-0 MMA that read it two ops ago has completed
-      const uint32_t b = c0 & 1;
-      TRACE(1, 11);
-      if (c0 >= 2) { mbar_wait(&bars[kBarD0 + b], ((c0 - 2) >> 1) & 1); tc_fence_after_sync(); }
-      TRACE(1, 12);
+      // A0[set] is free once the layer-0 MMA that read this set's previous slot has completed
+      TRACE(set ? 4 : 1, 11);
+      if (c0 >= 1) { mbar_wait(&bars[kBarD0 + b], (c0 - 1) & 1); tc_fence_after_sync(); }
+      TRACE(set ? 4 : 1, 12);
       const uint32_t dh = tmem + kColA0 + b * 64 + lane_base, dl = dh + 32;
 #pragma unroll
       for (int cc8 = 0; cc8 < kMaxCin; cc8 += 8) {
@@ -456,197 +474,207 @@ pfn_slot_kernel(const TcArgs A) {
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(&bars[kBarA0 + b]);
-      ++c0; ++sd;
-      new_group = cur_next(cd);
-      if (new_group) {
-        ed = entry_of(cd.gi);
-        m0 = m1; m1 = m2;
-      }
+      ++c0; ++id;
+      if (cur_next2(cd)) ed = entry_of(cd.gi);
     }
     cp_async_wait<0>();
-    TRACE_END(1);
-  } else {
+    TRACE_END(set ? 4 : 1);
+  } else if (warp < kE1Warp0) {
     // =====================================================================================================
-    // epilogue
+    // E0: layer-0 epilogue (for a single-layer PFN: the whole epilogue)
     // =====================================================================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     const int p = tid & (kGroup - 1);
-    const int q = tid >> 7;                                  // column quarter
+    const int h = tid >> 7;                                  // column half
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t c0 = 0, c1 = 0;   // layer-0 accumulators consumed / layer-1-type ops staged
-    float max0[8];             // layer-0 running max, this thread's 8 channels (two layers only)
-    float m1[16];              // last-layer running max of the raw accumulators, this thread's 16 channels
-    bool pend_fin = false;     // a finished group whose hoist result / output rows are still outstanding
-    uint32_t pend_k = 0;       // its hoist op
-    int pend_gi = 0;
-    uint32_t e1_k = 0;         // op whose accumulator the next E1 reads
-
+    uint32_t c0 = 0, c1 = 0;   // layer-0 accumulators consumed / layer-1-type operands staged
     TRACE_DECL(tid == 0)
-    auto e0 = [&]() {          // BN + ReLU, running max0, x0 -> TMEM as the A operand of layer 1
-      const uint32_t b = c0 & 1;
-      TRACE(2, 30);
-      mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
-      TRACE(2, 31);
-      tc_fence_after_sync();
-      uint32_t rr[8];
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
-                   : "r"(tmem + kColD0 + b * 64 + lane_base + 8 * q)
-                   : "memory");
-      tmem_ld_wait();
-      float hi[8], lo[8];
-      const float4 al0 = ld4(smem + SP.prm_a0 + 8 * q), al1 = ld4(smem + SP.prm_a0 + 8 * q + 4);
-      const float4 be0 = ld4(smem + SP.prm_b0 + 8 * q), be1 = ld4(smem + SP.prm_b0 + 8 * q + 4);
-      const float a8[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
-      const float b8[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xv = fmaxf(fmaf(__uint_as_float(rr[i]), a8[i], b8[i]), 0.f);
-        max0[i] = fmaxf(max0[i], xv);
-        split_tf32(xv, hi[i], lo[i]);
-      }
-      const uint32_t b1 = c1 & 1;
-      tmem_st8(tmem + kColA1 + b1 * 64 + lane_base + 8 * q, hi);
-      tmem_st8(tmem + kColA1 + b1 * 64 + 32 + lane_base + 8 * q, lo);
-      tmem_st_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&bars[kBarA1 + b1]);
-      TRACE(2, 32);
-      ++c0; ++c1;
-    };
-    auto ld_acc16 = [&](uint32_t k, uint32_t (&rr)[16]) {       // this thread's 16 columns of layer-1-type op k
-      const uint32_t b = k & 1;
-      TRACE(2, 33);
-      mbar_wait(&bars[kBarD1 + b], (k >> 1) & 1);
-      TRACE(2, 34);
-      tc_fence_after_sync();
-      tmem_ld16_nowait(tmem + kColD1 + b * 64 + lane_base + 16 * q, rr);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-    };
-    auto e1 = [&]() {          // running max of the raw last-layer accumulators
-      uint32_t rr[16];
-      ld_acc16(e1_k, rr);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) m1[i] = fmaxf(m1[i], __uint_as_float(rr[i]));
-    };
-    // OUT: BN(eval) + ReLU once per pillar; the tile is staged in shared memory so that every pillar_features row
-    // leaves as 256 contiguous bytes
-    auto write_out = [&](int gi) {
-      const float* pa = smem + (kLayers == 2 ? SP.prm_a1 : SP.prm_a0) + 16 * q;
-      const float* pb = smem + (kLayers == 2 ? SP.prm_b1 : SP.prm_b0) + 16 * q;
-      float* dst = s_out + p * kOutLd + 16 * q;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 al = ld4(pa + i), be = ld4(pb + i);
-        float4 o;
-        o.x = fmaxf(fmaf(m1[i + 0], al.x, be.x), 0.f);
-        o.y = fmaxf(fmaf(m1[i + 1], al.y, be.y), 0.f);
-        o.z = fmaxf(fmaf(m1[i + 2], al.z, be.z), 0.f);
-        o.w = fmaxf(fmaf(m1[i + 3], al.w, be.w), 0.f);
-        *reinterpret_cast<float4*>(dst + i) = o;
-      }
-      named_bar_sync(1, kEpiThreads);
-      const int* rows = s_rows + (gi % kRowRing) * kGroup;
-#pragma unroll
-      for (int t = 0; t < (kGroup * kCout / 4) / kEpiThreads; ++t) {
-        const int item = t * kEpiThreads + tid;
-        const int row = item >> 4, c4 = item & 15;
-        const int r = rows[row];
-        if (r >= 0) *reinterpret_cast<float4*>(A.out + (int64_t)r * kCout + c4 * 4) = ld4(s_out + row * kOutLd + c4 * 4);
-      }
-      named_bar_sync(2, kEpiThreads);
-    };
-    auto finish_group = [&]() {   // hoist result + output of the pending group
-      if (kLayers == 2) {
-        uint32_t rr[16];
-        ld_acc16(pend_k, rr);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) m1[i] = __fadd_rn(m1[i], __uint_as_float(rr[i]));
-      }
-      TRACE(2, 37);
-      write_out(pend_gi);
-      TRACE(2, 38);
-      pend_fin = false;
-    };
-
     int gi = 0;
-    for (int w = blockIdx.x; w < total; w += G, ++gi) {
-      bool is_seg;
-      const int slots = slots_of(w, is_seg);
-      if (kLayers == 2) {
+    if (kLayers == 2) {
+      float max0[16];          // layer-0 running max, this thread's 16 channels
+      const float* pa = smem + SP.prm_a0 + 16 * h;
+      const float* pb = smem + SP.prm_b0 + 16 * h;
+      for (int w = blockIdx.x; w < total; w += G, ++gi) {
+        bool is_seg;
+        const int slots = slots_of(w, is_seg);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) max0[i] = 0.f;
+        for (int i = 0; i < 16; ++i) max0[i] = 0.f;
         for (int j = 0; j < slots; ++j) {
-          e0();                                       // stages op c1 - 1
-          if (j == 0) {
-            if (pend_fin) finish_group();             // previous group: its hoist ran behind our first layer-0 epilogue
+          const uint32_t b = c0 & 1, b1 = c1 & 1;
+          TRACE(2, 30);
+          mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
+          if (c1 >= 2) mbar_wait(&bars[kBarD1 + b1], ((c1 - 2) >> 1) & 1);     // A1[b1] read by the MMA two ops ago
+          TRACE(2, 31);
+          tc_fence_after_sync();
+          uint32_t rr[16];
+          tmem_ld16_nowait(tmem + kColD0 + b * 64 + lane_base + 16 * h, rr);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) m1[i] = -INFINITY;
-          } else {
-            e1();                                     // previous slot
+          for (int half = 0; half < 2; ++half) {
+            float hi[8], lo[8];
+            const float4 al0 = ld4(pa + 8 * half), al1 = ld4(pa + 8 * half + 4);
+            const float4 be0 = ld4(pb + 8 * half), be1 = ld4(pb + 8 * half + 4);
+            const float a8[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
+            const float b8[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xv = fmaxf(fmaf(__uint_as_float(rr[8 * half + i]), a8[i], b8[i]), 0.f);
+              max0[8 * half + i] = fmaxf(max0[8 * half + i], xv);
+              split_tf32(xv, hi[i], lo[i]);
+            }
+            tmem_st8(tmem + kColA1 + b1 * 64 + lane_base + 16 * h + 8 * half, hi);
+            tmem_st8(tmem + kColA1 + b1 * 64 + 32 + lane_base + 16 * h + 8 * half, lo);
           }
-          e1_k = c1 - 1;
-        }
-        if (!is_seg) {
-          // hoist: max0 -> A1; the MMA warp multiplies by W1[:, 32:]^T
-          float hi[8], lo[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) split_tf32(max0[i], hi[i], lo[i]);
-          const uint32_t b1 = c1 & 1;
-          tmem_st8(tmem + kColA1 + b1 * 64 + lane_base + 8 * q, hi);
-          tmem_st8(tmem + kColA1 + b1 * 64 + 32 + lane_base + 8 * q, lo);
           tmem_st_wait();
           tc_fence_before_sync();
           mbar_arrive(&bars[kBarA1 + b1]);
-          pend_k = c1;
-          ++c1;
+          TRACE(2, 32);
+          ++c0; ++c1;
         }
-        e1();                                         // last slot
-        if (is_seg) {
-          // long pillar segment: partial maxima -> the pillar's accumulator
+        if (!is_seg) {
+          // hoist: max0 -> A1; the MMA warp multiplies by W1[:, 32:]^T
+          const uint32_t b1 = c1 & 1;
+          if (c1 >= 2) { mbar_wait(&bars[kBarD1 + b1], ((c1 - 2) >> 1) & 1); tc_fence_after_sync(); }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_tf32(max0[8 * half + i], hi[i], lo[i]);
+            tmem_st8(tmem + kColA1 + b1 * 64 + lane_base + 16 * h + 8 * half, hi);
+            tmem_st8(tmem + kColA1 + b1 * 64 + 32 + lane_base + 16 * h + 8 * half, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive(&bars[kBarA1 + b1]);
+          ++c1;
+        } else {
+          // long pillar segment: partial layer-0 maxima -> the pillar's accumulator
           const int li = s_rows[(gi % kRowRing) * kGroup + p];
           if (li >= 0) {
-            unsigned* acc = A.long_acc + (int64_t)li * 96;
+            unsigned* acc = A.long_acc + (int64_t)li * 96 + 16 * h;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) atomicMax(acc + 8 * q + i, ord_enc(max0[i]));
-#pragma unroll
-            for (int i = 0; i < 16; ++i) atomicMax(acc + 32 + 16 * q + i, ord_enc(m1[i]));
+            for (int i = 0; i < 16; ++i) atomicMax(acc + i, ord_enc(max0[i]));
           }
-        } else {
-          pend_fin = true; pend_gi = gi;
         }
-      } else {
-        // single layer: D0 (64 columns) is the last-layer accumulator
+      }
+    } else {
+      // single layer: D0 (64 columns) is the last-layer accumulator; this thread owns 32 of them
+      float m1[32];
+      for (int w = blockIdx.x; w < total; w += G, ++gi) {
+        bool is_seg;
+        const int slots = slots_of(w, is_seg);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) m1[i] = -INFINITY;
+        for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
         for (int j = 0; j < slots; ++j) {
           const uint32_t b = c0 & 1;
           mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
           tc_fence_after_sync();
-          uint32_t rr[16];
-          tmem_ld16_nowait(tmem + kColD0 + b * 64 + lane_base + 16 * q, rr);
-          tmem_ld_wait();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t rr[16];
+            tmem_ld16_nowait(tmem + kColD0 + b * 64 + lane_base + 32 * h + 16 * half, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m1[16 * half + i] = fmaxf(m1[16 * half + i], __uint_as_float(rr[i]));
+          }
           tc_fence_before_sync();
           mbar_arrive(&bars[kBarA1 + b]);             // "D0[b] consumed"
           ++c0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) m1[i] = fmaxf(m1[i], __uint_as_float(rr[i]));
         }
-        if (is_seg) {
-          const int li = s_rows[(gi % kRowRing) * kGroup + p];
-          if (li >= 0) {
-            unsigned* acc = A.long_acc + (int64_t)li * 96;
+        const int r = s_rows[(gi % kRowRing) * kGroup + p];
+        if (r >= 0) {
+          if (is_seg) {
+            unsigned* acc = A.long_acc + (int64_t)r * 96 + 32 + 32 * h;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicMax(acc + 32 + 16 * q + i, ord_enc(m1[i]));
+            for (int i = 0; i < 32; ++i) atomicMax(acc + i, ord_enc(m1[i]));
+          } else {
+            const float* pa = smem + SP.prm_a0 + 32 * h;
+            const float* pb = smem + SP.prm_b0 + 32 * h;
+            float* dst = A.out + (int64_t)r * kCout + 32 * h;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 al = ld4(pa + i), be = ld4(pb + i);
+              st_global_f4(dst + i, fmaxf(fmaf(m1[i + 0], al.x, be.x), 0.f), fmaxf(fmaf(m1[i + 1], al.y, be.y), 0.f),
+                           fmaxf(fmaf(m1[i + 2], al.z, be.z), 0.f), fmaxf(fmaf(m1[i + 3], al.w, be.w), 0.f));
+            }
           }
-        } else {
-          write_out(gi);
         }
       }
     }
-    if (pend_fin) finish_group();
     TRACE_END(2);
+  } else if (kLayers == 2) {
+    // =====================================================================================================
+    // E1: last-layer epilogue + output rows (two-layer PFN)
+    // =====================================================================================================
+    const int p = tid & (kGroup - 1);
+    const int h = (tid >> 7) & 1;                            // column half: channels 32 h .. 32 h + 31
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t k = 0;            // layer-1-type accumulators consumed
+    float m1[32];              // running max of the raw last-layer accumulators
+    TRACE_DECL(tid == kE0Threads)
+    int gi = 0;
+    for (int w = blockIdx.x; w < total; w += G, ++gi) {
+      bool is_seg;
+      const int slots = slots_of(w, is_seg);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
+      for (int j = 0; j < slots; ++j) {
+        const uint32_t b = k & 1;
+        TRACE(3, 33);
+        mbar_wait(&bars[kBarD1 + b], (k >> 1) & 1);
+        TRACE(3, 34);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rr[16];
+          tmem_ld16_nowait(tmem + kColD1 + b * 64 + lane_base + 32 * h + 16 * half, rr);
+          tmem_ld_wait();
+          if (half == 1) { tc_fence_before_sync(); mbar_arrive(&bars[kBarF1 + b]); }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m1[16 * half + i] = fmaxf(m1[16 * half + i], __uint_as_float(rr[i]));
+        }
+        TRACE(3, 35);
+        ++k;
+      }
+      const int r = s_rows[(gi % kRowRing) * kGroup + p];
+      if (!is_seg) {
+        // the x_max half (hoist) + BN + ReLU + this thread's 128 bytes of the output row
+        const uint32_t b = k & 1;
+        TRACE(3, 36);
+        mbar_wait(&bars[kBarD1 + b], (k >> 1) & 1);
+        TRACE(3, 37);
+        tc_fence_after_sync();
+        const float* pa = smem + SP.prm_a1 + 32 * h;
+        const float* pb = smem + SP.prm_b1 + 32 * h;
+        float* dst = A.out + (int64_t)r * kCout + 32 * h;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rr[16];
+          tmem_ld16_nowait(tmem + kColD1 + b * 64 + lane_base + 32 * h + 16 * half, rr);
+          tmem_ld_wait();
+          if (half == 1) { tc_fence_before_sync(); mbar_arrive(&bars[kBarF1 + b]); }
+          if (r >= 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const int c = 16 * half + i;
+              const float4 al = ld4(pa + c), be = ld4(pb + c);
+              st_global_f4(dst + c,
+                           fmaxf(fmaf(__fadd_rn(m1[c + 0], __uint_as_float(rr[i + 0])), al.x, be.x), 0.f),
+                           fmaxf(fmaf(__fadd_rn(m1[c + 1], __uint_as_float(rr[i + 1])), al.y, be.y), 0.f),
+                           fmaxf(fmaf(__fadd_rn(m1[c + 2], __uint_as_float(rr[i + 2])), al.z, be.z), 0.f),
+                           fmaxf(fmaf(__fadd_rn(m1[c + 3], __uint_as_float(rr[i + 3])), al.w, be.w), 0.f));
+            }
+          }
+        }
+        TRACE(3, 38);
+        ++k;
+      } else if (r >= 0) {
+        // long pillar segment: partial maxima -> the pillar's accumulator (r is its long-pillar index)
+        unsigned* acc = A.long_acc + (int64_t)r * 96 + 32 + 32 * h;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicMax(acc + i, ord_enc(m1[i]));
+      }
+    }
+    TRACE_END(3);
   }
   // ---- teardown ----
   tc_fence_before_sync();
@@ -825,8 +853,8 @@ extern "C" int pcp_selftest_umma_cycles(int32_t mode, int32_t n, int32_t ksteps,
 // debug: copies the event trace of CTA 0 (3 roles x kTraceCap x (id, clock)) and the 3 event counts to host memory
 extern "C" int pcp_debug_read_timing(long long* trace_host, int* counts_host) {
   PCP_CUDA(cudaDeviceSynchronize());
-  PCP_CUDA(cudaMemcpyFromSymbol(trace_host, g_trace, sizeof(long long) * 3 * kTraceCap * 2));
-  PCP_CUDA(cudaMemcpyFromSymbol(counts_host, g_trace_n, sizeof(int) * 3));
+  PCP_CUDA(cudaMemcpyFromSymbol(trace_host, g_trace, sizeof(long long) * kTraceRoles * kTraceCap * 2));
+  PCP_CUDA(cudaMemcpyFromSymbol(counts_host, g_trace_n, sizeof(int) * kTraceRoles));
   return 0;
 }
 #endif

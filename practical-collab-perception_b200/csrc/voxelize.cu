@@ -282,6 +282,13 @@ __device__ __forceinline__ void load_xyz(const float* __restrict__ points, int64
   }
 }
 
+// the pillar's cell, packed next to its mean: cx | cy << 16 (every point of a pillar quantises to the same cell)
+__device__ __forceinline__ float pack_cell(float x, float y, const pcp_grid& g) {
+  const unsigned cx = (unsigned)(int)quantise(x, g.range_min_x, g.voxel_x);
+  const unsigned cy = (unsigned)(int)quantise(y, g.range_min_y, g.voxel_y);
+  return __uint_as_float((cx & 0xffffu) | (cy << 16));
+}
+
 constexpr int kPrepThreads = 256;
 constexpr int kPrepWarps = kPrepThreads / 32;
 
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(kPrepThreads, 5)
 pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32_t* __restrict__ hdr,
                    unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
                    const int32_t* __restrict__ big_list, int32_t* __restrict__ sorted_idx, float4* __restrict__ mean,
-                   float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, int phase_mask) {
+                   float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, const pcp_grid g, int phase_mask) {
   __shared__ __align__(16) PrepSmem sm;
   __shared__ float s_red[3][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -360,6 +367,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
       // sequential sums in ascending row order, rows staged kSumChunk at a time (double buffered: one barrier per chunk)
       float* ch = reinterpret_cast<float*>(sm.cta.scratch);      // [2][3][kSumChunk]
       float acc = 0.f;
+      float cellw = 0.f;
       for (int c0 = 0; c0 < n; c0 += kSumChunk) {
         float* buf = ch + ((c0 / kSumChunk) & 1) * (3 * kSumChunk);
         const int i = c0 + tid;
@@ -368,6 +376,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
           sorted_idx[off + i] = idx;
           float x, y, z;
           load_xyz<kVec4>(points, stride, idx, x, y, z);
+          if (i == 0) cellw = pack_cell(x, y, g);
           buf[tid] = x; buf[kSumChunk + tid] = y; buf[2 * kSumChunk + tid] = z;
         }
         __syncthreads();
@@ -378,6 +387,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
         }
       }
       if (warp < 3 && lane == 0) s_red[warp][0] = __fdiv_rn(acc, (float)n);
+      if (tid == 0) s_red[0][1] = cellw;
       __syncthreads();
       mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
     } else {
@@ -401,10 +411,16 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
       }
       __syncthreads();
       mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
+      if (tid == 0) {
+        float x, y, z;
+        load_xyz<kVec4>(points, stride, sorted_idx[off], x, y, z);
+        s_red[0][1] = pack_cell(x, y, g);
+      }
     }
     if (tid == 0) {
-      long_mean[li] = make_float4(mx, my, mz, 0.f);
-      mean[r] = make_float4(mx, my, mz, 0.f);
+      const float cw = s_red[0][1];
+      long_mean[li] = make_float4(mx, my, mz, cw);
+      mean[r] = make_float4(mx, my, mz, cw);
     }
     __syncthreads();
   }
@@ -470,8 +486,9 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
     }
     const float my = __shfl_sync(0xffffffffu, acc, 1), mz = __shfl_sync(0xffffffffu, acc, 2);
     if (lane == 0) {
-      long_mean[li] = make_float4(acc, my, mz, 0.f);
-      mean[r] = make_float4(acc, my, mz, 0.f);
+      const float cw = pack_cell(x[0], y[0], g);
+      long_mean[li] = make_float4(acc, my, mz, cw);
+      mean[r] = make_float4(acc, my, mz, cw);
     }
     __syncwarp();
   }
@@ -506,7 +523,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
       }
       mine = __fdiv_rn(mine, (float)n);
       const float my = __shfl_sync(0xffffffffu, mine, 1), mz = __shfl_sync(0xffffffffu, mine, 2);
-      if (lane == 0) mean[r] = make_float4(mine, my, mz, 0.f);
+      if (lane == 0) mean[r] = make_float4(mine, my, mz, pack_cell(x, y, g));
       __syncwarp();
     }
   }
@@ -548,7 +565,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
       for (int j = 0; j < 8; ++j)
         if (j < n) { ax = __fadd_rn(ax, x[j]); ay = __fadd_rn(ay, y[j]); az = __fadd_rn(az, z[j]); }
       const float cnt = (float)n;
-      mean[r] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 0.f);
+      mean[r] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), pack_cell(x[0], y[0], g));
     }
   }
 }
@@ -572,6 +589,7 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   PCP_REQUIRE(n_points == 0 || points, PCP_E_INVALID, "pcp_voxelize: null points");
   PCP_REQUIRE(row_stride >= 3, PCP_E_INVALID, "pcp_voxelize: row_stride < 3");
   PCP_REQUIRE(max_frames > 0 && grid->nx > 0 && grid->ny > 0, PCP_E_INVALID, "pcp_voxelize: bad grid");
+  PCP_REQUIRE(grid->nx <= 65535 && grid->ny <= 65535, PCP_E_UNSUPPORTED, "pcp_voxelize: nx, ny must be <= 65535");
   PCP_REQUIRE((int64_t)max_frames * grid->nx * grid->ny < (1ll << 31), PCP_E_UNSUPPORTED,
               "pcp_voxelize: frames*nx*ny must fit int32 (the reference's merge_coords is int32 too)");
   const WsLayout L = ws_layout(n_points, max_frames, grid->nx, grid->ny);
@@ -615,10 +633,10 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
       const int mask = split ? (1 << ph) : 15;
       if (vec4)
         pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                     W.sorted_idx, W.mean, W.long_mean, W.long_acc, mask);
+                                                                     W.sorted_idx, W.mean, W.long_mean, W.long_acc, *grid, mask);
       else
         pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc, mask);
+                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc, *grid, mask);
     }
     PCP_LAUNCH_CHECK("pillar_prep_kernel");
   }

@@ -32,16 +32,16 @@ for _ in range(3):
     fe.pfn(pts, out)
 torch.cuda.synchronize()
 CAP = 8192
-buf = np.zeros((3, CAP, 2), dtype=np.int64)
-cnt = np.zeros(3, dtype=np.int32)
+buf = np.zeros((5, CAP, 2), dtype=np.int64)
+cnt = np.zeros(5, dtype=np.int32)
 lib = _lib.load()
 lib.pcp_debug_read_timing.argtypes = [C.c_void_p, C.c_void_p]
 print("rc", lib.pcp_debug_read_timing(buf.ctypes.data, cnt.ctypes.data), "events", cnt)
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 n_ev = int(sys.argv[2]) if len(sys.argv) > 2 else 120
-t0 = min(int(buf[r, 0, 1]) for r in range(3) if cnt[r] > 0)
-names = ["mma", "producer", "epilogue"]
-for r in range(3):
+t0 = min(int(buf[r, 0, 1]) for r in range(5) if cnt[r] > 0)
+names = ["mma", "producer set 0", "E0", "E1", "producer set 1"]
+for r in range(5):
     ev = buf[r, :min(int(cnt[r]), CAP)]
     if len(ev) == 0:
         continue
