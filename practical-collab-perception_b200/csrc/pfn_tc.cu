@@ -48,20 +48,23 @@ constexpr int kProdWarp0 = kE1Warp0 + kE1Threads / 32;             // 16
 constexpr int kMmaWarp = kProdWarp0 + kProdThreads / 32;          // 24
 constexpr int kPfnThreads = (kMmaWarp + 1) * 32;                  // 800
 constexpr int kTmemCols = 512;
-// tensor-memory column map (everything double buffered: operand / accumulator b of op c is c & 1)
-constexpr uint32_t kColD0 = 0;      // layer-0 accumulators   [b * 64, +32)  (+64 for a single-layer PFN)
+// tensor-memory column map.  The FRONT half of the pipeline (features -> layer 0 -> E0) is NF buffers deep, the back
+// half (x0 -> layer 1 -> E1) two: with 32-column operands / accumulators (two-layer PFN, k0 = 16) NF = 4, else 2.
+constexpr uint32_t kColD0 = 0;      // layer-0 accumulators   [b * (128 / NF), +N0)
 constexpr uint32_t kColD1 = 128;    // layer-1 / hoist accumulators [128 + b * 64, +64)
-constexpr uint32_t kColA0 = 256;    // layer-0 A operand (features): hi at 256 + b * 64, lo 32 columns further (k0 <= 24)
+constexpr uint32_t kColA0 = 256;    // layer-0 A operand (features): hi at 256 + b * (128 / NF), lo 64 / NF columns further
 constexpr uint32_t kColA1 = 384;    // layer-1 A operand (x0 / max0): hi at 384 + b * 64, lo 32 columns further
+constexpr int kMaxNF = 4;
 constexpr int kRowRing = 16;        // ring of per-group output-row tables (producers run a few groups ahead of the output)
-constexpr int kEntRing = 32;        // per producer set: ring of per-group work-list entries
+constexpr int kGTab = 256;          // per-CTA table of (slots, is-segment) of its first groups (later ones are recomputed)
+constexpr int kOutRowBytes = 144;   // E1 output staging: 128 bytes per thread + 16 bytes of padding (conflict-free STS.128)
 // mbarrier indices
-constexpr int kBarA0 = 0;           // [2] features staged in TMEM          (128 arrivals: the producer set of that parity)
-constexpr int kBarA1 = 2;           // [2] x0 / max0 staged in TMEM         (256 arrivals: E0)
-constexpr int kBarD0 = 4;           // [2] layer-0 accumulator ready        (tcgen05.commit)
-constexpr int kBarD1 = 6;           // [2] layer-1 / hoist accumulator ready (tcgen05.commit)
-constexpr int kBarF1 = 8;           // [2] layer-1 accumulator consumed     (256 arrivals: E1)
-constexpr int kNumBars = 10;
+constexpr int kBarA0 = 0;           // [NF] features staged in TMEM         (128 arrivals: one producer set)
+constexpr int kBarD0 = 4;           // [NF] layer-0 accumulator ready       (tcgen05.commit)
+constexpr int kBarA1 = 8;           // [2] x0 / max0 staged in TMEM         (256 arrivals: E0)
+constexpr int kBarD1 = 10;          // [2] layer-1 / hoist accumulator ready (tcgen05.commit)
+constexpr int kBarF1 = 12;          // [2] layer-1 accumulator consumed     (256 arrivals: E1)
+constexpr int kNumBars = 14;
 
 // ---- optional per-role event trace of CTA 0 (debug build only: make dbg; tools/pfn_timing.py) ----
 #ifdef PCP_PFN_TIMING
@@ -94,10 +97,12 @@ __device__ __forceinline__ void st_global_f4(float* p, float a, float b, float c
 //   nreg  = floats of a row staged per slot, depth = rows in flight per producer thread (cp.async ring of depth + 1 stages)
 template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 24, depth = 2; };
 template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8, depth = 4; };
-template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12, depth = 4; };
+template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12, depth = 3; };
+// per producer set: ring of per-group work-list entries (cursor A runs up to 6 * depth + 4 groups ahead of cursor D)
+__host__ __device__ constexpr int ent_ring(int depth) { return 6 * depth + 4 <= 16 ? 16 : 32; }
 
 struct SmemPlan {   // float offsets into dynamic shared memory
-  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, mean, row, rows, ints, total_bytes;
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, mean, row, rows, ostage, gtab, ints, total_bytes;
   int ent_set, idx_set, mean_set, row_set;   // floats per producer set
 };
 __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int depth) {
@@ -119,7 +124,7 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int 
     S.prm_a1 = o; o += kCout;
     S.prm_b1 = o; o += kCout;
   }
-  S.ent_set = kEntRing * kGroup * 2;            // work-list entries, [group ring][pillar] (8 bytes each)
+  S.ent_set = ent_ring(depth) * kGroup * 2;     // work-list entries, [group ring][pillar] (8 bytes each)
   S.idx_set = (depth + 1) * kGroup;             // row numbers, [slot ring][pillar]
   S.mean_set = (depth + 1) * kGroup * 4;        // per-pillar mean + cell, [slot ring][pillar] (16 bytes each)
   S.row_set = (depth + 1) * nreg * kGroup;      // staged rows, [slot ring][16/8/4-byte chunk][pillar]
@@ -128,7 +133,9 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int 
   S.mean = o; o += kProdSets * S.mean_set;
   S.row = o; o += kProdSets * S.row_set;
   S.rows = o; o += kRowRing * kGroup;             // output row (pillar rank) / long-pillar index of each lane
-  S.ints = o; o += 96;                            // 10 mbarriers | tmem base | group prefix | list counts | list offsets
+  S.ostage = o; o += (kE1Threads * kOutRowBytes) / 4;   // E1 output staging: one padded 128-byte row per thread
+  S.gtab = o; o += kGTab;                         // (slots | is_seg << 8) of this CTA's first kGTab groups
+  S.ints = o; o += 96;                            // 14 mbarriers | tmem base | group prefix | list counts | list offsets
   S.total_bytes = o * 4;
   return S;
 }
@@ -148,6 +155,9 @@ pfn_slot_kernel(const TcArgs A) {
   extern __shared__ __align__(128) float smem[];
   constexpr int N0 = (kLayers == 2) ? kHidden : kCout;
   constexpr int NREG = RowCfg<kCfg>::nreg;
+  constexpr int NF = (kLayers == 2 && kCfg == 1) ? 4 : 2;        // depth of the front half (A0 / D0 buffers)
+  constexpr uint32_t kFS = 128 / NF;                             // columns per A0 / D0 buffer
+  constexpr uint32_t kA0Lo = 64 / NF;                            // offset of the lo part inside an A0 buffer
   const int k0 = kCfg ? RowCfg<kCfg>::k0 : A.k0;
   const int n_raw = kCfg ? RowCfg<kCfg>::n_raw : A.n_raw;
   const int raw_col0 = kCfg ? 1 : A.raw_col0;
@@ -156,10 +166,11 @@ pfn_slot_kernel(const TcArgs A) {
   const int tid = threadIdx.x, warp = tid >> 5;
   int* const s_rows = reinterpret_cast<int*>(smem + SP.rows);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + SP.ints);
-  uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 20);
-  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 24);      // [kNumLists + 1] group prefix, processing order
-  int* const s_cnt = reinterpret_cast<int*>(smem + SP.ints + 36);      // [kNumLists] entries per list
-  long long* const s_loff = reinterpret_cast<long long*>(smem + SP.ints + 48);   // [kNumLists] list offsets
+  uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 28);
+  int* const s_pre = reinterpret_cast<int*>(smem + SP.ints + 32);      // [kNumLists + 1] group prefix, processing order
+  int* const s_cnt = reinterpret_cast<int*>(smem + SP.ints + 44);      // [kNumLists] entries per list
+  long long* const s_loff = reinterpret_cast<long long*>(smem + SP.ints + 56);   // [kNumLists] list offsets
+  int* const s_gtab = reinterpret_cast<int*>(smem + SP.gtab);
 
   // ---- one-time setup: parameters -> smem, barriers, TMEM, work prefix ----
   {
@@ -177,10 +188,12 @@ pfn_slot_kernel(const TcArgs A) {
         smem[SP.prm_b1 + i] = A.params[PL.b1 + i];
       }
     if (tid == 0) {
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < kMaxNF; ++b) {
         mbar_init(&bars[kBarA0 + b], kGroup);
-        mbar_init(&bars[kBarA1 + b], kE0Threads);
         mbar_init(&bars[kBarD0 + b], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars[kBarA1 + b], kE0Threads);
         mbar_init(&bars[kBarD1 + b], 1);
         mbar_init(&bars[kBarF1 + b], kE1Threads);
       }
@@ -211,11 +224,22 @@ pfn_slot_kernel(const TcArgs A) {
     for (int t = 1; t < kNumLists; ++t) q += (w >= s_pre[t]) ? 1 : 0;
     return kNumLists - 1 - q;
   };
-  auto slots_of = [&](int w, bool& is_seg) {
+  auto slots_calc = [&](int w) {                 // slots | is_seg << 8 of work item w
     int q;
     const int list = list_of(w, q);
-    is_seg = (list == kSegList);
-    return is_seg ? kSegRows : class_slots(list);
+    return list == kSegList ? (kSegRows | 256) : class_slots(list);
+  };
+  // (slots, is-segment) of this CTA's first groups, looked up by every role at every group boundary
+  for (int gi = tid; gi < kGTab; gi += kPfnThreads) {
+    const long long w = (long long)blockIdx.x + (long long)gi * G;
+    s_gtab[gi] = (w < total) ? slots_calc((int)w) : 1;
+  }
+  __syncthreads();
+  // gi = index of the group among this CTA's groups (w = blockIdx.x + gi * G)
+  auto slots_of = [&](int w, int gi, bool& is_seg) {
+    const int v = gi < kGTab ? s_gtab[gi] : slots_calc(w);
+    is_seg = (v & 256) != 0;
+    return v & 255;
   };
 
   if (warp == kMmaWarp) {
@@ -230,15 +254,15 @@ pfn_slot_kernel(const TcArgs A) {
     uint32_t c0 = 0, c1 = 0;      // layer-0 ops / layer-1-type ops issued so far
     TRACE_DECL((tid & 31) == 0)
     auto issue_m0 = [&]() {
-      const uint32_t b = c0 & 1;
+      const uint32_t b = c0 % NF;
       TRACE(0, 20);
-      mbar_wait(&bars[kBarA0 + b], (c0 >> 1) & 1);
-      if (kLayers == 1 && c0 >= 2) mbar_wait(&bars[kBarA1 + b], ((c0 - 2) >> 1) & 1);   // D0[b] consumed by E0
+      mbar_wait(&bars[kBarA0 + b], (c0 / NF) & 1);
+      if (kLayers == 1 && c0 >= NF) mbar_wait(&bars[kBarA1 + b], ((c0 - NF) / NF) & 1);   // D0[b] consumed by E0
       TRACE(0, 21);
       tc_fence_after_sync();
       if (elect_one_sync()) {
-        mma_3xtf32_ts(tmem + kColD0 + b * 64, tmem + kColA0 + b * 64, tmem + kColA0 + b * 64 + 32, sw0h, sw0l, N0, k0 / 8,
-                      idesc0, false);
+        mma_3xtf32_ts(tmem + kColD0 + b * kFS, tmem + kColA0 + b * kFS, tmem + kColA0 + b * kFS + kA0Lo, sw0h, sw0l, N0,
+                      k0 / 8, idesc0, false);
         mma_commit(&bars[kBarD0 + b]);
       }
       __syncwarp();
@@ -259,15 +283,20 @@ pfn_slot_kernel(const TcArgs A) {
       __syncwarp();
       ++c1;
     };
-    // D0[b] is overwritten by the layer-0 MMA two slots later; that MMA is issued after the layer-1 MMA of the slot
-    // in between, which waited for A1, i.e. for E0 having read D0[b] (two-layer PFN).
-    if ((int)blockIdx.x < total) issue_m0();
-    for (int w = blockIdx.x; w < total; w += G) {
+    // Layer 0 runs up to NF - 1 slots ahead of layer 1.  D0[b] is overwritten by the layer-0 MMA NF slots later; that
+    // MMA is issued after the layer-1 MMA of the slot it replaces, which waited for A1, i.e. for E0 having read D0[b].
+    uint32_t nslots = 0;          // slots of this CTA
+    {
+      int gi = 0;
+      for (int w = blockIdx.x; w < total; w += G, ++gi) { bool sg; nslots += slots_of(w, gi, sg); }
+    }
+    for (int i = 0; i < NF - 1 && c0 < nslots; ++i) issue_m0();
+    int gi = 0;
+    for (int w = blockIdx.x; w < total; w += G, ++gi) {
       bool is_seg;
-      const int slots = slots_of(w, is_seg);
-      const bool more_groups = (w + G) < total;
+      const int slots = slots_of(w, gi, is_seg);
       for (int j = 0; j < slots; ++j) {
-        if (j + 1 < slots || more_groups) issue_m0();          // the NEXT slot's layer 0 goes in front of this slot's layer 1
+        if (c0 < nslots) issue_m0();                           // layer 0 of a LATER slot goes in front of this slot's layer 1
         if (kLayers == 2) issue_m1(sw1ah, sw1al);
       }
       if (kLayers == 2 && !is_seg) issue_m1(sw1bh, sw1bl);     // hoist: max0 . W1[:, 32:]^T once per pillar
@@ -292,6 +321,7 @@ pfn_slot_kernel(const TcArgs A) {
     constexpr int DEPTH = RowCfg<kCfg>::depth;
     constexpr int STAGES = DEPTH + 1;
     constexpr int LEAD = 2 * DEPTH + 2;                    // cursor A's lead over cursor B, in groups
+    constexpr int kEntRing = ent_ring(DEPTH);
     static_assert(4 * DEPTH + LEAD + 2 <= kEntRing, "entry ring too small");
     const int set = (tid - kProdWarp0 * 32) >> 7;          // 0 / 1
     const int p = tid & (kGroup - 1);                      // pillar of the group == TMEM lane (kProdWarp0 * 32 % 128 == 0)
@@ -306,7 +336,7 @@ pfn_slot_kernel(const TcArgs A) {
     struct Cursor { int w, j, slots, gi; bool seg; };      // work item, slot inside it, its slot count, group counter
     auto cur_load = [&](Cursor& c) {
       c.seg = false;
-      c.slots = (c.w < total) ? slots_of(c.w, c.seg) : 1;
+      c.slots = (c.w < total) ? slots_of(c.w, c.gi, c.seg) : 1;
     };
     auto cur_next = [&](Cursor& c) -> bool {              // advance one slot; true when a new group starts
       if (++c.j < c.slots) return false;
@@ -390,7 +420,6 @@ pfn_slot_kernel(const TcArgs A) {
     uint32_t c0 = 0;                                       // this set's slots built so far
     int id = 0;                                            // iteration number of cursor D
     const int n_feat = n_raw + (with_dist ? 7 : 6);
-    const uint32_t b = (uint32_t)set;                      // operand buffer == slot parity == set
     TRACE_DECL(p == 0)
     while (cd.w < total) {
       // ---- pipeline upkeep: entries / one row number / one row request per iteration ----
@@ -443,11 +472,13 @@ pfn_slot_kernel(const TcArgs A) {
       ed_[4] = __fsub_rn(y, __fadd_rn(__fmul_rn(cy, A.g.voxel_y), A.g.y_offset));
       ed_[5] = __fsub_rn(z, A.g.z_offset);
       ed_[6] = with_dist ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))) : 0.f;  // :124
-      // A0[set] is free once the layer-0 MMA that read this set's previous slot has completed
+      // slot t of the CTA lives in operand buffer t % NF, which is free once the layer-0 MMA of slot t - NF has completed
+      const uint32_t t_slot = 2 * c0 + (uint32_t)set;
+      const uint32_t b = t_slot % NF;
       TRACE(set ? 4 : 1, 11);
-      if (c0 >= 1) { mbar_wait(&bars[kBarD0 + b], (c0 - 1) & 1); tc_fence_after_sync(); }
+      if (t_slot >= NF) { mbar_wait(&bars[kBarD0 + b], (t_slot / NF - 1) & 1); tc_fence_after_sync(); }
       TRACE(set ? 4 : 1, 12);
-      const uint32_t dh = tmem + kColA0 + b * 64 + lane_base, dl = dh + 32;
+      const uint32_t dh = tmem + kColA0 + b * kFS + lane_base, dl = dh + kA0Lo;
 #pragma unroll
       for (int cc8 = 0; cc8 < kMaxCin; cc8 += 8) {
         if (cc8 < k0) {
@@ -495,18 +526,18 @@ pfn_slot_kernel(const TcArgs A) {
       const float* pb = smem + SP.prm_b0 + 16 * h;
       for (int w = blockIdx.x; w < total; w += G, ++gi) {
         bool is_seg;
-        const int slots = slots_of(w, is_seg);
+        const int slots = slots_of(w, gi, is_seg);
 #pragma unroll
         for (int i = 0; i < 16; ++i) max0[i] = 0.f;
         for (int j = 0; j < slots; ++j) {
-          const uint32_t b = c0 & 1, b1 = c1 & 1;
+          const uint32_t b = c0 % NF, b1 = c1 & 1;
           TRACE(2, 30);
-          mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
+          mbar_wait(&bars[kBarD0 + b], (c0 / NF) & 1);
           if (c1 >= 2) mbar_wait(&bars[kBarD1 + b1], ((c1 - 2) >> 1) & 1);     // A1[b1] read by the MMA two ops ago
           TRACE(2, 31);
           tc_fence_after_sync();
           uint32_t rr[16];
-          tmem_ld16_nowait(tmem + kColD0 + b * 64 + lane_base + 16 * h, rr);
+          tmem_ld16_nowait(tmem + kColD0 + b * kFS + lane_base + 16 * h, rr);
           tmem_ld_wait();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -561,17 +592,17 @@ pfn_slot_kernel(const TcArgs A) {
       float m1[32];
       for (int w = blockIdx.x; w < total; w += G, ++gi) {
         bool is_seg;
-        const int slots = slots_of(w, is_seg);
+        const int slots = slots_of(w, gi, is_seg);
 #pragma unroll
         for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
         for (int j = 0; j < slots; ++j) {
-          const uint32_t b = c0 & 1;
-          mbar_wait(&bars[kBarD0 + b], (c0 >> 1) & 1);
+          const uint32_t b = c0 % NF;
+          mbar_wait(&bars[kBarD0 + b], (c0 / NF) & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t rr[16];
-            tmem_ld16_nowait(tmem + kColD0 + b * 64 + lane_base + 32 * h + 16 * half, rr);
+            tmem_ld16_nowait(tmem + kColD0 + b * kFS + lane_base + 32 * h + 16 * half, rr);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) m1[16 * half + i] = fmaxf(m1[16 * half + i], __uint_as_float(rr[i]));
@@ -612,9 +643,11 @@ pfn_slot_kernel(const TcArgs A) {
     float m1[32];              // running max of the raw last-layer accumulators
     TRACE_DECL(tid == kE0Threads)
     int gi = 0;
+    // output staging: this thread's 128 bytes (padded rows); the warp reads the tile back transposed so that its stores are whole lines
+    float* const my_stage = smem + SP.ostage + (tid - kE0Threads) * (kOutRowBytes / 4);
     for (int w = blockIdx.x; w < total; w += G, ++gi) {
       bool is_seg;
-      const int slots = slots_of(w, is_seg);
+      const int slots = slots_of(w, gi, is_seg);
 #pragma unroll
       for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
       for (int j = 0; j < slots; ++j) {
@@ -645,24 +678,39 @@ pfn_slot_kernel(const TcArgs A) {
         tc_fence_after_sync();
         const float* pa = smem + SP.prm_a1 + 32 * h;
         const float* pb = smem + SP.prm_b1 + 32 * h;
-        float* dst = A.out + (int64_t)r * kCout + 32 * h;
+        __syncwarp();                                        // the previous group's rows have left the staging tile
+        TRACE(3, 39);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t rr[16];
           tmem_ld16_nowait(tmem + kColD1 + b * 64 + lane_base + 32 * h + 16 * half, rr);
           tmem_ld_wait();
           if (half == 1) { tc_fence_before_sync(); mbar_arrive(&bars[kBarF1 + b]); }
-          if (r >= 0) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const int c = 16 * half + i;
-              const float4 al = ld4(pa + c), be = ld4(pb + c);
-              st_global_f4(dst + c,
-                           fmaxf(fmaf(__fadd_rn(m1[c + 0], __uint_as_float(rr[i + 0])), al.x, be.x), 0.f),
-                           fmaxf(fmaf(__fadd_rn(m1[c + 1], __uint_as_float(rr[i + 1])), al.y, be.y), 0.f),
-                           fmaxf(fmaf(__fadd_rn(m1[c + 2], __uint_as_float(rr[i + 2])), al.z, be.z), 0.f),
-                           fmaxf(fmaf(__fadd_rn(m1[c + 3], __uint_as_float(rr[i + 3])), al.w, be.w), 0.f));
-            }
+          for (int i = 0; i < 16; i += 4) {
+            const int c = 16 * half + i;
+            const float4 al = ld4(pa + c), be = ld4(pb + c);
+            float4 o;
+            o.x = fmaxf(fmaf(__fadd_rn(m1[c + 0], __uint_as_float(rr[i + 0])), al.x, be.x), 0.f);
+            o.y = fmaxf(fmaf(__fadd_rn(m1[c + 1], __uint_as_float(rr[i + 1])), al.y, be.y), 0.f);
+            o.z = fmaxf(fmaf(__fadd_rn(m1[c + 2], __uint_as_float(rr[i + 2])), al.z, be.z), 0.f);
+            o.w = fmaxf(fmaf(__fadd_rn(m1[c + 3], __uint_as_float(rr[i + 3])), al.w, be.w), 0.f);
+            *reinterpret_cast<float4*>(my_stage + c) = o;
+          }
+        }
+        __syncwarp();
+        TRACE(3, 40);
+        // transposed read-back: every store instruction of the warp writes 4 whole 128-byte lines
+        {
+          const int lane = tid & 31;
+          const float* wstage = smem + SP.ostage + ((tid - kE0Threads) & ~31) * (kOutRowBytes / 4);
+          const int* rows = s_rows + (gi % kRowRing) * kGroup + (p & ~31);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + (lane >> 3), chunk = lane & 7;
+            const int rr_ = rows[row];
+            const float4 v = ld4(wstage + row * (kOutRowBytes / 4) + chunk * 4);
+            if (rr_ >= 0) *reinterpret_cast<float4*>(A.out + (int64_t)rr_ * kCout + 32 * h + chunk * 4) = v;
           }
         }
         TRACE(3, 38);

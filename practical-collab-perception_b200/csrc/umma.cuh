@@ -199,6 +199,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
+// ---- bulk (TMA) copies shared -> global: one thread sends `bytes` (multiple of 16) as whole lines ----
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- TF32 split ------------------------------------------------------------------------------------
 // x = hi + lo exactly, hi has a 10-bit mantissa (truncation); the tensor core drops the low 13 bits of lo.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
