@@ -524,21 +524,35 @@ pfn_slot_kernel(const TcArgs A) {
       float max0[16];          // layer-0 running max, this thread's 16 channels
       const float* pa = smem + SP.prm_a0 + 16 * h;
       const float* pb = smem + SP.prm_b0 + 16 * h;
+      // Software pipeline: the accumulators of the NEXT slot are requested (tcgen05.ld) as soon as the registers of the
+      // current one are consumed - half by half - so that the load latency overlaps the math, the tcgen05.st drain and
+      // the hand-over of the current slot.
+      uint32_t nslots = 0;
+      {
+        int g2 = 0;
+        for (int w = blockIdx.x; w < total; w += G, ++g2) { bool sg; nslots += slots_of(w, g2, sg); }
+      }
+      uint32_t rr[16];
+      auto d0_addr = [&](uint32_t t) { return tmem + kColD0 + (t % NF) * kFS + lane_base + 16 * h; };
+      if (nslots > 0) {
+        mbar_wait(&bars[kBarD0 + 0], 0);
+        tc_fence_after_sync();
+        tmem_ld16_nowait(d0_addr(0), rr);
+      }
       for (int w = blockIdx.x; w < total; w += G, ++gi) {
         bool is_seg;
         const int slots = slots_of(w, gi, is_seg);
 #pragma unroll
         for (int i = 0; i < 16; ++i) max0[i] = 0.f;
         for (int j = 0; j < slots; ++j) {
-          const uint32_t b = c0 % NF, b1 = c1 & 1;
+          const uint32_t b1 = c1 & 1;
+          const bool more = (c0 + 1) < nslots;
           TRACE(2, 30);
-          mbar_wait(&bars[kBarD0 + b], (c0 / NF) & 1);
+          tmem_ld_wait();                                                       // rr = accumulators of slot c0
           if (c1 >= 2) mbar_wait(&bars[kBarD1 + b1], ((c1 - 2) >> 1) & 1);     // A1[b1] read by the MMA two ops ago
+          if (more) mbar_wait(&bars[kBarD0 + (c0 + 1) % NF], ((c0 + 1) / NF) & 1);
           TRACE(2, 31);
           tc_fence_after_sync();
-          uint32_t rr[16];
-          tmem_ld16_nowait(tmem + kColD0 + b * kFS + lane_base + 16 * h, rr);
-          tmem_ld_wait();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float hi[8], lo[8];
@@ -554,6 +568,10 @@ pfn_slot_kernel(const TcArgs A) {
             }
             tmem_st8(tmem + kColA1 + b1 * 64 + lane_base + 16 * h + 8 * half, hi);
             tmem_st8(tmem + kColA1 + b1 * 64 + 32 + lane_base + 16 * h + 8 * half, lo);
+            if (more) {                                                         // these 8 registers are free again
+              if (half == 0) tmem_ld8_nowait(d0_addr(c0 + 1), rr[0], rr[1], rr[2], rr[3], rr[4], rr[5], rr[6], rr[7]);
+              else tmem_ld8_nowait(d0_addr(c0 + 1) + 8, rr[8], rr[9], rr[10], rr[11], rr[12], rr[13], rr[14], rr[15]);
+            }
           }
           tmem_st_wait();
           tc_fence_before_sync();
