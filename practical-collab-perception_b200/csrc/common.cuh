@@ -68,9 +68,10 @@ __host__ __device__ inline int class_of(int n) {
 // ---------------------------------------------------------------------------------------------
 // workspace layout.  One contiguous caller-owned block:
 //   hdr        int32[64]        counts (PCP_COUNT_*), scan ticket, list lengths, long-pillar count
-//   scan_state uint64[tiles]    decoupled look-back tile descriptors
-//   cell       int32[cells]     per-cell point count -> (after the scan) pillar rank or -1;
+//   tile_info  int32[tiles][16] per-tile counters of the cell scan (points, pillars, per-class pillars, long pillars, ...)
+//   cell       int32[cells]     per-cell point count -> (after the scan) first sorted position of the cell's points, or -1;
 //                               x-major like the reference's linear key: b*nx*ny + cx*ny + cy
+//   cell_rank  int32[cells]     pillar rank of the cell or -1 (same order)
 //   key        int32[N]         linear key of every input row, -1 = culled
 //   within     int32[N]         arrival slot of the row inside its cell
 //   seg_off    int32[cap+1]     first sorted position of each pillar (exclusive scan of counts)
@@ -82,10 +83,10 @@ __host__ __device__ inline int class_of(int n) {
 //   long_table int4[N/33+1]     long pillars {pillar rank, first sorted position, rows, first segment}
 //   long_mean  float4[N/33+1]   mean xyz of each long pillar (sequential fp32 sum in ascending row order)
 //   long_acc   uint32[96*(N/33+1)] per long pillar: ordered-int running max of layer-0 (32) and layer-1 (64) values
-// [hdr | scan_state | cell] is cleared by one memset at the start of pcp_voxelize().
+// [hdr | tile_info | cell] is cleared by one memset at the start of pcp_voxelize().
 // ---------------------------------------------------------------------------------------------
 constexpr int kHdrInts = 64;
-constexpr int kHdrScanTicket = 16;   // dynamic tile id of the scan
+constexpr int kHdrPrepTicket = 16;   // [16, 20): work tickets of pillar_prep_kernel (long, mid-16, mid-32, short)
 constexpr int kHdrListCount = 32;    // [32, 32 + kNumLists): entries in each list
 constexpr int kHdrLongCount = 48;    // long pillars
 constexpr int kHdrBigCount = 49;     // long pillars above kWarpLongMax rows (handled by a whole CTA in pillar_prep_kernel)
@@ -106,7 +107,7 @@ __host__ __device__ inline void unpack_entry(unsigned long long e, int& r, int& 
 }
 
 struct WsLayout {
-  size_t hdr, scan_state, cell, key, within, seg_off, sorted_idx, lists, mean, long_table, big_list, long_mean, long_acc, total;
+  size_t hdr, tile_info, cell, cell_rank, key, within, seg_off, sorted_idx, lists, mean, long_table, big_list, long_mean, long_acc, total;
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
   int64_t cells, cap, scan_tiles, seg_cap, long_cap;
   ListOffsets lo;
@@ -123,9 +124,10 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   L.long_cap = n / (kSegRows + 1) + 1;
   size_t o = 0;
   L.hdr = o;         o = align_up(o + sizeof(int32_t) * kHdrInts, 256);
-  L.scan_state = o;  o = align_up(o + sizeof(uint64_t) * (size_t)(L.scan_tiles + 1), 256);
+  L.tile_info = o;   o = align_up(o + sizeof(int32_t) * 17 * (size_t)(L.scan_tiles + 1), 256);   // records + per-tile frame count
   L.cell = o;        o = align_up(o + sizeof(int32_t) * (size_t)L.cells, 256);
   L.clear_bytes = o;
+  L.cell_rank = o;   o = align_up(o + sizeof(int32_t) * (size_t)L.cells, 256);
   L.key = o;         o = align_up(o + sizeof(int32_t) * (size_t)(n + 1), 256);
   L.within = o;      o = align_up(o + sizeof(int32_t) * (size_t)(n + 1), 256);
   L.seg_off = o;     o = align_up(o + sizeof(int32_t) * (size_t)(L.cap + 2), 256);
@@ -152,8 +154,9 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
 
 struct WsView {
   int32_t* hdr;
-  unsigned long long* scan_state;
+  int32_t* tile_info;
   int32_t* cell;
+  int32_t* cell_rank;
   int32_t* key;
   int32_t* within;
   int32_t* seg_off;
@@ -170,8 +173,9 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   char* p = static_cast<char*>(base);
   WsView v;
   v.hdr = reinterpret_cast<int32_t*>(p + L.hdr);
-  v.scan_state = reinterpret_cast<unsigned long long*>(p + L.scan_state);
+  v.tile_info = reinterpret_cast<int32_t*>(p + L.tile_info);
   v.cell = reinterpret_cast<int32_t*>(p + L.cell);
+  v.cell_rank = reinterpret_cast<int32_t*>(p + L.cell_rank);
   v.key = reinterpret_cast<int32_t*>(p + L.key);
   v.within = reinterpret_cast<int32_t*>(p + L.within);
   v.seg_off = reinterpret_cast<int32_t*>(p + L.seg_off);

@@ -120,7 +120,7 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
   PCP_REQUIRE(pillar_features, PCP_E_INVALID, "pcp_bev_scatter_ws: null pillar_features");
   const WsView W = ws_view(const_cast<void*>(workspace), L);
   canvas_kernel<true><<<canvas_grid(grid->nx, grid->ny, num_frames), kTileY * 32, 0, stream>>>(
-      pillar_features, W.cell, channels, grid->nx, grid->ny, canvas_out);
+      pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
   PCP_LAUNCH_CHECK("canvas_kernel<ws>");
   return 0;
 }

@@ -25,76 +25,67 @@ namespace pcp {
 // ------------------------------------------------------------------------------------------------
 // 1. quantise + count
 // ------------------------------------------------------------------------------------------------
+constexpr int kPtsPerThread = 4;   // independent rows per thread: 4 loads, then 4 atomics, then 4 stores in flight
+
 template <bool kVec4>
 __global__ void __launch_bounds__(256)
 quantise_count_kernel(const float* __restrict__ points, int64_t stride, int64_t n, int32_t frames,
                       pcp_grid g, int32_t* __restrict__ cell, int32_t* __restrict__ key,
                       int32_t* __restrict__ within, int32_t* __restrict__ hdr) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* row = points + i * stride;
-  float bf, x, y;
-  if (kVec4) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(row));
-    bf = v.x; x = v.y; y = v.z;
-  } else {
-    bf = __ldg(row); x = __ldg(row + 1); y = __ldg(row + 2);
-  }
-  const float qx = quantise(x, g.range_min_x, g.voxel_x);
-  const float qy = quantise(y, g.range_min_y, g.voxel_y);
-  // reference: (coords >= 0) & (coords < grid) on the int-cast floor (dynamic_pillar_vfe.py:99);
-  // qx, qy are integral floats, the float compare is the same predicate and is false for NaN.
-  bool keep = (qx >= 0.f) && (qx < (float)g.nx) && (qy >= 0.f) && (qy < (float)g.ny);
-  int32_t k = -1, w = 0;
-  if (keep) {
-    // points[:, 0].int() truncates toward zero (:104)
-    if (!(bf > -1.f) || !(bf < (float)frames)) {
-      atomicAdd(&hdr[PCP_COUNT_BAD_FRAME], 1);
-    } else {
-      const int32_t b = (int32_t)bf;
-      k = b * (g.nx * g.ny) + (int32_t)qx * g.ny + (int32_t)qy;
-      w = atomicAdd(&cell[k], 1);
+  const int64_t base = (int64_t)blockIdx.x * (256 * kPtsPerThread) + threadIdx.x;
+  float bf[kPtsPerThread], x[kPtsPerThread], y[kPtsPerThread];
+#pragma unroll
+  for (int u = 0; u < kPtsPerThread; ++u) {
+    const int64_t i = base + u * 256;
+    bf[u] = 0.f; x[u] = 0.f; y[u] = 0.f;
+    if (i < n) {
+      const float* row = points + i * stride;
+      if (kVec4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+        bf[u] = v.x; x[u] = v.y; y[u] = v.z;
+      } else {
+        bf[u] = __ldg(row); x[u] = __ldg(row + 1); y[u] = __ldg(row + 2);
+      }
     }
   }
-  key[i] = k;
-  within[i] = w;
+  int32_t k[kPtsPerThread], w[kPtsPerThread];
+#pragma unroll
+  for (int u = 0; u < kPtsPerThread; ++u) {
+    const float qx = quantise(x[u], g.range_min_x, g.voxel_x);
+    const float qy = quantise(y[u], g.range_min_y, g.voxel_y);
+    // reference: (coords >= 0) & (coords < grid) on the int-cast floor (dynamic_pillar_vfe.py:99);
+    // qx, qy are integral floats, the float compare is the same predicate and is false for NaN.
+    const bool keep = (base + u * 256 < n) && (qx >= 0.f) && (qx < (float)g.nx) && (qy >= 0.f) && (qy < (float)g.ny);
+    k[u] = -1; w[u] = 0;
+    if (keep) {
+      // points[:, 0].int() truncates toward zero (:104)
+      if (!(bf[u] > -1.f) || !(bf[u] < (float)frames)) {
+        atomicAdd(&hdr[PCP_COUNT_BAD_FRAME], 1);
+      } else {
+        k[u] = (int32_t)bf[u] * (g.nx * g.ny) + (int32_t)qx * g.ny + (int32_t)qy;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kPtsPerThread; ++u)
+    if (k[u] >= 0) w[u] = atomicAdd(&cell[k[u]], 1);
+#pragma unroll
+  for (int u = 0; u < kPtsPerThread; ++u) {
+    const int64_t i = base + u * 256;
+    if (i < n) { key[i] = k[u]; within[i] = w[u]; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2. single-pass scan over the cells (decoupled look-back)
-//    packed 64-bit partial: [63:62] status, [61:32] sum of counts (points), [31:0] sum of flags (pillars)
+// 2. scan over the cells in two launches: per-tile sums, then every tile adds up the sums of the tiles before it
+//    (the whole array of tile sums is a few kB in L2; no spinning, no tile-to-tile dependency chain)
+//    packed 64-bit partial: [61:32] sum of counts (points), [31:0] sum of flags (pillars)
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned long long kStatusAgg = 1ull << 62;
-constexpr unsigned long long kStatusPrefix = 2ull << 62;
-constexpr unsigned long long kPayloadMask = (1ull << 62) - 1;
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = kScanTileCells / kScanThreads;  // 8
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t ny,
-                  unsigned long long* __restrict__ state, int32_t* __restrict__ hdr,
-                  int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
-                  int32_t* __restrict__ pillar_count, unsigned long long* __restrict__ lists, const ListOffsets lo,
-                  int4* __restrict__ long_table, int32_t* __restrict__ big_list, int64_t scan_tiles) {
-  __shared__ int s_tile;
-  __shared__ int s_cls[kNumClasses], s_cls_base[kNumClasses];
-  __shared__ unsigned long long s_warp[kScanThreads / 32];
-  __shared__ unsigned long long s_prefix;
-  __shared__ int s_red[2][kScanThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(&hdr[kHdrScanTicket], 1);
-  if (tid < kNumClasses) s_cls[tid] = 0;
-  __syncthreads();
-  const int64_t tile = s_tile;
-  const int64_t base = tile * kScanTileCells + (int64_t)tid * kScanItems;
-
-  int32_t c[kScanItems];
+__device__ __forceinline__ void load_tile_counts(const int32_t* __restrict__ cell, int64_t base, int64_t cells,
+                                                 int32_t (&c)[kScanItems]) {
   if (base + kScanItems <= cells) {
     const int4 a = *reinterpret_cast<const int4*>(cell + base);
     const int4 b = *reinterpret_cast<const int4*>(cell + base + 4);
@@ -103,14 +94,135 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) c[j] = (base + j < cells) ? cell[base + j] : 0;
   }
-  unsigned long long mine = 0;
-  int cmax = 0, last_nonempty = -1;
+}
+
+// per-tile record written by tile_sums_kernel (16 ints)
+constexpr int kTiPoints = 0;     // points in the tile
+constexpr int kTiPillars = 1;    // non-empty cells
+constexpr int kTiClass = 2;      // [2, 12): pillars per length class
+constexpr int kTiLong = 12;      // long pillars
+constexpr int kTiSegs = 13;      // segments of the long pillars
+constexpr int kTiBig = 14;       // long pillars above kWarpLongMax rows
+constexpr int kTiMax = 15;       // largest pillar (max, not a sum)
+constexpr int kTiInts = 16;
+
+__global__ void __launch_bounds__(kScanThreads)
+tile_sums_kernel(const int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t ny, int32_t* __restrict__ tile_info,
+                 int32_t* __restrict__ tile_frames) {
+  __shared__ int s_acc[kTiInts];
+  __shared__ int s_fr;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < kTiInts) s_acc[tid] = 0;
+  if (tid == 0) s_fr = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kScanTileCells + (int64_t)tid * kScanItems;
+  int32_t c[kScanItems];
+  load_tile_counts(cell, base, cells, c);
+  int pts = 0, pil = 0, cmax = 0, last_nonempty = -1;
+  unsigned long long cls = 0;           // 10 x 6-bit counters: pillars of this thread per class (at most 8 each)
+  int nlong = 0, nseg = 0, nbig = 0;
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
-    mine += ((unsigned long long)(uint32_t)c[j] << 32) | (c[j] > 0 ? 1ull : 0ull);
-    cmax = max(cmax, c[j]);
-    if (c[j] > 0) last_nonempty = j;
+    if (c[j] > 0) {
+      pts += c[j]; ++pil; cmax = max(cmax, c[j]); last_nonempty = j;
+      if (c[j] <= kSegRows) cls += 1ull << (6 * class_of(c[j]));
+      else { ++nlong; nseg += (c[j] + kSegRows - 1) / kSegRows; nbig += (c[j] > kWarpLongMax) ? 1 : 0; }
+    }
   }
+  // warp reductions, then one shared-memory atomic per warp and counter
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    pts += __shfl_xor_sync(0xffffffffu, pts, d);
+    pil += __shfl_xor_sync(0xffffffffu, pil, d);
+    cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
+  }
+  if (lane == 0) { atomicAdd(&s_acc[kTiPoints], pts); atomicAdd(&s_acc[kTiPillars], pil); atomicMax(&s_acc[kTiMax], cmax); }
+#pragma unroll
+  for (int k = 0; k < kNumClasses; ++k) {
+    int v = (int)((cls >> (6 * k)) & 63ull);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0 && v) atomicAdd(&s_acc[kTiClass + k], v);
+  }
+  if (__any_sync(0xffffffffu, nlong > 0)) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      nlong += __shfl_xor_sync(0xffffffffu, nlong, d);
+      nseg += __shfl_xor_sync(0xffffffffu, nseg, d);
+      nbig += __shfl_xor_sync(0xffffffffu, nbig, d);
+    }
+    if (lane == 0) { atomicAdd(&s_acc[kTiLong], nlong); atomicAdd(&s_acc[kTiSegs], nseg); atomicAdd(&s_acc[kTiBig], nbig); }
+  }
+  // frame of the last non-empty cell of the tile + 1 (0: empty tile); cells < 2^31 (checked by the host)
+  int fr = 0;
+  if (last_nonempty >= 0) fr = (int)(((uint32_t)base + (uint32_t)last_nonempty) / ((uint32_t)nx * (uint32_t)ny)) + 1;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) fr = max(fr, __shfl_xor_sync(0xffffffffu, fr, d));
+  if (lane == 0 && fr) atomicMax(&s_fr, fr);
+  __syncthreads();
+  if (tid < kTiInts) tile_info[(int64_t)blockIdx.x * kTiInts + tid] = s_acc[tid];
+  if (tid == 0) tile_frames[blockIdx.x] = s_fr;
+}
+
+// Second launch: every tile sums the records of the tiles before it (its exclusive prefix of every counter), scans its own
+// cells and writes, for every non-empty cell, the pillar rank, the first sorted position, voxel_coords and the pillar's
+// work-list entry.  No global atomics: list positions, long-pillar indices and segment ranges come from the prefixes.
+__global__ void __launch_bounds__(kScanThreads)
+scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, int64_t cells, int32_t nx, int32_t ny,
+                  const int32_t* __restrict__ tile_info, const int32_t* __restrict__ tile_frames, int32_t* __restrict__ hdr,
+                  int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
+                  int32_t* __restrict__ pillar_count, unsigned long long* __restrict__ lists, const ListOffsets lo,
+                  int4* __restrict__ long_table, int32_t* __restrict__ big_list, int64_t scan_tiles) {
+  __shared__ int s_cls[kTiInts];                 // running in-tile counters (classes, long, segs, big)
+  __shared__ int s_before[kTiInts];              // sums over the tiles before this one (kTiMax: max)
+  __shared__ int s_part[kScanThreads / 32][kTiInts];
+  __shared__ unsigned long long s_warp[kScanThreads / 32];
+  __shared__ long long s_lo[kNumClasses];
+  __shared__ int s_frames[kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kTiInts) s_cls[tid] = 0;
+  if (tid < kNumClasses) s_lo[tid] = lo.off[tid];
+  const int64_t tile = blockIdx.x;
+  const int64_t base = tile * kScanTileCells + (int64_t)tid * kScanItems;
+  // ---- exclusive prefix of the tile records ----
+  {
+    int acc[kTiInts];
+#pragma unroll
+    for (int i = 0; i < kTiInts; ++i) acc[i] = 0;
+    int frames = 0;
+    if (tile == scan_tiles - 1)
+      for (int64_t t = tid; t <= tile; t += kScanThreads) frames = max(frames, __ldg(tile_frames + t));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) frames = max(frames, __shfl_xor_sync(0xffffffffu, frames, d));
+    if (lane == 0) s_frames[warp] = frames;
+    for (int64_t t = tid; t < tile; t += kScanThreads) {
+      const int4* rec = reinterpret_cast<const int4*>(tile_info + t * kTiInts);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 v = __ldg(rec + q);
+        acc[4 * q + 0] += v.x; acc[4 * q + 1] += v.y; acc[4 * q + 2] += v.z;
+        if (q < 3) acc[4 * q + 3] += v.w; else acc[kTiMax] = max(acc[kTiMax], v.w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kTiInts; ++i) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const int o = __shfl_xor_sync(0xffffffffu, acc[i], d);
+        acc[i] = (i == kTiMax) ? max(acc[i], o) : acc[i] + o;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kTiInts; ++i) s_part[warp][i] = acc[i];
+    }
+  }
+
+  int32_t c[kScanItems];
+  load_tile_counts(cell, base, cells, c);
+  unsigned long long mine = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) mine += ((unsigned long long)(uint32_t)c[j] << 32) | (c[j] > 0 ? 1ull : 0ull);
   // block exclusive scan of `mine`
   unsigned long long incl = mine;
 #pragma unroll
@@ -119,113 +231,92 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
     if (lane >= d) incl += t;
   }
   if (lane == 31) s_warp[warp] = incl;
-  // per-tile reductions for the header (max points per pillar, last frame that owns a pillar)
-  const int64_t nxy = (int64_t)nx * ny;
-  int fr = last_nonempty >= 0 ? (int)((base + last_nonempty) / nxy) + 1 : 0;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
-    fr = max(fr, __shfl_xor_sync(0xffffffffu, fr, d));
-  }
-  if (lane == 0) { s_red[0][warp] = cmax; s_red[1][warp] = fr; }
   __syncthreads();
+  if (tid < kTiInts) {
+    int v = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) v = (tid == kTiMax) ? max(v, s_part[w][tid]) : v + s_part[w][tid];
+    s_before[tid] = v;
+  }
   unsigned long long warp_excl = 0, tile_total = 0;
 #pragma unroll
   for (int w = 0; w < kScanThreads / 32; ++w) {
     if (w < warp) warp_excl += s_warp[w];
     tile_total += s_warp[w];
   }
-  if (warp == 0) {
-    unsigned long long running = 0;
-    if (tile == 0) {
-      if (lane == 0) atomicExch(&state[0], kStatusPrefix | tile_total);
-    } else {
-      if (lane == 0) atomicExch(&state[tile], kStatusAgg | tile_total);
-      int64_t j = tile - 1;
-      while (true) {
-        const int64_t idx = j - lane;
-        unsigned long long v = kStatusPrefix;  // virtual predecessor of tile 0: prefix 0
-        if (idx >= 0) {
-          v = ld_volatile_u64(&state[idx]);
-          while ((v >> 62) == 0) v = ld_volatile_u64(&state[idx]);
-        }
-        const unsigned pref = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-        const int first = pref ? (__ffs(pref) - 1) : 32;
-        unsigned long long contrib = (lane <= first) ? (v & kPayloadMask) : 0ull;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-        running += contrib;
-        if (pref) break;
-        j -= 32;
-      }
-      if (lane == 0) atomicExch(&state[tile], kStatusPrefix | ((running + tile_total) & kPayloadMask));
-    }
-    if (lane == 0) {
-      s_prefix = running;
-      int m = 0, f = 0;
-#pragma unroll
-      for (int w = 0; w < kScanThreads / 32; ++w) { m = max(m, s_red[0][w]); f = max(f, s_red[1][w]); }
-      if (m > 0) {
-        atomicMax(&hdr[PCP_COUNT_MAX_PER_PILLAR], m);
-        atomicMax(&hdr[PCP_COUNT_FRAMES], f);
-      }
-      if (tile == scan_tiles - 1) {
-        const unsigned long long tot = running + tile_total;
-        const int32_t P = (int32_t)(tot & 0xffffffffull);
-        const int32_t Nk = (int32_t)((tot >> 32) & 0x3fffffffull);
-        hdr[PCP_COUNT_PILLARS] = P;
-        hdr[PCP_COUNT_KEPT] = Nk;
-        seg_off[P] = Nk;
-      }
-    }
-  }
   __syncthreads();
-  unsigned long long excl = s_prefix + warp_excl + (incl - mine);
+  const unsigned long long before = ((unsigned long long)(uint32_t)s_before[kTiPoints] << 32) | (uint32_t)s_before[kTiPillars];
+  // cells < 2^31 (checked by the host): 32-bit coordinates of this thread's first cell, updated incrementally below
+  const uint32_t nxy = (uint32_t)nx * (uint32_t)ny;
+  const uint32_t base32 = (uint32_t)base;
+  const uint32_t b0 = base32 / nxy, rem0 = base32 - b0 * nxy;
+  const uint32_t cx0 = rem0 / (uint32_t)ny, cy0 = rem0 - cx0 * (uint32_t)ny;
+  if (tile == scan_tiles - 1) {
+    // the last tile knows every total: counts block, list lengths, long-pillar counters
+    const int32_t* own = tile_info + tile * kTiInts;
+    if (tid == 0) {
+      const unsigned long long tot = before + tile_total;
+      const int32_t P = (int32_t)(tot & 0xffffffffull);
+      const int32_t Nk = (int32_t)((tot >> 32) & 0x3fffffffull);
+      hdr[PCP_COUNT_PILLARS] = P;
+      hdr[PCP_COUNT_KEPT] = Nk;
+      hdr[PCP_COUNT_MAX_PER_PILLAR] = max(s_before[kTiMax], own[kTiMax]);
+      seg_off[P] = Nk;
+      hdr[kHdrLongCount] = s_before[kTiLong] + own[kTiLong];
+      hdr[kHdrListCount + kSegList] = s_before[kTiSegs] + own[kTiSegs];
+      hdr[kHdrBigCount] = s_before[kTiBig] + own[kTiBig];
+      int frames = 0;
+#pragma unroll
+      for (int w = 0; w < kScanThreads / 32; ++w) frames = max(frames, s_frames[w]);
+      hdr[PCP_COUNT_FRAMES] = frames;     // max frame index among pillars + 1
+    }
+    if (tid < kNumClasses) hdr[kHdrListCount + tid] = s_before[kTiClass + tid] + own[kTiClass + tid];
+  }
+  unsigned long long excl = before + warp_excl + (incl - mine);
   unsigned long long my_ent[kScanItems];          // packed list entry
   int my_slot[kScanItems];                        // class << 16 | slot inside this tile's class batch
+  int32_t b = (int32_t)b0, cx = (int32_t)cx0, cy = (int32_t)cy0;
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     const int64_t idx = base + j;
     my_ent[j] = 0ull; my_slot[j] = -1;
+    if (j > 0) {                                  // next cell of the x-major key order
+      if (++cy == ny) { cy = 0; if (++cx == nx) { cx = 0; ++b; } }
+    }
     if (idx < cells) {
       if (c[j] > 0) {
         const int32_t r = (int32_t)(excl & 0xffffffffull);
         const int32_t off = (int32_t)((excl >> 32) & 0x3fffffffull);
         seg_off[r] = off;
-        const int32_t b = (int32_t)(idx / nxy);
-        const int32_t rem = (int32_t)(idx - (int64_t)b * nxy);
-        const int32_t cx = rem / ny, cy = rem - cx * ny;
         // (frame, z = 0, y, x): dynamic_pillar_vfe.py:138-143 after the [0, 3, 2, 1] reorder
         *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4(b, 0, cy, cx);
         if (pillar_count) pillar_count[r] = c[j];
-        cell[idx] = r;
+        cell[idx] = off;
+        cell_rank[idx] = r;
         if (c[j] <= kSegRows) {
           const int k = class_of(c[j]);
           my_ent[j] = pack_entry(r, off, c[j]);
-          my_slot[j] = (k << 16) | atomicAdd(&s_cls[k], 1);
+          my_slot[j] = (k << 16) | atomicAdd(&s_cls[kTiClass + k], 1);
         } else {
-          // long pillar: reserve its segments; sort_long_kernel fills the segment table
+          // long pillar: its index, its segment range (pillar_prep_kernel writes the segment entries)
           const int nseg = (c[j] + kSegRows - 1) / kSegRows;
-          const int li = atomicAdd(&hdr[kHdrLongCount], 1);
-          const int sb = atomicAdd(&hdr[kHdrListCount + kSegList], nseg);
+          const int li = s_before[kTiLong] + atomicAdd(&s_cls[kTiLong], 1);
+          const int sb = s_before[kTiSegs] + atomicAdd(&s_cls[kTiSegs], nseg);
           long_table[li] = make_int4(r, off, c[j], sb);
-          if (c[j] > kWarpLongMax) big_list[atomicAdd(&hdr[kHdrBigCount], 1)] = li;
+          if (c[j] > kWarpLongMax) big_list[s_before[kTiBig] + atomicAdd(&s_cls[kTiBig], 1)] = li;
         }
         excl += ((unsigned long long)(uint32_t)c[j] << 32) | 1ull;
       } else {
         cell[idx] = -1;
+        cell_rank[idx] = -1;
       }
     }
   }
-  // work lists: one global atomic per (tile, class)
-  __syncthreads();
-  if (tid < kNumClasses) s_cls_base[tid] = s_cls[tid] > 0 ? atomicAdd(&hdr[kHdrListCount + tid], s_cls[tid]) : 0;
-  __syncthreads();
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     if (my_slot[j] >= 0) {
       const int k = my_slot[j] >> 16;
-      lists[lo.off[k] + s_cls_base[k] + (my_slot[j] & 0xffff)] = my_ent[j];
+      lists[s_lo[k] + s_before[kTiClass + k] + (my_slot[j] & 0xffff)] = my_ent[j];
     }
   }
 }
@@ -235,22 +326,30 @@ scan_cells_kernel(int32_t* __restrict__ cell, int64_t cells, int32_t nx, int32_t
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within,
-             const int32_t* __restrict__ cell, const int32_t* __restrict__ seg_off, int64_t n,
+             const int32_t* __restrict__ cell, const int32_t* __restrict__ cell_rank, int64_t n,
              int32_t* __restrict__ sorted_idx, int32_t* __restrict__ point_pillar,
              const int32_t* __restrict__ hdr, int32_t* __restrict__ counts_out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && counts_out) {
+  const int64_t base = (int64_t)blockIdx.x * (256 * kPtsPerThread) + threadIdx.x;
+  if (base == 0 && counts_out) {
 #pragma unroll
     for (int j = 0; j < PCP_COUNTS_LEN; ++j) counts_out[j] = hdr[j];
   }
-  if (i >= n) return;
-  const int32_t k = key[i];
-  int32_t r = -1;
-  if (k >= 0) {
-    r = __ldg(cell + k);
-    sorted_idx[__ldg(seg_off + r) + within[i]] = (int32_t)i;
+  int32_t k[kPtsPerThread], w[kPtsPerThread], o[kPtsPerThread];
+#pragma unroll
+  for (int u = 0; u < kPtsPerThread; ++u) {
+    const int64_t i = base + u * 256;
+    k[u] = (i < n) ? key[i] : -1;
+    w[u] = (i < n) ? within[i] : 0;
   }
-  if (point_pillar) point_pillar[i] = r;
+  // one random 4-byte read per point: the cell's first sorted position (the scan left it in the histogram array)
+#pragma unroll
+  for (int u = 0; u < kPtsPerThread; ++u) o[u] = (k[u] >= 0) ? __ldg(cell + k[u]) : -1;
+#pragma unroll
+  for (int u = 0; u < kPtsPerThread; ++u) {
+    const int64_t i = base + u * 256;
+    if (k[u] >= 0) sorted_idx[o[u] + w[u]] = (int32_t)i;
+    if (point_pillar && i < n) point_pillar[i] = (k[u] >= 0) ? __ldg(cell_rank + k[u]) : -1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,6 +388,83 @@ __device__ __forceinline__ float pack_cell(float x, float y, const pcp_grid& g) 
   return __uint_as_float((cx & 0xffffu) | (cy << 16));
 }
 
+// one pillar of at most NMAX rows (one length class) per thread: order the row numbers (a sum of two values does not
+// depend on the order, so classes 0 and 1 are left as they are), gather xyz, sum in ascending row order, divide
+template <int NMAX, bool kVec4>
+__device__ __forceinline__ void prep_short_one(const float* __restrict__ points, int64_t stride, const pcp_grid& g,
+                                               unsigned long long entry, int32_t* __restrict__ sorted_idx,
+                                               float4* __restrict__ mean) {
+  int r, off, n;
+  unpack_entry(entry, r, off, n);
+  int32_t v[NMAX];
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
+  if (NMAX > 2) {
+#pragma unroll
+    for (int i = 1; i < NMAX; ++i)
+#pragma unroll
+      for (int j = i; j > 0; --j) cswap(v[j - 1], v[j]);
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+      if (j < n) sorted_idx[off + j] = v[j];
+  }
+  float x[NMAX], y[NMAX], z[NMAX];
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j)
+    if (j < n) load_xyz<kVec4>(points, stride, v[j], x[j], y[j], z[j]);
+  float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j)
+    if (j < n) { ax = __fadd_rn(ax, x[j]); ay = __fadd_rn(ay, y[j]); az = __fadd_rn(az, z[j]); }
+  const float cnt = (float)n;
+  mean[r] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), pack_cell(x[0], y[0], g));
+}
+
+// W lanes per pillar (two length classes of at most W rows, walked back to back), items [w_begin, w_end) of the
+// concatenated lists: rank by counting against the warp's shared-memory copy, lanes 0, 1, 2 of the group run the
+// sequential sums of x, y, z.  warp_smem: 4 x 32 words of this warp.
+template <int W, bool kVec4>
+__device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64_t stride, const pcp_grid& g,
+                                         const unsigned long long* __restrict__ list_a, int count_a,
+                                         const unsigned long long* __restrict__ list_b, int count_b, int w_begin, int w_end,
+                                         int32_t* __restrict__ sorted_idx, float4* __restrict__ mean, int32_t* warp_smem) {
+  constexpr int kPer = 32 / W;                          // pillars per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / W, ln = lane & (W - 1);
+  const int total = min(count_a + count_b, w_end);
+  int32_t* sv = warp_smem + sub * W;                    // [32] row numbers
+  float* sx = reinterpret_cast<float*>(warp_smem) + 32 + sub * W;   // [3][32] x | y | z in ascending row order
+  for (int w0 = w_begin + warp * kPer; w0 < total; w0 += (blockDim.x >> 5) * kPer) {
+    const int w = w0 + sub;
+    int r = 0, off = 0, n = 0;
+    if (w < total) unpack_entry(__ldg(w < count_a ? list_a + w : list_b + (w - count_a)), r, off, n);
+    const int32_t v = (ln < n) ? sorted_idx[off + ln] : 0x7fffffff;
+    sv[ln] = v;
+    __syncwarp();
+    int rank = 0;
+#pragma unroll
+    for (int i = 0; i < W; i += 4) {
+      const int4 t = *reinterpret_cast<const int4*>(sv + i);       // padding lanes hold INT_MAX: never smaller
+      rank += (t.x < v) + (t.y < v) + (t.z < v) + (t.w < v);
+    }
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (ln < n) {
+      sorted_idx[off + rank] = v;
+      load_xyz<kVec4>(points, stride, v, x, y, z);
+      sx[rank] = x; sx[32 + rank] = y; sx[64 + rank] = z;
+    }
+    __syncwarp();
+    float acc = 0.f;
+    if (ln < 3) {
+      const float* src = sx + 32 * ln;
+      for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, src[i]);
+      acc = __fdiv_rn(acc, (float)max(n, 1));
+    }
+    const float my = __shfl_sync(0xffffffffu, acc, 1, W), mz = __shfl_sync(0xffffffffu, acc, 2, W);
+    if (ln == 0 && w < total) mean[r] = make_float4(acc, my, mz, pack_cell(sx[0], sx[32], g));
+    __syncwarp();
+  }
+}
+
 constexpr int kPrepThreads = 256;
 constexpr int kPrepWarps = kPrepThreads / 32;
 
@@ -305,15 +481,23 @@ struct PrepSmem {
 };
 
 template <bool kVec4>
-__global__ void __launch_bounds__(kPrepThreads, 5)
-pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32_t* __restrict__ hdr,
+__global__ void __launch_bounds__(kPrepThreads, 4)
+pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __restrict__ hdr,
                    unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
                    const int32_t* __restrict__ big_list, int32_t* __restrict__ sorted_idx, float4* __restrict__ mean,
                    float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, const pcp_grid g, int phase_mask) {
   __shared__ __align__(16) PrepSmem sm;
   __shared__ float s_red[3][8];
+  __shared__ int s_chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nlong = hdr[kHdrLongCount];
+  // Work is handed out in CTA-sized chunks through tickets: CTAs that spent time on a big pillar take fewer chunks.
+  auto grab = [&](int which, int chunk) {
+    __syncthreads();
+    if (tid == 0) s_chunk = atomicAdd(&hdr[kHdrPrepTicket + which], chunk);
+    __syncthreads();
+    return s_chunk;
+  };
 
   // ---------------- long pillars, CTA path (> kWarpLongMax rows) ----------------
   const int nbig = (phase_mask & 1) ? hdr[kHdrBigCount] : 0;
@@ -426,7 +610,9 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
   }
 
   // ---------------- long pillars, warp path (33 .. kWarpLongMax rows): one warp per pillar ----------------
-  for (int li = blockIdx.x * kPrepWarps + warp; (phase_mask & 2) && li < nlong; li += gridDim.x * kPrepWarps) {
+  for (int l0 = (phase_mask & 2) ? grab(0, kPrepWarps) : nlong; l0 < nlong; l0 = grab(0, kPrepWarps)) {
+    const int li = l0 + warp;
+    if (li >= nlong) continue;
     const int4 e = long_table[li];
     const int32_t r = e.x, off = e.y, n = e.z, sb = e.w;
     if (n > kWarpLongMax) continue;
@@ -494,78 +680,43 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const int32
   }
 
 
-  // ---------------- mid pillars: classes 6..9 (9..32 rows), one warp per pillar ----------------
-  {
-    int pre[5];
-    pre[0] = 0;
-#pragma unroll
-    for (int k = 6; k <= 9; ++k) pre[k - 5] = pre[k - 6] + hdr[kHdrListCount + k];
-    constexpr int wpb = kPrepWarps;
-    for (int w = blockIdx.x * wpb + warp; (phase_mask & 4) && w < pre[4]; w += gridDim.x * wpb) {
-      int q = 0;
-#pragma unroll
-      for (int t = 1; t < 4; ++t) q += (w >= pre[t]) ? 1 : 0;
-      int r, off, n;
-      unpack_entry(__ldg(lists + lo.off[6 + q] + (w - pre[q])), r, off, n);
-      const int32_t v = (lane < n) ? sorted_idx[off + lane] : 0x7fffffff;
-      int rank = 0;
-      for (int i = 0; i < n; ++i) rank += (__shfl_sync(0xffffffffu, v, i) < v) ? 1 : 0;
-      int32_t* sw = sm.warp_words[warp][0];
-      if (lane < n) { sorted_idx[off + rank] = v; sw[rank] = v; }
-      __syncwarp();
-      float x = 0.f, y = 0.f, z = 0.f;
-      if (lane < n) load_xyz<kVec4>(points, stride, sw[lane], x, y, z);
-      // lanes 0, 1, 2 run the sequential sums of x, y, z
-      float mine = 0.f;
-      for (int i = 0; i < n; ++i) {
-        const float vx = __shfl_sync(0xffffffffu, x, i), vy = __shfl_sync(0xffffffffu, y, i), vz = __shfl_sync(0xffffffffu, z, i);
-        mine = __fadd_rn(mine, lane == 0 ? vx : (lane == 1 ? vy : vz));
-      }
-      mine = __fdiv_rn(mine, (float)n);
-      const float my = __shfl_sync(0xffffffffu, mine, 1), mz = __shfl_sync(0xffffffffu, mine, 2);
-      if (lane == 0) mean[r] = make_float4(mine, my, mz, pack_cell(x, y, g));
-      __syncwarp();
+  // ---------------- mid pillars: classes 6, 7 (9..16 rows): half a warp per pillar; 8, 9 (17..32 rows): a warp ----------------
+  if (phase_mask & 4) {
+    {
+      const int ca = hdr[kHdrListCount + 6], cb = hdr[kHdrListCount + 7];
+      constexpr int kChunk = kPrepWarps * 2 * 4;          // 4 rounds of the CTA
+      for (int w0 = grab(1, kChunk); w0 < ca + cb; w0 = grab(1, kChunk))
+        prep_mid<16, kVec4>(points, stride, g, lists + lo.off[6], ca, lists + lo.off[7], cb, w0, w0 + kChunk, sorted_idx, mean,
+                            &sm.warp_words[warp][0][0]);
+    }
+    {
+      const int ca = hdr[kHdrListCount + 8], cb = hdr[kHdrListCount + 9];
+      constexpr int kChunk = kPrepWarps * 4;
+      for (int w0 = grab(2, kChunk); w0 < ca + cb; w0 = grab(2, kChunk))
+        prep_mid<32, kVec4>(points, stride, g, lists + lo.off[8], ca, lists + lo.off[9], cb, w0, w0 + kChunk, sorted_idx, mean,
+                            &sm.warp_words[warp][0][0]);
     }
   }
 
-  // ---------------- short pillars: classes 0..5 (1..8 rows), one thread per pillar ----------------
-  {
+  // ---------------- short pillars: classes 0..5 (1..8 rows), one thread per pillar, all classes in one index space ----------------
+  if (phase_mask & 8) {
     int pre[7];
     pre[0] = 0;
 #pragma unroll
     for (int k = 0; k <= 5; ++k) pre[k + 1] = pre[k] + hdr[kHdrListCount + k];
-    for (int w = blockIdx.x * kPrepThreads + tid; (phase_mask & 8) && w < pre[6]; w += gridDim.x * kPrepThreads) {
-      int k = 0;
-#pragma unroll
-      for (int q = 1; q <= 5; ++q) k += (w >= pre[q]) ? 1 : 0;
-      int r, off, n;
-      unpack_entry(__ldg(lists + lo.off[k] + (w - pre[k])), r, off, n);
-      int32_t v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
-      if (n > 1) {
-        // optimal 8-input sorting network (19 compare-exchanges)
-        cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
-        cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
-        cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
-        cswap(v[1], v[5]); cswap(v[2], v[6]);
-        cswap(v[1], v[4]); cswap(v[3], v[6]);
-        cswap(v[2], v[4]); cswap(v[3], v[5]);
-        cswap(v[3], v[4]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < n) sorted_idx[off + j] = v[j];
+    constexpr int kChunk = kPrepThreads * 2;
+    for (int w0 = grab(3, kChunk); w0 < pre[6]; w0 = grab(3, kChunk)) {
+#pragma unroll 1
+      for (int u = 0; u < 2; ++u) {
+        const int w = w0 + u * kPrepThreads + tid;
+        if (w >= pre[6]) continue;
+        if (w < pre[1]) prep_short_one<1, kVec4>(points, stride, g, __ldg(lists + lo.off[0] + w), sorted_idx, mean);
+        else if (w < pre[2]) prep_short_one<2, kVec4>(points, stride, g, __ldg(lists + lo.off[1] + (w - pre[1])), sorted_idx, mean);
+        else if (w < pre[3]) prep_short_one<3, kVec4>(points, stride, g, __ldg(lists + lo.off[2] + (w - pre[2])), sorted_idx, mean);
+        else if (w < pre[4]) prep_short_one<4, kVec4>(points, stride, g, __ldg(lists + lo.off[3] + (w - pre[3])), sorted_idx, mean);
+        else if (w < pre[5]) prep_short_one<6, kVec4>(points, stride, g, __ldg(lists + lo.off[4] + (w - pre[4])), sorted_idx, mean);
+        else prep_short_one<8, kVec4>(points, stride, g, __ldg(lists + lo.off[5] + (w - pre[5])), sorted_idx, mean);
       }
-      float x[8], y[8], z[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < n) load_xyz<kVec4>(points, stride, v[j], x[j], y[j], z[j]);
-      float ax = 0.f, ay = 0.f, az = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < n) { ax = __fadd_rn(ax, x[j]); ay = __fadd_rn(ay, y[j]); az = __fadd_rn(az, z[j]); }
-      const float cnt = (float)n;
-      mean[r] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), pack_cell(x[0], y[0], g));
     }
   }
 }
@@ -604,7 +755,7 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   PCP_CUDA(cudaMemsetAsync(workspace, 0, L.clear_bytes, stream));
   if (n_points > 0) {
     const bool vec4 = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
-    const unsigned blocks = (unsigned)((n_points + 255) / 256);
+    const unsigned blocks = (unsigned)((n_points + 256 * kPtsPerThread - 1) / (256 * kPtsPerThread));
     if (vec4)
       quantise_count_kernel<true><<<blocks, 256, 0, stream>>>(points, row_stride, n_points, max_frames, *grid,
                                                               W.cell, W.key, W.within, W.hdr);
@@ -613,19 +764,22 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
                                                                W.cell, W.key, W.within, W.hdr);
     PCP_LAUNCH_CHECK("quantise_count_kernel");
   }
+  tile_sums_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(W.cell, L.cells, grid->nx, grid->ny, W.tile_info,
+                                                                      W.tile_info + 16 * (L.scan_tiles + 1));
+  PCP_LAUNCH_CHECK("tile_sums_kernel");
   scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
-      W.cell, L.cells, grid->nx, grid->ny, W.scan_state, W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
+      W.cell, W.cell_rank, L.cells, grid->nx, grid->ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
       W.lists, L.lo, W.long_table, W.big_list, L.scan_tiles);
   PCP_LAUNCH_CHECK("scan_cells_kernel");
   {
-    const unsigned blocks = (unsigned)((n_points + 255) / 256);
-    place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.seg_off, n_points, W.sorted_idx,
+    const unsigned blocks = (unsigned)((n_points + 256 * kPtsPerThread - 1) / (256 * kPtsPerThread));
+    place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.cell_rank, n_points, W.sorted_idx,
                                                           point_pillar_out, W.hdr, counts_out);
     PCP_LAUNCH_CHECK("place_kernel");
   }
   if (n_points > 0) {
     const int64_t want = (n_points + kPrepThreads - 1) / kPrepThreads;
-    const unsigned blocks = (unsigned)(want < 148 * 5 ? want : 148 * 5);
+    const unsigned blocks = (unsigned)(want < 148 * 4 ? want : 148 * 4);
     const bool vec4 = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
     // PCP_PREP_SPLIT=1 (diagnostic): one launch per phase so that a launch list shows each phase's time
     static const bool split = getenv("PCP_PREP_SPLIT") != nullptr;
