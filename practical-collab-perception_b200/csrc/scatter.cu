@@ -6,6 +6,8 @@
 // a CTA owns a (8 rows x 128 columns) patch of one frame, looks the pillar rank of its 1024 cells up
 // once, and for every group of 4 channels gathers 16-byte pieces of the pillar rows, transposes them in
 // registers and issues 128-bit streaming stores, 512 contiguous bytes per warp per (channel, row).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pcp {
@@ -21,8 +23,8 @@ __device__ __forceinline__ void st_stream_f4(float* p, float a, float b, float c
 // kXMajor = true : rank map is the voxelize workspace, laid out like the reference's linear key
 //                  (frame, cx, cy) -> b*nx*ny + cx*ny + cy
 // kXMajor = false: rank map is canvas-ordered (frame, y, x) (generic path)
-template <bool kXMajor>
-__global__ void __launch_bounds__(kTileY * 32)
+template <bool kXMajor, int kUnroll, int kMinBlocks>
+__global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
 canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
               float* __restrict__ canvas) {
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
@@ -55,17 +57,25 @@ canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map
       for (int c = 0; c < channels; ++c) st_stream_f4(dst + (int64_t)c * nxy, 0.f, 0.f, 0.f, 0.f);
       return;
     }
-#pragma unroll 2
-    for (int c = 0; c < channels; c += 4) {
-      float4 v[4];
+    for (int c0 = 0; c0 < channels; c0 += 4 * kUnroll) {
+      float4 v[kUnroll][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        v[i] = (r[i] >= 0) ? __ldg(reinterpret_cast<const float4*>(pf + (int64_t)r[i] * channels + c))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      st_stream_f4(dst + (int64_t)(c + 0) * nxy, v[0].x, v[1].x, v[2].x, v[3].x);
-      st_stream_f4(dst + (int64_t)(c + 1) * nxy, v[0].y, v[1].y, v[2].y, v[3].y);
-      st_stream_f4(dst + (int64_t)(c + 2) * nxy, v[0].z, v[1].z, v[2].z, v[3].z);
-      st_stream_f4(dst + (int64_t)(c + 3) * nxy, v[0].w, v[1].w, v[2].w, v[3].w);
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          v[u][i] = (r[i] >= 0 && c0 + 4 * u < channels)
+                        ? __ldg(reinterpret_cast<const float4*>(pf + (int64_t)r[i] * channels + c0 + 4 * u))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int c = c0 + 4 * u;
+        if (c < channels) {
+          st_stream_f4(dst + (int64_t)(c + 0) * nxy, v[u][0].x, v[u][1].x, v[u][2].x, v[u][3].x);
+          st_stream_f4(dst + (int64_t)(c + 1) * nxy, v[u][0].y, v[u][1].y, v[u][2].y, v[u][3].y);
+          st_stream_f4(dst + (int64_t)(c + 2) * nxy, v[u][0].z, v[u][1].z, v[u][2].z, v[u][3].z);
+          st_stream_f4(dst + (int64_t)(c + 3) * nxy, v[u][0].w, v[u][1].w, v[u][2].w, v[u][3].w);
+        }
+      }
     }
   } else {
     for (int c = 0; c < channels; ++c)
@@ -119,8 +129,23 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
   if (num_frames == 0) return 0;
   PCP_REQUIRE(pillar_features, PCP_E_INVALID, "pcp_bev_scatter_ws: null pillar_features");
   const WsView W = ws_view(const_cast<void*>(workspace), L);
-  canvas_kernel<true><<<canvas_grid(grid->nx, grid->ny, num_frames), kTileY * 32, 0, stream>>>(
-      pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+  {
+    static const int variant = getenv("PCP_CANVAS_VARIANT") ? atoi(getenv("PCP_CANVAS_VARIANT")) : 0;   // tuning aid
+    const dim3 cg = canvas_grid(grid->nx, grid->ny, num_frames);
+    const int th = kTileY * 32;
+    if (variant == 5) {      // diagnostic: pure write stream (every cell treated as empty)
+      PCP_CUDA(cudaMemsetAsync(canvas_out, 0, sizeof(float) * (size_t)num_frames * channels * grid->nx * grid->ny, stream));
+    } else if (variant == 1)
+      canvas_kernel<true, 2, 4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+    else if (variant == 2)
+      canvas_kernel<true, 4, 2><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+    else if (variant == 3)
+      canvas_kernel<true, 4, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+    else if (variant == 4)
+      canvas_kernel<true, 1, 6><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+    else
+      canvas_kernel<true, 2, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+  }
   PCP_LAUNCH_CHECK("canvas_kernel<ws>");
   return 0;
 }
@@ -141,7 +166,7 @@ extern "C" int pcp_bev_scatter(const float* pillar_features, const int32_t* voxe
                                                                                   nx, ny, cell_map_scratch);
     PCP_LAUNCH_CHECK("coords_to_map_kernel");
   }
-  canvas_kernel<false><<<canvas_grid(nx, ny, num_frames), kTileY * 32, 0, stream>>>(pillar_features, cell_map_scratch,
+  canvas_kernel<false, 2, 3><<<canvas_grid(nx, ny, num_frames), kTileY * 32, 0, stream>>>(pillar_features, cell_map_scratch,
                                                                                      channels, nx, ny, canvas_out);
   PCP_LAUNCH_CHECK("canvas_kernel<map>");
   return 0;
