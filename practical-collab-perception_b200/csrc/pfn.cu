@@ -65,6 +65,8 @@ __global__ void pack_params_kernel(int c_in, int num_layers, const float* w0, co
       out[P.w1ah + i] = h; out[P.w1al + i] = l;
       umma::split_tf32_rn(sgn * w1[n * (2 * kHidden) + kHidden + k], h, l);
       out[P.w1bh + i] = h; out[P.w1bl + i] = l;
+      umma::split_tf32_rn(sgn * __fadd_rn(w1[n * (2 * kHidden) + k], w1[n * (2 * kHidden) + kHidden + k]), h, l);
+      out[P.w1sh + i] = h; out[P.w1sl + i] = l;
     }
     for (int i = tid; i < kCout * kHidden; i += nth) {
       const int n = i / kHidden, k = i % kHidden;

@@ -95,14 +95,14 @@ __device__ __forceinline__ void st_global_f4(float* p, float a, float b, float c
 //       1 = car / early-fusion rows: c_raw 5, absolute xyz, no distance, row stride % 4 == 0, 16-byte aligned
 //       2 = ego (lately fusion) rows: c_raw 11, absolute xyz, no distance, even row stride, 8-byte aligned
 //   nreg  = floats of a row staged per slot, depth = rows in flight per producer thread (cp.async ring of depth + 1 stages)
-template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 24, depth = 2; };
-template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8, depth = 4; };
-template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12, depth = 3; };
+template <int kCfg> struct RowCfg { static constexpr int n_raw = 0, k0 = 0, nreg = 24, depth = 1; };
+template <> struct RowCfg<1> { static constexpr int n_raw = 5, k0 = 16, nreg = 8, depth = 3; };
+template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 12, depth = 2; };
 // per producer set: ring of per-group work-list entries (cursor A runs up to 6 * depth + 4 groups ahead of cursor D)
 __host__ __device__ constexpr int ent_ring(int depth) { return 6 * depth + 4 <= 16 ? 16 : 32; }
 
 struct SmemPlan {   // float offsets into dynamic shared memory
-  int w0h, w0l, w1ah, w1al, w1bh, w1bl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, mean, row, rows, ostage, gtab, ints, total_bytes;
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, w1sh, w1sl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, mean, row, rows, ostage, gtab, ints, total_bytes;
   int ent_set, idx_set, mean_set, row_set;   // floats per producer set
 };
 __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int depth) {
@@ -116,6 +116,8 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int 
     S.w1al = o; o += kHidden * kCout;
     S.w1bh = o; o += kHidden * kCout;
     S.w1bl = o; o += kHidden * kCout;
+    S.w1sh = o; o += kHidden * kCout;
+    S.w1sl = o; o += kHidden * kCout;
   }
   S.panels_end = o;
   S.prm_a0 = o; o += n0;
@@ -250,6 +252,7 @@ pfn_slot_kernel(const TcArgs A) {
     const uint32_t sw0h = smem_u32(smem + SP.w0h), sw0l = smem_u32(smem + SP.w0l);
     const uint32_t sw1ah = smem_u32(smem + SP.w1ah), sw1al = smem_u32(smem + SP.w1al);
     const uint32_t sw1bh = smem_u32(smem + SP.w1bh), sw1bl = smem_u32(smem + SP.w1bl);
+    const uint32_t sw1sh = smem_u32(smem + SP.w1sh), sw1sl = smem_u32(smem + SP.w1sl);
     const uint32_t idesc0 = idesc_tf32_m128(N0), idesc1 = idesc_tf32_m128(kCout);
     uint32_t c0 = 0, c1 = 0;      // layer-0 ops / layer-1-type ops issued so far
     TRACE_DECL((tid & 31) == 0)
@@ -295,11 +298,13 @@ pfn_slot_kernel(const TcArgs A) {
     for (int w = blockIdx.x; w < total; w += G, ++gi) {
       bool is_seg;
       const int slots = slots_of(w, gi, is_seg);
+      // one-point pillars: x_max == x, so x . (W1[:, :32] + W1[:, 32:])^T is the whole last layer - no hoist
+      const bool single = (slots == 1) && !is_seg;
       for (int j = 0; j < slots; ++j) {
         if (c0 < nslots) issue_m0();                           // layer 0 of a LATER slot goes in front of this slot's layer 1
-        if (kLayers == 2) issue_m1(sw1ah, sw1al);
+        if (kLayers == 2) { if (single) issue_m1(sw1sh, sw1sl); else issue_m1(sw1ah, sw1al); }
       }
-      if (kLayers == 2 && !is_seg) issue_m1(sw1bh, sw1bl);     // hoist: max0 . W1[:, 32:]^T once per pillar
+      if (kLayers == 2 && !is_seg && !single) issue_m1(sw1bh, sw1bl);     // hoist: max0 . W1[:, 32:]^T once per pillar
       TRACE(0, 24);
     }
     TRACE_END(0);
@@ -579,7 +584,9 @@ pfn_slot_kernel(const TcArgs A) {
           TRACE(2, 32);
           ++c0; ++c1;
         }
-        if (!is_seg) {
+        if (slots == 1 && !is_seg) {
+          // one-point pillars: no hoist (the MMA warp used the summed weights)
+        } else if (!is_seg) {
           // hoist: max0 -> A1; the MMA warp multiplies by W1[:, 32:]^T
           const uint32_t b1 = c1 & 1;
           if (c1 >= 2) { mbar_wait(&bars[kBarD1 + b1], ((c1 - 2) >> 1) & 1); tc_fence_after_sync(); }
@@ -666,9 +673,11 @@ pfn_slot_kernel(const TcArgs A) {
     for (int w = blockIdx.x; w < total; w += G, ++gi) {
       bool is_seg;
       const int slots = slots_of(w, gi, is_seg);
+      // one-point pillars: the single accumulator (summed weights) is already max + hoist; it goes through the output path
+      const bool single = (slots == 1) && !is_seg;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) m1[i] = -INFINITY;
-      for (int j = 0; j < slots; ++j) {
+      for (int i = 0; i < 32; ++i) m1[i] = single ? 0.f : -INFINITY;
+      for (int j = 0; j < (single ? 0 : slots); ++j) {
         const uint32_t b = k & 1;
         TRACE(3, 33);
         mbar_wait(&bars[kBarD1 + b], (k >> 1) & 1);

@@ -16,12 +16,13 @@ __host__ __device__ inline int pfn_k0(int c_in) { return (c_in + 7) / 8 * 8; }
 //   two layers: w0h | w0l  [k0/4][32][4]      layer 0: Linear(c_in -> 32)
 //               w1ah | w1al [8][64][4]        layer 1, columns 0..31  (the per-point half:  x . W1[:, :32]^T)
 //               w1bh | w1bl [8][64][4]        layer 1, columns 32..63 (the per-pillar half: x_max . W1[:, 32:]^T)
+//               w1sh | w1sl [8][64][4]        W1[:, :32] + W1[:, 32:]: one-point pillars (x_max == x) need a single product
 //               a0[32] b0[32]                 folded BN of layer 0 (signed scale, shift)
 //               a1[64] b1[64]                 |scale|, shift of layer 1
 //               w1b_f32 [64][32]              sign-folded fp32 copy of W1[:, 32:] for the long-pillar finishing kernel
 //   one layer:  w0h | w0l  [k0/4][64][4] (sign-folded) | a0[64] (|scale|) b0[64]
 struct ParamLayout {
-  int w0h, w0l, w1ah, w1al, w1bh, w1bl, a0, b0, a1, b1, w1b_f32, total;
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, w1sh, w1sl, a0, b0, a1, b1, w1b_f32, total;
 };
 __host__ __device__ inline ParamLayout param_layout(int c_in, int num_layers) {
   ParamLayout P{};
@@ -35,6 +36,8 @@ __host__ __device__ inline ParamLayout param_layout(int c_in, int num_layers) {
     P.w1al = o; o += kHidden * kCout;
     P.w1bh = o; o += kHidden * kCout;
     P.w1bl = o; o += kHidden * kCout;
+    P.w1sh = o; o += kHidden * kCout;
+    P.w1sl = o; o += kHidden * kCout;
   }
   P.a0 = o; o += n0;
   P.b0 = o; o += n0;

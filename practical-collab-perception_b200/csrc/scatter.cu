@@ -26,7 +26,7 @@ __device__ __forceinline__ void st_stream_f4(float* p, float a, float b, float c
 template <bool kXMajor, int kUnroll, int kMinBlocks>
 __global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
 canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
-              float* __restrict__ canvas) {
+              float* __restrict__ canvas, int force_empty) {
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int y = blockIdx.y * kTileY + wy;
@@ -47,6 +47,7 @@ canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map
       for (int i = 0; i < 4; ++i) r[i] = (x0 + i < nx) ? __ldg(m + i) : -1;
     }
   }
+  if (force_empty) { r[0] = r[1] = r[2] = r[3] = -1; }
   float* dst = canvas + ((int64_t)b * channels) * nxy + (int64_t)y * nx + x0;
   const bool vec = (x0 + 3 < nx) && ((nx & 3) == 0) && ((reinterpret_cast<uintptr_t>(canvas) & 15) == 0);
   const bool any = (r[0] >= 0) | (r[1] >= 0) | (r[2] >= 0) | (r[3] >= 0);
@@ -136,15 +137,15 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
     if (variant == 5) {      // diagnostic: pure write stream (every cell treated as empty)
       PCP_CUDA(cudaMemsetAsync(canvas_out, 0, sizeof(float) * (size_t)num_frames * channels * grid->nx * grid->ny, stream));
     } else if (variant == 1)
-      canvas_kernel<true, 2, 4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+      canvas_kernel<true, 2, 4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
     else if (variant == 2)
-      canvas_kernel<true, 4, 2><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+      canvas_kernel<true, 4, 2><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
     else if (variant == 3)
-      canvas_kernel<true, 4, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+      canvas_kernel<true, 4, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
     else if (variant == 4)
-      canvas_kernel<true, 1, 6><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+      canvas_kernel<true, 1, 6><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
     else
-      canvas_kernel<true, 2, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+      canvas_kernel<true, 2, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
   }
   PCP_LAUNCH_CHECK("canvas_kernel<ws>");
   return 0;
@@ -167,7 +168,7 @@ extern "C" int pcp_bev_scatter(const float* pillar_features, const int32_t* voxe
     PCP_LAUNCH_CHECK("coords_to_map_kernel");
   }
   canvas_kernel<false, 2, 3><<<canvas_grid(nx, ny, num_frames), kTileY * 32, 0, stream>>>(pillar_features, cell_map_scratch,
-                                                                                     channels, nx, ny, canvas_out);
+                                                                                     channels, nx, ny, canvas_out, 0);
   PCP_LAUNCH_CHECK("canvas_kernel<map>");
   return 0;
 }
