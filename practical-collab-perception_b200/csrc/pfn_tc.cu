@@ -102,7 +102,7 @@ template <> struct RowCfg<2> { static constexpr int n_raw = 11, k0 = 24, nreg = 
 __host__ __device__ constexpr int ent_ring(int depth) { return 6 * depth + 4 <= 16 ? 16 : 32; }
 
 struct SmemPlan {   // float offsets into dynamic shared memory
-  int w0h, w0l, w1ah, w1al, w1bh, w1bl, w1sh, w1sl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, mean, row, rows, ostage, gtab, ints, total_bytes;
+  int w0h, w0l, w1ah, w1al, w1bh, w1bl, w1sh, w1sl, panels_end, prm_a0, prm_b0, prm_a1, prm_b1, ent, idx, mean, row, rows, ostage, gtab, curs, ints, total_bytes;
   int ent_set, idx_set, mean_set, row_set;   // floats per producer set
 };
 __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int depth) {
@@ -137,6 +137,7 @@ __host__ __device__ inline SmemPlan smem_plan(int k0, int layers, int nreg, int 
   S.rows = o; o += kRowRing * kGroup;             // output row (pillar rank) / long-pillar index of each lane
   S.ostage = o; o += (kE1Threads * kOutRowBytes) / 4;   // E1 output staging: one padded 128-byte row per thread
   S.gtab = o; o += kGTab;                         // (slots | is_seg << 8) of this CTA's first kGTab groups
+  S.curs = o; o += (kProdThreads / 32) * 8;       // per producer warp: ring of packed cursor states (group, slot, is-segment)
   S.ints = o; o += 96;                            // 14 mbarriers | tmem base | group prefix | list counts | list offsets
   S.total_bytes = o * 4;
   return S;
@@ -373,15 +374,20 @@ pfn_slot_kernel(const TcArgs A) {
     auto entry_of = [&](int gi) { return s_ent[(gi & (kEntRing - 1)) * kGroup + p]; };
 
     int ga_w = blockIdx.x, ga_gi = 0;                      // cursor A
-    Cursor cb, cc, cd;
-    cur_init(cb); cur_init(cc); cur_init(cd);
-    unsigned long long eb = kNoEntry, ec = kNoEntry, ed = kNoEntry;   // cached entries of the cursors' groups
+    Cursor cb;
+    cur_init(cb);
+    unsigned long long eb = kNoEntry;                       // cached entry of cursor B's group
     // An entry requested in the iteration after cursor B entered group Y - LEAD (or Y - LEAD + 1) is committed at
     // least DEPTH iterations before B can enter group Y: B advances at most two groups per iteration.
     auto step_a = [&](int b_gi) {
       while (ga_gi <= b_gi + LEAD) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
     };
+    // Cursor B is the only one that walks the slot sequence; it leaves its state (group, slot, is-segment) in a small
+    // per-warp ring that cursors C and D read DEPTH and 2 * DEPTH iterations later (every lane writes the same word).
+    static_assert(2 * DEPTH + 1 <= 8, "cursor ring too small");
+    uint32_t* const s_curs = reinterpret_cast<uint32_t*>(smem + SP.curs) + (warp - kProdWarp0) * 8;
     auto step_b = [&](int it) {                            // row number of cursor B's slot -> s_idx[ring]
+      s_curs[it & 7] = ((uint32_t)cb.gi << 6) | ((uint32_t)cb.j << 1) | (cb.seg ? 1u : 0u);
       if (eb != kNoEntry) {
         int r, off, len;
         unpack_entry(eb, r, off, len);
@@ -390,6 +396,8 @@ pfn_slot_kernel(const TcArgs A) {
       if (cur_next2(cb)) eb = entry_of(cb.gi);
     };
     auto step_c = [&](int it) {                            // row and pillar mean of cursor C's slot -> s_row / s_mean[ring]
+      const uint32_t u = s_curs[it & 7];
+      const unsigned long long ec = entry_of((int)(u >> 6));
       if (ec != kNoEntry) {
         const int st = it % STAGES;
         const int idx = s_idx[st * kGroup + p];
@@ -405,16 +413,15 @@ pfn_slot_kernel(const TcArgs A) {
           for (int c = 0; c < n_cols; ++c) cp_async4(dst + c * kGroup + p, row + 1 + c);
         }
         const int r = (int)(ec & 0x1fffffffull);
-        cp_async16(s_mean + st * kGroup + p, (cc.seg ? A.long_mean : A.mean) + r);
+        cp_async16(s_mean + st * kGroup + p, ((u & 1u) ? A.long_mean : A.mean) + r);
       }
-      if (cur_next2(cc)) ec = entry_of(cc.gi);
     };
     int ib = 0, ic = 0;                                    // iteration numbers of cursors B and C
     // entries of the first 4 * DEPTH + LEAD + 2 groups (everything cursor B can reach during the prologue plus its lead)
     while (ga_gi < 4 * DEPTH + LEAD + 2) { issue_entry(ga_w, ga_gi); ga_w += G; ++ga_gi; }
     cp_async_commit();
     cp_async_wait<0>();
-    eb = entry_of(cb.gi); ec = eb; ed = eb;
+    eb = entry_of(cb.gi);
     for (int t = 0; t < DEPTH; ++t) step_b(ib++);          // row numbers of its slots 0 .. DEPTH - 1 - one round trip
     cp_async_commit();
     cp_async_wait<0>();
@@ -426,7 +433,11 @@ pfn_slot_kernel(const TcArgs A) {
     int id = 0;                                            // iteration number of cursor D
     const int n_feat = n_raw + (with_dist ? 7 : 6);
     TRACE_DECL(p == 0)
-    while (cd.w < total) {
+    while (true) {
+      const uint32_t ud = s_curs[id & 7];                  // written by cursor B 2 * DEPTH iterations (or the prologue) ago
+      const int d_gi = (int)(ud >> 6), d_j = (int)((ud >> 1) & 31u);
+      const bool d_seg = (ud & 1u) != 0;
+      if ((long long)blockIdx.x + (long long)d_gi * G >= total) break;
       // ---- pipeline upkeep: entries / one row number / one row request per iteration ----
       TRACE(set ? 4 : 1, 10);
       cp_async_wait<DEPTH - 1>();                          // everything issued DEPTH or more iterations ago has landed
@@ -435,13 +446,14 @@ pfn_slot_kernel(const TcArgs A) {
       step_c(ic++);
       cp_async_commit();
       TRACE(set ? 4 : 1, 14);
+      const unsigned long long ed = entry_of(d_gi);
       const bool valid = ed != kNoEntry;
       const float4 m = s_mean[(id % STAGES) * kGroup + p];
-      if (cd.j == 0) {
+      if (d_j == 0) {
         // first slot of a group (built by exactly one of the two sets): publish the group's output rows
         const int r = valid ? (int)(ed & 0x1fffffffull) : -1;
-        s_rows[(cd.gi % kRowRing) * kGroup + p] = r;      // pillar rank, or long-pillar index of a segment
-        if (A.mean_out && valid && !cd.seg) {
+        s_rows[(d_gi % kRowRing) * kGroup + p] = r;      // pillar rank, or long-pillar index of a segment
+        if (A.mean_out && valid && !d_seg) {
           float* mo = A.mean_out + (int64_t)r * 3;
           mo[0] = m.x; mo[1] = m.y; mo[2] = m.z;
         }
@@ -511,7 +523,6 @@ pfn_slot_kernel(const TcArgs A) {
       tc_fence_before_sync();
       mbar_arrive(&bars[kBarA0 + b]);
       ++c0; ++id;
-      if (cur_next2(cd)) ed = entry_of(cd.gi);
     }
     cp_async_wait<0>();
     TRACE_END(set ? 4 : 1);
@@ -554,6 +565,7 @@ pfn_slot_kernel(const TcArgs A) {
           const bool more = (c0 + 1) < nslots;
           TRACE(2, 30);
           tmem_ld_wait();                                                       // rr = accumulators of slot c0
+          TRACE(2, 301);
           if (c1 >= 2) mbar_wait(&bars[kBarD1 + b1], ((c1 - 2) >> 1) & 1);     // A1[b1] read by the MMA two ops ago
           if (more) mbar_wait(&bars[kBarD0 + (c0 + 1) % NF], ((c0 + 1) / NF) & 1);
           TRACE(2, 31);
@@ -577,8 +589,10 @@ pfn_slot_kernel(const TcArgs A) {
               if (half == 0) tmem_ld8_nowait(d0_addr(c0 + 1), rr[0], rr[1], rr[2], rr[3], rr[4], rr[5], rr[6], rr[7]);
               else tmem_ld8_nowait(d0_addr(c0 + 1) + 8, rr[8], rr[9], rr[10], rr[11], rr[12], rr[13], rr[14], rr[15]);
             }
+            TRACE(2, 302 + half);
           }
           tmem_st_wait();
+          TRACE(2, 304);
           tc_fence_before_sync();
           mbar_arrive(&bars[kBarA1 + b1]);
           TRACE(2, 32);
