@@ -155,7 +155,7 @@ def test_pillar_mean_and_segment_reductions_bit_exact():
     assert torch.equal(got_mean, po.scatter_mean(vals[kept], want["unq_inv"], P)), "segment mean is not bit exact"
 
 
-@pytest.mark.parametrize("n_in_pillar", [2, 8, 9, 31, 32, 33, 127, 128, 129, 500, 4096, 5000, 20000])
+@pytest.mark.parametrize("n_in_pillar", [2, 8, 9, 12, 13, 16, 17, 24, 25, 31, 32, 33, 127, 128, 129, 500, 1024, 1025, 4096, 5000, 20000])
 def test_long_pillars(n_in_pillar):
     """Pillars longer than a 128-point chunk stream through the multi-chunk path; sorted-segment code
     paths switch at 8 / 32 / 4096 points."""
@@ -173,6 +173,31 @@ def test_long_pillars(n_in_pillar):
     bd = run_modules(vfe, scat, pts, batch_size=1)
     want = oracle_want(pts, cfg, layers_from_state_dict(sd))
     check_against(bd, want, pts.shape[0])
+
+
+@pytest.mark.parametrize("n_in_pillar", [3, 16, 17, 33, 128, 129, 700, 1024, 1025, 4096])
+def test_pillar_means_bit_exact_on_every_ordering_path(n_in_pillar):
+    """The per-pillar mean is a sequential fp32 sum in ascending row order on every path of pillar_prep_kernel
+    (thread / half warp / warp / CTA with counting rank / CTA with bitonic network): bit-equal to index_add_ on the CPU."""
+    from pcp_b200.frontend import FrontEnd, GridSpec
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5, seed=3)
+    g = torch.Generator().manual_seed(100 + n_in_pillar)
+    base = syn.lidar_frame(2000, 91)
+    dense = syn.lidar_frame(n_in_pillar, 92)
+    dense[:, 1] = 30.0 + torch.rand(n_in_pillar, generator=g) * 0.19      # far from the origin: sums are order sensitive
+    dense[:, 2] = -41.0 + torch.rand(n_in_pillar, generator=g) * 0.19
+    pts = torch.cat([base, dense], 0)
+    pts = pts[torch.randperm(pts.shape[0], generator=g)].contiguous()
+    fe = FrontEnd(GridSpec(vox, rng, grid), 5)
+    bn = lambda i: [sd[f"pfn_layers.{i}.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")]
+    fe.pack_params(sd["pfn_layers.0.linear.weight"].to(DEV), bn(0), sd["pfn_layers.1.linear.weight"].to(DEV), bn(1))
+    p_dev = pts.to(DEV)
+    out = fe.voxelize(p_dev, 1, want_point_pillar=True)
+    fe.pfn(p_dev, out, want_mean=True)
+    P = int(fe.read_counts(out)[0])
+    want = po.dynamic_pillar_vfe(pts, cfg, layers_from_state_dict(sd), unique_dim0=False)
+    assert P == want["voxel_coords"].shape[0]
+    assert torch.equal(out["pillar_mean_buf"][:P].cpu(), want["points_mean"]), "pillar mean is not bit exact"
 
 
 def test_all_points_in_one_pillar_and_all_culled_frame():
