@@ -167,7 +167,7 @@ tile_sums_kernel(const int32_t* __restrict__ cell, int64_t cells, int32_t nx, in
 // Second launch: every tile sums the records of the tiles before it (its exclusive prefix of every counter), scans its own
 // cells and writes, for every non-empty cell, the pillar rank, the first sorted position, voxel_coords and the pillar's
 // work-list entry.  No global atomics: list positions, long-pillar indices and segment ranges come from the prefixes.
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, int64_t cells, int32_t nx, int32_t ny,
                   const int32_t* __restrict__ tile_info, const int32_t* __restrict__ tile_frames, int32_t* __restrict__ hdr,
                   int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
@@ -179,6 +179,10 @@ scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, i
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ long long s_lo[kNumClasses];
   __shared__ int s_frames[kScanThreads / 32];
+  // the tile's non-empty cells, compacted in rank order (phase A fills, phase B walks them with all threads busy)
+  __shared__ int32_t s_pcnt[kScanTileCells];     // rows of the pillar
+  __shared__ int32_t s_poff[kScanTileCells];     // its first sorted position
+  __shared__ uint16_t s_pidx[kScanTileCells];    // its cell inside the tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < kTiInts) s_cls[tid] = 0;
   if (tid < kNumClasses) s_lo[tid] = lo.off[tid];
@@ -245,19 +249,13 @@ scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, i
     tile_total += s_warp[w];
   }
   __syncthreads();
-  const unsigned long long before = ((unsigned long long)(uint32_t)s_before[kTiPoints] << 32) | (uint32_t)s_before[kTiPillars];
-  // cells < 2^31 (checked by the host): 32-bit coordinates of this thread's first cell, updated incrementally below
-  const uint32_t nxy = (uint32_t)nx * (uint32_t)ny;
-  const uint32_t base32 = (uint32_t)base;
-  const uint32_t b0 = base32 / nxy, rem0 = base32 - b0 * nxy;
-  const uint32_t cx0 = rem0 / (uint32_t)ny, cy0 = rem0 - cx0 * (uint32_t)ny;
+  const int32_t r_tile = s_before[kTiPillars], off_tile = s_before[kTiPoints];     // first rank / sorted position of the tile
   if (tile == scan_tiles - 1) {
     // the last tile knows every total: counts block, list lengths, long-pillar counters
     const int32_t* own = tile_info + tile * kTiInts;
     if (tid == 0) {
-      const unsigned long long tot = before + tile_total;
-      const int32_t P = (int32_t)(tot & 0xffffffffull);
-      const int32_t Nk = (int32_t)((tot >> 32) & 0x3fffffffull);
+      const int32_t P = r_tile + (int32_t)(tile_total & 0xffffffffull);
+      const int32_t Nk = off_tile + (int32_t)((tile_total >> 32) & 0x3fffffffull);
       hdr[PCP_COUNT_PILLARS] = P;
       hdr[PCP_COUNT_KEPT] = Nk;
       hdr[PCP_COUNT_MAX_PER_PILLAR] = max(s_before[kTiMax], own[kTiMax]);
@@ -272,51 +270,59 @@ scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, i
     }
     if (tid < kNumClasses) hdr[kHdrListCount + tid] = s_before[kTiClass + tid] + own[kTiClass + tid];
   }
-  unsigned long long excl = before + warp_excl + (incl - mine);
-  unsigned long long my_ent[kScanItems];          // packed list entry
-  int my_slot[kScanItems];                        // class << 16 | slot inside this tile's class batch
-  int32_t b = (int32_t)b0, cx = (int32_t)cx0, cy = (int32_t)cy0;
+  // ---- phase A: per cell - first sorted position / rank (or -1) as vector stores; non-empty cells -> compact list ----
+  {
+    const unsigned long long excl0 = warp_excl + (incl - mine);          // inside the tile
+    int rl = (int)(excl0 & 0xffffffffull);                               // local rank
+    int ol = (int)((excl0 >> 32) & 0x3fffffffull);                       // local sorted position
+    int32_t vo[kScanItems], vr[kScanItems];
 #pragma unroll
-  for (int j = 0; j < kScanItems; ++j) {
-    const int64_t idx = base + j;
-    my_ent[j] = 0ull; my_slot[j] = -1;
-    if (j > 0) {                                  // next cell of the x-major key order
-      if (++cy == ny) { cy = 0; if (++cx == nx) { cx = 0; ++b; } }
-    }
-    if (idx < cells) {
+    for (int j = 0; j < kScanItems; ++j) {
+      vo[j] = -1; vr[j] = -1;
       if (c[j] > 0) {
-        const int32_t r = (int32_t)(excl & 0xffffffffull);
-        const int32_t off = (int32_t)((excl >> 32) & 0x3fffffffull);
-        seg_off[r] = off;
-        // (frame, z = 0, y, x): dynamic_pillar_vfe.py:138-143 after the [0, 3, 2, 1] reorder
-        *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4(b, 0, cy, cx);
-        if (pillar_count) pillar_count[r] = c[j];
-        cell[idx] = off;
-        cell_rank[idx] = r;
-        if (c[j] <= kSegRows) {
-          const int k = class_of(c[j]);
-          my_ent[j] = pack_entry(r, off, c[j]);
-          my_slot[j] = (k << 16) | atomicAdd(&s_cls[kTiClass + k], 1);
-        } else {
-          // long pillar: its index, its segment range (pillar_prep_kernel writes the segment entries)
-          const int nseg = (c[j] + kSegRows - 1) / kSegRows;
-          const int li = s_before[kTiLong] + atomicAdd(&s_cls[kTiLong], 1);
-          const int sb = s_before[kTiSegs] + atomicAdd(&s_cls[kTiSegs], nseg);
-          long_table[li] = make_int4(r, off, c[j], sb);
-          if (c[j] > kWarpLongMax) big_list[s_before[kTiBig] + atomicAdd(&s_cls[kTiBig], 1)] = li;
-        }
-        excl += ((unsigned long long)(uint32_t)c[j] << 32) | 1ull;
-      } else {
-        cell[idx] = -1;
-        cell_rank[idx] = -1;
+        vo[j] = off_tile + ol; vr[j] = r_tile + rl;
+        s_pcnt[rl] = c[j]; s_poff[rl] = off_tile + ol; s_pidx[rl] = (uint16_t)(tid * kScanItems + j);
+        ++rl; ol += c[j];
       }
     }
-  }
+    if (base + kScanItems <= cells) {
+      *reinterpret_cast<int4*>(cell + base) = make_int4(vo[0], vo[1], vo[2], vo[3]);
+      *reinterpret_cast<int4*>(cell + base + 4) = make_int4(vo[4], vo[5], vo[6], vo[7]);
+      *reinterpret_cast<int4*>(cell_rank + base) = make_int4(vr[0], vr[1], vr[2], vr[3]);
+      *reinterpret_cast<int4*>(cell_rank + base + 4) = make_int4(vr[4], vr[5], vr[6], vr[7]);
+    } else {
 #pragma unroll
-  for (int j = 0; j < kScanItems; ++j) {
-    if (my_slot[j] >= 0) {
-      const int k = my_slot[j] >> 16;
-      lists[s_lo[k] + s_before[kTiClass + k] + (my_slot[j] & 0xffff)] = my_ent[j];
+      for (int j = 0; j < kScanItems; ++j)
+        if (base + j < cells) { cell[base + j] = vo[j]; cell_rank[base + j] = vr[j]; }
+    }
+  }
+  __syncthreads();
+  // ---- phase B: per pillar, consecutive threads = consecutive ranks ----
+  const int npil = (int)(tile_total & 0xffffffffull);
+  const uint32_t nxy = (uint32_t)nx * (uint32_t)ny;                      // cells < 2^31 (checked by the host)
+  const uint32_t tile_cell0 = (uint32_t)(tile * kScanTileCells);
+  for (int q = tid; q < npil; q += kScanThreads) {
+    const int32_t cnt = s_pcnt[q], off = s_poff[q];
+    const int32_t r = r_tile + q;
+    const uint32_t idx = tile_cell0 + s_pidx[q];
+    const uint32_t b = idx / nxy, rem = idx - b * nxy;
+    const uint32_t cx = rem / (uint32_t)ny, cy = rem - cx * (uint32_t)ny;
+    seg_off[r] = off;
+    // (frame, z = 0, y, x): dynamic_pillar_vfe.py:138-143 after the [0, 3, 2, 1] reorder
+    *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4((int)b, 0, (int)cy, (int)cx);
+    if (pillar_count) pillar_count[r] = cnt;
+    if (cnt <= kSegRows) {
+      // the tile's first position in the class list is the sum of the class counters of the tiles before it
+      const int k = class_of(cnt);
+      const int slot = s_before[kTiClass + k] + atomicAdd(&s_cls[kTiClass + k], 1);
+      lists[s_lo[k] + slot] = pack_entry(r, off, cnt);
+    } else {
+      // long pillar: its index, its segment range (pillar_prep_kernel writes the segment entries)
+      const int nseg = (cnt + kSegRows - 1) / kSegRows;
+      const int li = s_before[kTiLong] + atomicAdd(&s_cls[kTiLong], 1);
+      const int sb = s_before[kTiSegs] + atomicAdd(&s_cls[kTiSegs], nseg);
+      long_table[li] = make_int4(r, off, cnt, sb);
+      if (cnt > kWarpLongMax) big_list[s_before[kTiBig] + atomicAdd(&s_cls[kTiBig], 1)] = li;
     }
   }
 }
