@@ -249,7 +249,7 @@ pfn_slot_kernel(const TcArgs A) {
     // =====================================================================================================
     // MMA warp
     // =====================================================================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    // (no setmaxnreg: ptxas does not confine a role's registers to the lowered budget, so nothing may be handed back)
     const uint32_t sw0h = smem_u32(smem + SP.w0h), sw0l = smem_u32(smem + SP.w0l);
     const uint32_t sw1ah = smem_u32(smem + SP.w1ah), sw1al = smem_u32(smem + SP.w1al);
     const uint32_t sw1bh = smem_u32(smem + SP.w1bh), sw1bl = smem_u32(smem + SP.w1bl);
