@@ -249,7 +249,10 @@ pfn_slot_kernel(const TcArgs A) {
     // =====================================================================================================
     // MMA warp
     // =====================================================================================================
-    // (no setmaxnreg: ptxas does not confine a role's registers to the lowered budget, so nothing may be handed back)
+    // The issue warp hands registers above 56 back to the CTA pool.  Nobody claims them; the instruction is here because
+    // ptxas schedules the kernel measurably better with it (161 vs 168 us).  ptxas does NOT confine the code that follows
+    // to the lowered budget by itself: tests/test_abi.py checks in the SASS that this role stays below 56 registers.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     const uint32_t sw0h = smem_u32(smem + SP.w0h), sw0l = smem_u32(smem + SP.w0l);
     const uint32_t sw1ah = smem_u32(smem + SP.w1ah), sw1al = smem_u32(smem + SP.w1al);
     const uint32_t sw1bh = smem_u32(smem + SP.w1bh), sw1bl = smem_u32(smem + SP.w1bl);

@@ -61,8 +61,9 @@ def test_argument_validation_returns_codes_not_crashes(lib):
     rc = lib.pcp_voxelize(None, 8, 10, 1, C.byref(g), None, 0, None, None, None, 10, None, None)
     assert rc == -1 and b"null" in lib.pcp_last_error_string()
     d = PcpPfnDesc(5, 1, 0, 3, 32, 64)
-    # hi/lo operand panels (K padded to 16) of W0, W1[:, :32], W1[:, 32:] + folded BN + fp32 W1[:, 32:] (long pillars)
-    assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 2, 32, 64))) == 2 * 16 * 32 + 4 * 32 * 64 + 64 + 128 + 64 * 32
+    # hi/lo operand panels (K padded to 16) of W0, W1[:, :32], W1[:, 32:], their sum (one-point pillars) + folded BN
+    # + fp32 W1[:, 32:] (long pillars)
+    assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 2, 32, 64))) == 2 * 16 * 32 + 6 * 32 * 64 + 64 + 128 + 64 * 32
     assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 1, 0, 64))) == 2 * 16 * 64 + 128
     rc = lib.pcp_pack_pfn_params(C.byref(d), *([None] * 12), C.c_float(1e-3), None, None)
     assert rc == -3 and b"num_layers" in lib.pcp_last_error_string()
@@ -87,3 +88,31 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU/torch fallback"):
         _lib.load()
+
+
+def test_pfn_issue_warp_stays_inside_its_register_budget():
+    """pfn_slot_kernel lowers the MMA-issue warp's register budget with setmaxnreg.dec 56; ptxas does not enforce
+    the budget on the code that follows, so check the SASS: no register above R55 between the USETMAXREG and the
+    first instruction of another role (cp.async / tensor-memory loads and stores)."""
+    import re
+    import shutil
+    import subprocess
+    obj = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "build", "pfn_tc.o")
+    if not (os.path.isfile(obj) and shutil.which("cuobjdump")):
+        pytest.skip("no object file / cuobjdump")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    seen = 0
+    for fn in sass.split("Function : ")[1:]:
+        if "pfn_slot_kernel" not in fn.split("\n")[0]:
+            continue
+        lines = fn.split("\n")
+        start = [i for i, l in enumerate(lines) if "USETMAXREG" in l]
+        assert len(start) == 1, "expected exactly one setmaxnreg in pfn_slot_kernel"
+        assert "0x38" in lines[start[0]], lines[start[0]]          # 56 registers
+        end = start[0]
+        while end < len(lines) and not re.search(r"LDGSTS|STTM|LDTM", lines[end]):
+            end += 1
+        regs = [int(x) for l in lines[start[0]:end] for x in re.findall(r"\bR(\d+)\b", l)]
+        assert max(regs) < 56, f"issue warp uses R{max(regs)} after lowering its budget to 56"
+        seen += 1
+    assert seen >= 3
