@@ -94,9 +94,9 @@ def test_pfn_issue_warp_stays_inside_its_register_budget():
     """pfn_slot_kernel lowers the MMA-issue warp's register budget with setmaxnreg.dec 56; ptxas does not enforce
     the budget on the code that follows, so check the SASS: no register above R55 between the USETMAXREG and the
     first instruction of another role (cp.async / tensor-memory loads and stores)."""
-    import re
     import shutil
     import subprocess
+    from pcp_b200 import _lib
     obj = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "build", "pfn_tc.o")
     if not (os.path.isfile(obj) and shutil.which("cuobjdump")):
         pytest.skip("no object file / cuobjdump")
