@@ -86,6 +86,54 @@ canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map
   }
 }
 
+// 256-bit gathers (sm_100: ld.global.v8.f32): one 32-byte sector of a pillar row per lane and instruction
+struct float8 { float v[8]; };
+__device__ __forceinline__ float8 ldg_f8(const float* p) {
+  float8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+// Fast path of the workspace variant: channels % 8 == 0, nx % 4 == 0, 32-byte aligned pillar rows, 16-byte aligned canvas.
+// Same tiling as canvas_kernel (a warp = one canvas row piece of 128 cells, a lane = 4 consecutive cells); per step a
+// lane gathers 8 channels of each of its pillars with one 256-bit load and issues eight 128-bit streaming stores.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
+canvas_v8_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
+                 float* __restrict__ canvas) {
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int y = blockIdx.y * kTileY + wy;
+  const int x0 = blockIdx.x * kTileX + lane * 4;
+  if (y >= ny || x0 >= nx) return;
+  const int64_t nxy = (int64_t)nx * ny;
+  int r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = __ldg(rank_map + b * nxy + (int64_t)(x0 + i) * ny + y);
+  float* dst = canvas + ((int64_t)b * channels) * nxy + (int64_t)y * nx + x0;
+  const bool any = (r[0] >= 0) | (r[1] >= 0) | (r[2] >= 0) | (r[3] >= 0);
+  if (!__any_sync(0xffffffffu, any)) {
+#pragma unroll 8
+    for (int c = 0; c < channels; ++c) st_stream_f4(dst + (int64_t)c * nxy, 0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  for (int c = 0; c < channels; c += 8) {
+    float8 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (r[i] >= 0) v[i] = ldg_f8(pf + (int64_t)r[i] * channels + c);
+      else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[i].v[q] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st_stream_f4(dst + (int64_t)(c + q) * nxy, v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]);
+  }
+}
+
 // generic path: canvas-ordered rank map from arbitrary voxel_coords rows (frame, z, y, x)
 __global__ void __launch_bounds__(256)
 coords_to_map_kernel(const int32_t* __restrict__ coords, int64_t P, int frames, int nx, int ny,
@@ -134,7 +182,13 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
     static const int variant = getenv("PCP_CANVAS_VARIANT") ? atoi(getenv("PCP_CANVAS_VARIANT")) : 0;   // tuning aid
     const dim3 cg = canvas_grid(grid->nx, grid->ny, num_frames);
     const int th = kTileY * 32;
-    if (variant == 5) {      // diagnostic: pure write stream (every cell treated as empty)
+    const bool fast8 = (channels % 8 == 0) && (grid->nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(pillar_features) & 31) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(canvas_out) & 15) == 0);
+    if ((variant == 0 || variant == 7) && fast8) {
+      canvas_v8_kernel<3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+    } else if (variant == 8 && fast8) {
+      canvas_v8_kernel<4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+    } else if (variant == 5) {      // diagnostic: pure write stream (every cell treated as empty)
       PCP_CUDA(cudaMemsetAsync(canvas_out, 0, sizeof(float) * (size_t)num_frames * channels * grid->nx * grid->ny, stream));
     } else if (variant == 1)
       canvas_kernel<true, 2, 4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
