@@ -165,7 +165,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -368,14 +368,37 @@ def run_ours(args):
             "gpu_launches": 8 * args.steps,
             "clocks": clk.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return line
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries below us write banners to file descriptor 1 (NCCL prints its
+    version there whatever NCCL_DEBUG says in some configurations), so fd 1 is pointed at stderr for the whole run
+    and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

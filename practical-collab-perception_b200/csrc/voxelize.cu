@@ -309,7 +309,7 @@ scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, i
     const uint32_t cx = rem / (uint32_t)ny, cy = rem - cx * (uint32_t)ny;
     seg_off[r] = off;
     // (frame, z = 0, y, x): dynamic_pillar_vfe.py:138-143 after the [0, 3, 2, 1] reorder
-    *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4((int)b, 0, (int)cy, (int)cx);
+    if (voxel_coords) *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4((int)b, 0, (int)cy, (int)cx);
     if (pillar_count) pillar_count[r] = cnt;
     if (cnt <= kSegRows) {
       // the tile's first position in the class list is the sum of the class counters of the tiles before it
@@ -378,6 +378,7 @@ __device__ __forceinline__ void cswap(int32_t& a, int32_t& b) {
 template <bool kVec4>
 __device__ __forceinline__ void load_xyz(const float* __restrict__ points, int64_t stride, int32_t idx, float& x, float& y,
                                          float& z) {
+  if (points == nullptr) { x = 0.f; y = 0.f; z = 0.f; return; }   // callers that only need the row order (no xyz mean)
   const float* row = points + (int64_t)idx * stride;
   if (kVec4) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(row));
@@ -729,6 +730,47 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
 
 }  // namespace pcp
 
+namespace pcp {
+// Everything after the keying kernel (which filled cell[] with the per-cell counts, key[] and within[]): cell scan, counting-sort
+// placement, ascending row order inside every pillar (+ the xyz mean when `points` is given).  Shared by pcp_voxelize(),
+// pcp_voxelize3d() and pcp_bev_scatter_mean().
+int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, int32_t ny, const float* points, int64_t stride,
+                    const pcp_grid& grid, int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
+                    int32_t* counts_out, cudaStream_t stream) {
+  tile_sums_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(W.cell, L.cells, nx, ny, W.tile_info,
+                                                                      W.tile_info + 16 * (L.scan_tiles + 1));
+  PCP_LAUNCH_CHECK("tile_sums_kernel");
+  scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
+      W.cell, W.cell_rank, L.cells, nx, ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
+      W.lists, L.lo, W.long_table, W.big_list, L.scan_tiles);
+  PCP_LAUNCH_CHECK("scan_cells_kernel");
+  {
+    const unsigned blocks = (unsigned)((n + 256 * kPtsPerThread - 1) / (256 * kPtsPerThread));
+    place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.cell_rank, n, W.sorted_idx,
+                                                          point_pillar_out, W.hdr, counts_out);
+    PCP_LAUNCH_CHECK("place_kernel");
+  }
+  if (n > 0) {
+    const int64_t want = (n + kPrepThreads - 1) / kPrepThreads;
+    const unsigned blocks = (unsigned)(want < 148 * 4 ? want : 148 * 4);
+    const bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    // PCP_PREP_SPLIT=1 (diagnostic): one launch per phase so that a launch list shows each phase's time
+    static const bool split = getenv("PCP_PREP_SPLIT") != nullptr;
+    for (int ph = 0; ph < (split ? 4 : 1); ++ph) {
+      const int mask = split ? (1 << ph) : 15;
+      if (vec4)
+        pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                     W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, mask);
+      else
+        pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, mask);
+    }
+    PCP_LAUNCH_CHECK("pillar_prep_kernel");
+  }
+  return 0;
+}
+}  // namespace pcp
+
 using namespace pcp;
 
 extern "C" size_t pcp_workspace_bytes(int64_t n_points, int32_t max_frames, int32_t nx, int32_t ny) {
@@ -770,35 +812,6 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
                                                                W.cell, W.key, W.within, W.hdr);
     PCP_LAUNCH_CHECK("quantise_count_kernel");
   }
-  tile_sums_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(W.cell, L.cells, grid->nx, grid->ny, W.tile_info,
-                                                                      W.tile_info + 16 * (L.scan_tiles + 1));
-  PCP_LAUNCH_CHECK("tile_sums_kernel");
-  scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
-      W.cell, W.cell_rank, L.cells, grid->nx, grid->ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
-      W.lists, L.lo, W.long_table, W.big_list, L.scan_tiles);
-  PCP_LAUNCH_CHECK("scan_cells_kernel");
-  {
-    const unsigned blocks = (unsigned)((n_points + 256 * kPtsPerThread - 1) / (256 * kPtsPerThread));
-    place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.cell_rank, n_points, W.sorted_idx,
-                                                          point_pillar_out, W.hdr, counts_out);
-    PCP_LAUNCH_CHECK("place_kernel");
-  }
-  if (n_points > 0) {
-    const int64_t want = (n_points + kPrepThreads - 1) / kPrepThreads;
-    const unsigned blocks = (unsigned)(want < 148 * 4 ? want : 148 * 4);
-    const bool vec4 = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
-    // PCP_PREP_SPLIT=1 (diagnostic): one launch per phase so that a launch list shows each phase's time
-    static const bool split = getenv("PCP_PREP_SPLIT") != nullptr;
-    for (int ph = 0; ph < (split ? 4 : 1); ++ph) {
-      const int mask = split ? (1 << ph) : 15;
-      if (vec4)
-        pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                     W.sorted_idx, W.mean, W.long_mean, W.long_acc, *grid, mask);
-      else
-        pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, row_stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc, *grid, mask);
-    }
-    PCP_LAUNCH_CHECK("pillar_prep_kernel");
-  }
-  return 0;
+  return finish_grouping(L, W, n_points, grid->nx, grid->ny, points, row_stride, *grid, point_pillar_out, voxel_coords_out,
+                         pillar_count_out, counts_out, stream);
 }
