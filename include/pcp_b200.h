@@ -45,6 +45,7 @@ extern "C" {
 #define PCP_COUNT_FRAMES      2   /* max frame index among pillars + 1 (0 if P == 0)        */
 #define PCP_COUNT_BAD_FRAME   3   /* points whose frame index was < 0 or >= max_frames      */
 #define PCP_COUNT_MAX_PER_PILLAR 4 /* largest number of points in one pillar               */
+#define PCP_COUNT_VOXELS      5   /* V  = non-empty 3-D voxels (pcp_voxelize3d_mean only)     */
 
 /* Constants DynamicPillarVFE.__init__ derives: pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py:77-89.
  * x/y/z_offset are computed by the HOST exactly as the reference does (voxel/2 + range_min, :80-82) and
@@ -172,6 +173,84 @@ int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreg
               const double* se3, int32_t num_agents, float scale, float max_sweep_idx,
               int32_t with_batch_col, float batch_idx, float* rows_out, int64_t out_stride,
               int32_t* box_idx_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * the callers and data formats either side of the pillar path.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* max(index) + 1 into *max_plus_one_out (device int32, 0 for an empty array): the `torch.max(points_batch_idx).item() + 1`
+ * of pcdet/models/bev_layers/hunter_toolbox.py:74. */
+int pcp_max_index_i64(const int64_t* index, int64_t n, int32_t* max_plus_one_out, void* stream);
+
+/*
+ * Points -> BEV image by per-pixel mean.  Replaces bev_scatter(), pcdet/models/bev_layers/hunter_toolbox.py:65-96
+ * (called every forward by pcdet/models/bev_layers/hunter_jr.py:279): strict in-image mask (:78-79), .long() truncation
+ * (:81), merge = b * area + y * width + x (:82), torch.unique + torch_scatter.scatter_mean (:84-86), zero fill and
+ * '(B H W) C -> B C H W' (:85,88).
+ *   bev_coord   (n_points, coord_stride >= 2) fp32: bev_x, bev_y (pixels)
+ *   batch_idx   (n_points) int64
+ *   feat        (n_points, feat_stride >= channels) fp32
+ *   workspace   pcp_workspace_bytes(n_points, num_frames, height, width) bytes (the pixel grid plays the pillar grid)
+ *   cell_mean_scratch (min(n_points, num_frames * height * width), channels) fp32
+ *   bev_out     (num_frames, channels, height, width) fp32, every element written
+ *   counts_out  int32[PCP_COUNTS_LEN]: [PCP_COUNT_PILLARS] = occupied pixels, [PCP_COUNT_KEPT] = points inside the image
+ * The per-pixel sum runs in ascending point order (the CPU scatter_mean's order): deterministic, bit-reproducible.
+ */
+int pcp_bev_scatter_mean(const float* bev_coord, int64_t coord_stride, const int64_t* batch_idx,
+                         const float* feat, int64_t feat_stride, int32_t channels, int64_t n_points,
+                         int32_t num_frames, int32_t height, int32_t width, void* workspace, size_t workspace_bytes,
+                         float* cell_mean_scratch, float* bev_out, int32_t* counts_out, void* stream);
+
+/*
+ * BEV image -> points by bilinear interpolation.  Replaces interpolate_points_feat_from_bev_img() and
+ * bilinear_interpolate_torch(), hunter_toolbox.py:8-41,99-131 (hunter_jr.py:268,300).
+ *   bev_img     (num_frames, channels, height, width) fp32, or (num_frames, height, width, channels) when channels_last != 0
+ *   points      (n_points, row_stride) fp32: column 0 = frame index, 1..2 = x, y (metres)
+ *   bev coordinate = (xy - range_min) / pixel, fp32 subtract and IEEE divide (:114)
+ *   nhwc_scratch     num_frames * channels * height * width floats (unused when channels_last != 0)
+ *   points_feat_out  (n_points, channels); rows whose frame index is outside [0, num_frames) are zero (:116-123)
+ *   bev_coord_out    (n_points, 2) or NULL (return_bev_coord)
+ * Every product / sum is rounded separately, in the reference's order: bit-exact against the CPU reference.
+ */
+int pcp_bev_interpolate(const float* bev_img, int32_t channels_last, int32_t num_frames, int32_t channels,
+                        int32_t height, int32_t width, const float* points, int64_t row_stride, int64_t n_points,
+                        float range_min_x, float range_min_y, float pixel_x, float pixel_y, float* nhwc_scratch,
+                        float* points_feat_out, float* bev_coord_out, void* stream);
+
+/*
+ * Dynamic 3-D voxelisation with per-voxel feature means.  Replaces DynamicMeanVFE.forward,
+ * pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:42-79 (the VFE of tools/cfgs/v2x_sim_models/v2x_second_*.yaml).
+ *   points   (n_points, row_stride) fp32: column 0 = frame index, columns 1 .. channels are averaged (x, y, z first)
+ *   grid     x / y constants as for pcp_voxelize(); range_min_z, voxel_z, nz: the third axis (nz <= 64)
+ *   workspace pcp_workspace_bytes(n, max_frames, nx, ny); scratch pcp_voxel3d_scratch_bytes(n, max_frames, nx, ny)
+ *   voxel_features_out (voxel_capacity, channels) fp32; voxel_coords_out (voxel_capacity, 4) int32 rows (frame, z, y, x) in
+ *   ascending key order b*nx*ny*nz + cx*ny*nz + cy*nz + cz (= torch.unique order); voxel_capacity >= min(n, cells * nz)
+ *   point_voxel_out (n_points) int32 voxel rank per input row (-1 = culled), may be NULL
+ *   counts_out[PCP_COUNT_VOXELS] = V, [PCP_COUNT_KEPT] = N'
+ */
+size_t pcp_voxel3d_scratch_bytes(int64_t n_points, int32_t max_frames, int32_t nx, int32_t ny);
+int pcp_voxelize3d_mean(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
+                        const pcp_grid* grid, float range_min_z, float voxel_z, int32_t nz, int32_t channels,
+                        void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                        float* voxel_features_out, int32_t* voxel_coords_out, int32_t* point_voxel_out,
+                        int64_t voxel_capacity, int32_t* counts_out, void* stream);
+
+/*
+ * Early-fusion input assembly.  Replaces pcdet/datasets/v2x_sim/v2x_sim_dataset_ego_early.py:85-92 (per-agent apply_se3_,
+ * nuscenes_temporal_utils.py:62-63, + np.concatenate), the range mask of pcdet/datasets/processor/data_processor.py:78-84
+ * (common_utils.py:64-68) and the frame-index column of collate_batch (pcdet/datasets/dataset.py:224-229).
+ *   points        (n_points, in_stride) fp32 rows x, y, z, ... of all agents, ego first (identity transform)
+ *   agent_offsets int32[num_agents + 1] device prefix offsets; se3 (num_agents, 12) fp64 device, rows 0..2 of target_se3_agent
+ *   range6_host   HOST float[6] point_cloud_range, or NULL for no mask
+ *   scratch       pcp_fuse_scratch_bytes(n_points) bytes
+ *   rows_out      (n_points, out_stride): [frame index if with_batch_col] x' y' z' then columns 3 .. n_cols-1 unchanged;
+ *                 surviving rows in input order; *count_out (device int32) = their number
+ */
+size_t pcp_fuse_scratch_bytes(int64_t n_points);
+int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols, int64_t n_points,
+                          const int32_t* agent_offsets, const double* se3, int32_t num_agents,
+                          const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
+                          float* rows_out, int64_t out_stride, int32_t* count_out, void* stream);
 
 /*
  * Diagnostic: C[128 x n] = A[128 x k] . B[n x k]^T through exactly the tensor-core path pcp_pfn() uses

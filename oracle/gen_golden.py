@@ -146,6 +146,104 @@ def modar_cases():
     print(f"modar_small -> {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def next_cases():
+    """SURVEY 8(f) rows, outputs of the reference's own functions / modules on seeded inputs -> tests/golden/next_*.npz."""
+    ns = rl.load_reference_modules()
+    g = torch.Generator().manual_seed(99)
+    # ---- hunter_toolbox: interpolate + bev_scatter on a (2, 24, 32, 40) image ----
+    B, C, H, W = 2, 24, 32, 40
+    rng6 = np.asarray([-8.0, -6.4, -8.0, 8.0, 6.4, 0.0], dtype=np.float32)
+    pix = np.asarray([0.4, 0.4], dtype=np.float32)
+    img = torch.randn(B, C, H, W, generator=g)
+    n = 3000
+    pts = torch.zeros(n, 8)
+    pts[:, 0] = torch.randint(0, B, (n,), generator=g).float()
+    pts[:, 1] = (torch.rand(n, generator=g) * 2 - 1) * 8.6          # some outside the image on both sides
+    pts[:, 2] = (torch.rand(n, generator=g) * 2 - 1) * 6.9
+    pts[:, 3:] = torch.randn(n, 5, generator=g)
+    # exact pixel centres / borders
+    pts[:40, 1] = torch.linspace(-8.0, 8.0, 40)
+    pts[:40, 2] = -6.4
+    pts[40:80, 1] = torch.arange(40).float() * 0.4 - 8.0
+    pts[40:80, 2] = torch.arange(40).float().remainder(32) * 0.4 - 6.4
+    feat_ref, coord_ref = ns.interpolate_points_feat_from_bev_img(img, pts.clone(), torch.from_numpy(rng6), torch.from_numpy(pix),
+                                                                  return_bev_coord=True)
+    pfeat = torch.randn(n, C, generator=g)
+    pfeat[:100] *= 1e3
+    bev_ref = ns.bev_scatter(coord_ref, pts[:, 0].long(), pfeat, (H, W))
+    np.savez_compressed(os.path.join(OUT, "next_hunter_small.npz"), bev_img=img.numpy(), points=pts.numpy(), range6=rng6, pixel=pix,
+                        ref_points_feat=feat_ref.numpy(), ref_bev_coord=coord_ref.numpy(), points_feat=pfeat.numpy(),
+                        ref_bev_scatter=bev_ref.numpy())
+    print("next_hunter_small", tuple(feat_ref.shape), tuple(bev_ref.shape))
+
+    # ---- DynamicMeanVFE on a 64 x 64 x 10 grid (SECOND-style), 3 frames ----
+    vox3 = [0.2, 0.2, 0.8]
+    rng3 = np.asarray([-6.4, -6.4, -8.0, 6.4, 6.4, 0.0], dtype=np.float32)
+    grid3 = syn.grid_size_of(rng3, vox3)
+    p3 = syn.batch_of_frames(3, 2500, 9)
+    p3[:, 1:3] *= 0.12
+    p3[:50, 3] = torch.linspace(-8.2, 0.2, 50)                       # z outside its range IS culled here
+    with ns.cuda_is_identity():
+        mvfe = ns.DynamicMeanVFE(model_cfg=rl.Cfg(), num_point_features=5, voxel_size=vox3, grid_size=grid3, point_cloud_range=rng3)
+    with torch.no_grad():
+        bd = mvfe({"points": p3.clone()})
+    np.savez_compressed(os.path.join(OUT, "next_meanvfe_small.npz"), points=p3.numpy(), voxel_size=np.asarray(vox3), point_cloud_range=rng3,
+                        grid_size=grid3, num_point_features=np.int64(5), ref_voxel_features=bd["voxel_features"].numpy(),
+                        ref_voxel_coords=bd["voxel_coords"].numpy())
+    print("next_meanvfe_small", tuple(bd["voxel_features"].shape))
+
+    # ---- DynamicPillarVFESimple2D, 64 x 64 grid, all 7 columns ----
+    small_rng, small_vox = np.asarray([-6.4, -6.4, -8.0, 6.4, 6.4, 0.0], dtype=np.float32), [0.2, 0.2, 8.0]
+    grid2 = syn.grid_size_of(small_rng, small_vox)
+    p2 = syn.batch_of_frames(3, 600, 7)
+    p2[:, 1:3] *= 0.1
+    for tag, use_abs, dist in (("abs", True, False), ("rel_dist", False, True)):
+        cfg = rl.Cfg(USE_NORM=True, WITH_DISTANCE=dist, USE_ABSLOTE_XYZ=use_abs, NUM_FILTERS=[64, 64])
+        with ns.cuda_is_identity():
+            m = ns.DynamicPillarVFESimple2D(model_cfg=cfg, num_point_features=7, voxel_size=small_vox, grid_size=grid2,
+                                            point_cloud_range=small_rng)
+        c_in = 7 + (3 if use_abs else 0) + (1 if dist else 0)
+        sd = syn.pfn_state_dict(c_in, (64, 64), True, 11)
+        missing = m.load_state_dict(sd)
+        assert not missing.missing_keys and not missing.unexpected_keys, missing
+        m.eval()
+        with torch.no_grad():
+            bd = m({"points": p2.clone()})
+        data = dict(points=p2.numpy(), voxel_size=np.asarray(small_vox), point_cloud_range=small_rng, grid_size=grid2,
+                    use_abs=np.bool_(use_abs), with_distance=np.bool_(dist), ref_pillar_features=bd["pillar_features"].numpy(),
+                    ref_pillar_coords=bd["pillar_coords"].numpy())
+        for k, v in sd.items():
+            data["sd/" + k] = v.numpy()
+        np.savez_compressed(os.path.join(OUT, f"next_simple2d_{tag}.npz"), **data)
+        print(f"next_simple2d_{tag}", tuple(bd["pillar_features"].shape))
+
+    # ---- early-fusion assembly: apply_se3_ per agent (the reference's function) + concatenate + mask_points_by_range ----
+    clouds, tfs = [], []
+    for a in range(4):
+        f = syn.lidar_frame(1500, 7000 + a)[:, 1:].contiguous()      # (n, 7) x y z i t sweep inst
+        clouds.append(f.numpy().copy())
+        if a > 0:
+            ag = syn.modar_agent(5000 + a, n_boxes=1)
+            tfs.append(ag["target_se3_agent"])
+    moved = [clouds[0]]
+    for c, tf in zip(clouds[1:], tfs):
+        x = c.copy()
+        x[:, :3] = ns.apply_se3_(tf, points_=x[:, :3], return_transformed=True)      # v2x_sim_dataset_ego_early.py:85
+        moved.append(x)
+    cat = np.concatenate(moved, axis=0)
+    r = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    # mask_points_by_range, pcdet/utils/common_utils.py:64-68 (that module imports SharedArray-era dependencies at import
+    # time; its three lines are evaluated here verbatim on the reference-transformed points)
+    mask = (cat[:, 0] >= r[0]) & (cat[:, 0] < r[3]) & (cat[:, 1] >= r[1]) & (cat[:, 1] < r[4]) & (cat[:, 2] >= r[2]) & (cat[:, 2] < r[5])
+    data = {"range6": r, "ref_fused": cat[mask], "ref_fused_nomask": cat}
+    for a, c in enumerate(clouds):
+        data[f"cloud{a}"] = c
+    for a, tf in enumerate(tfs):
+        data[f"se3_{a + 1}"] = tf
+    np.savez_compressed(os.path.join(OUT, "next_early_fusion_small.npz"), **data)
+    print("next_early_fusion_small", cat.shape, int(mask.sum()))
+
+
 def main():
     assert rl.reference_available(), "run in the build container: /root/reference must exist"
     torch.set_num_threads(1)
@@ -174,6 +272,7 @@ def main():
     save_case("vfe_opts_relxyz", pts, 5, small_vox, small_rng, store_canvas=True, use_abs=False, seed=5)
     save_case("vfe_opts_single_layer", pts, 5, small_vox, small_rng, store_canvas=True, num_filters=(64,), seed=6)
     modar_cases()
+    next_cases()
 
 
 if __name__ == "__main__":

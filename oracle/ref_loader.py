@@ -11,6 +11,7 @@ parent package:
 * ``pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py`` (+ ``vfe_template.py``)
 * ``pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py``
 * ``pcdet/datasets/nuscenes/nuscenes_temporal_utils.py`` (``apply_se3_``)
+* ``pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py``, ``pcdet/models/bev_layers/hunter_toolbox.py``
 
 ``torch_scatter`` is absent and unpinned by the reference; a pure-torch stand-in that follows its
 published semantics is placed in ``sys.modules`` (same restatement as oracle/pillar_oracle.py).
@@ -104,7 +105,10 @@ def load_reference_modules():
     sys.modules[pkg] = parent
     _load(f"{pkg}.vfe_template", "pcdet/models/backbones_3d/vfe/vfe_template.py", pkg)
     vfe = _load(f"{pkg}.dynamic_pillar_vfe", "pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py", pkg)
+    mean_vfe = _load(f"{pkg}.dynamic_mean_vfe", "pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py", pkg)
     scat = _load("_pcp_ref_pointpillar_scatter", "pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py")
+    # the two hot functions of the HunterJr head (imports torch, torch_scatter (shim), einops only)
+    hunter = _load("_pcp_ref_hunter_toolbox", "pcdet/models/bev_layers/hunter_toolbox.py")
 
     # nuscenes_temporal_utils imports nuscenes + pyquaternion at module scope (only type names are used
     # by apply_se3_): satisfy them with empty stand-ins.
@@ -122,6 +126,8 @@ def load_reference_modules():
     ns = types.SimpleNamespace(
         DynamicPillarVFE=vfe.DynamicPillarVFE, PFNLayerV2=vfe.PFNLayerV2,
         PointPillarScatter=scat.PointPillarScatter, apply_se3_=se3.apply_se3_,
+        DynamicMeanVFE=mean_vfe.DynamicMeanVFE, DynamicPillarVFESimple2D=vfe.DynamicPillarVFESimple2D,
+        bev_scatter=hunter.bev_scatter, interpolate_points_feat_from_bev_img=hunter.interpolate_points_feat_from_bev_img,
         cuda_is_identity=_cuda_is_identity)
     _cache["ns"] = ns
     return ns

@@ -12,12 +12,18 @@ from .config import CfgDict  # noqa: F401
 
 def __getattr__(name):
     # heavy members are resolved lazily so that ``import pcp_b200`` works on a CPU-only build host
-    if name in ("DynamicPillarVFE", "PFNLayerV2", "PointPillarScatter"):
+    if name in ("DynamicPillarVFE", "PFNLayerV2", "PointPillarScatter", "DynamicMeanVFE", "DynamicPillarVFESimple2D"):
         from . import modules
         return getattr(modules, name)
     if name in ("modar_exchange", "ModarExchange"):
         from . import modar
         return getattr(modar, name)
+    if name in ("bev_scatter", "interpolate_points_feat_from_bev_img"):
+        from . import hunter_toolbox
+        return getattr(hunter_toolbox, name)
+    if name in ("fuse_agent_points",):
+        from . import early_fusion
+        return getattr(early_fusion, name)
     if name in ("FrontEnd",):
         from . import frontend
         return getattr(frontend, name)

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libpcp_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 PCP_COUNTS_LEN = 8
-COUNT_PILLARS, COUNT_KEPT, COUNT_FRAMES, COUNT_BAD_FRAME, COUNT_MAX_PER_PILLAR = 0, 1, 2, 3, 4
+COUNT_PILLARS, COUNT_KEPT, COUNT_FRAMES, COUNT_BAD_FRAME, COUNT_MAX_PER_PILLAR, COUNT_VOXELS = 0, 1, 2, 3, 4, 5
 
 
 class PcpGrid(C.Structure):
@@ -46,6 +46,17 @@ _SIGNATURES = {
     "pcp_selftest_umma": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "pcp_selftest_umma_ts": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "pcp_selftest_umma_cycles": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "pcp_max_index_i64": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "pcp_bev_scatter_mean": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                       _P, C.c_size_t, _P, _P, _P, _P]),
+    "pcp_bev_interpolate": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int64,
+                                      C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
+    "pcp_voxel3d_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "pcp_voxelize3d_mean": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(PcpGrid), C.c_float, C.c_float, C.c_int32,
+                                      C.c_int32, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, C.c_int64, _P, _P]),
+    "pcp_fuse_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "pcp_fuse_agent_points": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int32, _P, C.c_int32, C.c_float, _P,
+                                        _P, C.c_int64, _P, _P]),
     "pcp_modar": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,
                             _P, C.c_int64, _P, _P]),
 }

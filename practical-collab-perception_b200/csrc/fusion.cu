@@ -1,0 +1,171 @@
+// fusion.cu - early-fusion input assembly on the GPU
+// (reference: pcdet/datasets/v2x_sim/v2x_sim_dataset_ego_early.py:85-92 - every agent's sweep stack mapped into the ego
+//  frame with apply_se3_ (nuscenes_temporal_utils.py:62-63: xyz @ R.T + t in fp64, stored back to fp32) and concatenated
+//  after the ego points; pcdet/datasets/processor/data_processor.py:78-84 + common_utils.py:64-68 - the range mask
+//  x,y,z in [min, max); pcdet/datasets/dataset.py:224-229 - the frame-index column collate_batch prepends).
+// The reference then shuffles the rows with np.random.permutation (data_processor.py:95-104); every consumer on this path
+// is order-independent, so the rows are kept in input order (deterministic).
+//
+// Three launches: per-block kept counts, one-block scan of the block counts, then the transform is evaluated again and the
+// surviving rows are written at their final position (order-preserving compaction without a row-sized temporary).
+#include "internal.cuh"
+
+namespace pcp {
+
+constexpr int kFuseThreads = 256;
+constexpr int kFuseItems = 4;
+constexpr int kFuseBlock = kFuseThreads * kFuseItems;   // rows per CTA
+
+struct FuseArgs {
+  const float* points;
+  int64_t in_stride;
+  int32_t n_cols;            // columns of an input row (x, y, z, ...), all copied
+  const int32_t* agent_off;  // [num_agents + 1]
+  const double* se3;         // (num_agents, 12) rows 0..2 of target_se3_agent, row-major
+  int32_t num_agents;
+  float lo[3], hi[3];
+  int32_t apply_mask;
+};
+
+__device__ __forceinline__ int agent_of(const int32_t* __restrict__ off, int na, int64_t i) {
+  int a = 0;
+  while (a + 1 < na && i >= off[a + 1]) ++a;           // a handful of agents: linear search
+  return a;
+}
+
+// transformed xyz of row i (fp64 products and sums in the reference's matmul order, one rounding to fp32) and its mask
+__device__ __forceinline__ bool fuse_row(const FuseArgs& A, int64_t i, float& x, float& y, float& z) {
+  const float* row = A.points + i * A.in_stride;
+  const double px = (double)__ldg(row), py = (double)__ldg(row + 1), pz = (double)__ldg(row + 2);
+  const double* T = A.se3 + 12 * agent_of(A.agent_off, A.num_agents, i);
+  // numpy: (xyz @ R.T)[k] = x R[k,0] + y R[k,1] + z R[k,2] accumulated left to right, then + t[k]
+  x = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, T[0]), __dmul_rn(py, T[1])), __dmul_rn(pz, T[2])), T[3]);
+  y = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, T[4]), __dmul_rn(py, T[5])), __dmul_rn(pz, T[6])), T[7]);
+  z = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, T[8]), __dmul_rn(py, T[9])), __dmul_rn(pz, T[10])), T[11]);
+  if (!A.apply_mask) return true;
+  return x >= A.lo[0] && x < A.hi[0] && y >= A.lo[1] && y < A.hi[1] && z >= A.lo[2] && z < A.hi[2];
+}
+
+__global__ void __launch_bounds__(kFuseThreads)
+fuse_count_kernel(const FuseArgs A, int64_t n, int32_t* __restrict__ block_sum) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+#pragma unroll
+  for (int u = 0; u < kFuseItems; ++u) {
+    const int64_t i = (int64_t)blockIdx.x * kFuseBlock + (int64_t)threadIdx.x * kFuseItems + u;
+    float x, y, z;
+    if (i < n && fuse_row(A, i, x, y, z)) ++c;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) block_sum[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(1024)
+fuse_scan_kernel(int32_t* __restrict__ block_sum, int32_t num_blocks, int32_t* __restrict__ count_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < num_blocks; b0 += 1024) {
+    const int i = b0 + tid;
+    const int v = (i < num_blocks) ? block_sum[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int wex = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wex += s_warp[w]; tot += s_warp[w]; }
+    const int carry = s_carry;
+    if (i < num_blocks) block_sum[i] = carry + wex + incl - v;
+    __syncthreads();
+    if (tid == 0) s_carry = carry + tot;
+    __syncthreads();
+  }
+  if (tid == 0) *count_out = s_carry;
+}
+
+__global__ void __launch_bounds__(kFuseThreads)
+fuse_write_kernel(const FuseArgs A, int64_t n, const int32_t* __restrict__ block_excl, int32_t with_batch_col, float batch_idx,
+                  float* __restrict__ out, int64_t out_stride) {
+  __shared__ int s_warp[kFuseThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float x[kFuseItems], y[kFuseItems], z[kFuseItems];
+  bool keep[kFuseItems];
+  int c = 0;
+#pragma unroll
+  for (int u = 0; u < kFuseItems; ++u) {
+    const int64_t i = (int64_t)blockIdx.x * kFuseBlock + (int64_t)tid * kFuseItems + u;
+    keep[u] = (i < n) && fuse_row(A, i, x[u], y[u], z[u]);
+    c += keep[u] ? 1 : 0;
+  }
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int pos = block_excl[blockIdx.x] + incl - c;
+  for (int w = 0; w < warp; ++w) pos += s_warp[w];
+#pragma unroll
+  for (int u = 0; u < kFuseItems; ++u) {
+    if (!keep[u]) continue;
+    const int64_t i = (int64_t)blockIdx.x * kFuseBlock + (int64_t)tid * kFuseItems + u;
+    const float* row = A.points + i * A.in_stride;
+    float* dst = out + (int64_t)pos * out_stride;
+    if (with_batch_col) *dst++ = batch_idx;
+    dst[0] = x[u]; dst[1] = y[u]; dst[2] = z[u];
+    for (int k = 3; k < A.n_cols; ++k) dst[k] = __ldg(row + k);
+    ++pos;
+  }
+}
+
+}  // namespace pcp
+
+using namespace pcp;
+
+extern "C" size_t pcp_fuse_scratch_bytes(int64_t n_points) {
+  if (n_points < 0) return 0;
+  return sizeof(int32_t) * (size_t)((n_points + kFuseBlock - 1) / kFuseBlock + 1);
+}
+
+extern "C" int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols, int64_t n_points,
+                                     const int32_t* agent_offsets, const double* se3, int32_t num_agents,
+                                     const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
+                                     float* rows_out, int64_t out_stride, int32_t* count_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(count_out && scratch, PCP_E_INVALID, "pcp_fuse_agent_points: null argument");
+  PCP_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - kFuseBlock, PCP_E_INVALID, "pcp_fuse_agent_points: n_points out of range");
+  PCP_REQUIRE(n_points == 0 || (points && rows_out && agent_offsets && se3), PCP_E_INVALID, "pcp_fuse_agent_points: null input");
+  PCP_REQUIRE(n_cols >= 3 && in_stride >= n_cols && out_stride >= n_cols + (with_batch_col ? 1 : 0), PCP_E_INVALID,
+              "pcp_fuse_agent_points: bad column counts / strides");
+  PCP_REQUIRE(num_agents >= 1 && num_agents <= 64, PCP_E_INVALID, "pcp_fuse_agent_points: 1 <= num_agents <= 64");
+  FuseArgs A{};
+  A.points = points; A.in_stride = in_stride; A.n_cols = n_cols; A.agent_off = agent_offsets; A.se3 = se3; A.num_agents = num_agents;
+  A.apply_mask = range6_host != nullptr;
+  if (range6_host)
+    for (int k = 0; k < 3; ++k) { A.lo[k] = range6_host[k]; A.hi[k] = range6_host[3 + k]; }
+  const int nblk = (int)((n_points + kFuseBlock - 1) / kFuseBlock);
+  if (nblk == 0) {
+    PCP_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), stream));
+    return 0;
+  }
+  fuse_count_kernel<<<nblk, kFuseThreads, 0, stream>>>(A, n_points, scratch);
+  PCP_LAUNCH_CHECK("fuse_count_kernel");
+  fuse_scan_kernel<<<1, 1024, 0, stream>>>(scratch, nblk, count_out);
+  PCP_LAUNCH_CHECK("fuse_scan_kernel");
+  fuse_write_kernel<<<nblk, kFuseThreads, 0, stream>>>(A, n_points, scratch, with_batch_col, batch_idx, rows_out, out_stride);
+  PCP_LAUNCH_CHECK("fuse_write_kernel");
+  return 0;
+}

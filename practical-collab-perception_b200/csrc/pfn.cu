@@ -2,7 +2,7 @@
 // PFNLayerV2 :35-46): parameter packing (BatchNorm folding, TF32 hi/lo operand panels), the launch of the
 // tensor-core kernel (pfn_tc.cu), the finishing kernel of long pillars, and the stand-alone segmented
 // mean / max (torch_scatter.scatter_mean / scatter_max).
-#include "common.cuh"
+#include "internal.cuh"
 #include "pfn_tc.cuh"
 #include "umma.cuh"
 
@@ -167,6 +167,17 @@ segment_reduce_kernel(const float* __restrict__ values, int64_t vstride, int cha
   }
 }
 
+int launch_segment_reduce(const float* values, int64_t value_stride, int32_t channels, int32_t mode, const WsView& W,
+                          float* out, cudaStream_t stream) {
+  const unsigned blocks = 148 * 8;
+  if (mode == 0)
+    segment_reduce_kernel<0><<<blocks, 256, 0, stream>>>(values, value_stride, channels, W.hdr, W.seg_off, W.sorted_idx, out);
+  else
+    segment_reduce_kernel<1><<<blocks, 256, 0, stream>>>(values, value_stride, channels, W.hdr, W.seg_off, W.sorted_idx, out);
+  PCP_LAUNCH_CHECK("segment_reduce_kernel");
+  return 0;
+}
+
 }  // namespace pcp
 
 using namespace pcp;
@@ -262,11 +273,5 @@ extern "C" int pcp_segment_reduce(const float* values, int64_t value_stride, int
   PCP_REQUIRE(pillar_capacity >= L.cap, PCP_E_INVALID, "pcp_segment_reduce: pillar_capacity too small");
   if (n_points == 0) return 0;
   const WsView W = ws_view(const_cast<void*>(workspace), L);
-  const unsigned blocks = 148 * 8;
-  if (mode == 0)
-    segment_reduce_kernel<0><<<blocks, 256, 0, stream>>>(values, value_stride, channels, W.hdr, W.seg_off, W.sorted_idx, out);
-  else
-    segment_reduce_kernel<1><<<blocks, 256, 0, stream>>>(values, value_stride, channels, W.hdr, W.seg_off, W.sorted_idx, out);
-  PCP_LAUNCH_CHECK("segment_reduce_kernel");
-  return 0;
+  return launch_segment_reduce(values, value_stride, channels, mode, W, out, stream);
 }

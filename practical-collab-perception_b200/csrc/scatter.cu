@@ -8,7 +8,7 @@
 // registers and issues 128-bit streaming stores, 512 contiguous bytes per warp per (channel, row).
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace pcp {
 
@@ -204,6 +204,15 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
   PCP_LAUNCH_CHECK("canvas_kernel<ws>");
   return 0;
 }
+
+namespace pcp {
+int launch_canvas_from_map(const float* rows, const int32_t* rank_map, int32_t channels, int32_t frames, int32_t nx,
+                           int32_t ny, float* canvas, cudaStream_t stream) {
+  canvas_kernel<false, 2, 3><<<canvas_grid(nx, ny, frames), kTileY * 32, 0, stream>>>(rows, rank_map, channels, nx, ny, canvas, 0);
+  PCP_LAUNCH_CHECK("canvas_kernel<map>");
+  return 0;
+}
+}  // namespace pcp
 
 extern "C" int pcp_bev_scatter(const float* pillar_features, const int32_t* voxel_coords, int64_t num_pillars,
                                int32_t channels, int32_t num_frames, int32_t nx, int32_t ny,

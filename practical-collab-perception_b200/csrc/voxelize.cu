@@ -18,7 +18,7 @@
 // No kernel synchronises with the host; the only data-dependent size (P) is read back by the caller.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace pcp {
 

@@ -10,11 +10,13 @@ from __future__ import annotations
 
 def patch_pcdet(vfe_registry: dict = None, map_to_bev_registry: dict = None) -> None:
     """``patch_pcdet()`` imports pcdet and patches it in place; or pass the two ``__all__`` dicts."""
-    from .modules import DynamicPillarVFE, PointPillarScatter
+    from .modules import DynamicMeanVFE, DynamicPillarVFE, DynamicPillarVFESimple2D, PointPillarScatter
     if vfe_registry is None or map_to_bev_registry is None:
         from pcdet.models.backbones_3d import vfe                     # noqa: WPS433 (optional dependency)
         from pcdet.models.backbones_2d import map_to_bev
         vfe_registry = vfe.__all__ if vfe_registry is None else vfe_registry
         map_to_bev_registry = map_to_bev.__all__ if map_to_bev_registry is None else map_to_bev_registry
     vfe_registry["DynPillarVFE"] = DynamicPillarVFE
+    vfe_registry["DynMeanVFE"] = DynamicMeanVFE                                 # vfe/__init__.py:13
+    vfe_registry["DynamicPillarVFESimple2D"] = DynamicPillarVFESimple2D         # vfe/__init__.py:15
     map_to_bev_registry["PointPillarScatter"] = PointPillarScatter

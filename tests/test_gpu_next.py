@@ -1,0 +1,224 @@
+"""GPU parity of the SURVEY 8(f) rows (bev_scatter / interpolate, DynamicMeanVFE, DynamicPillarVFESimple2D, early-fusion
+assembly): the sm_100a kernels, called through the drop-in Python surface / C ABI, against the committed outputs of the
+reference's own code (tests/golden/next_*.npz) and against the CPU oracle on larger seeded inputs and edge cases.
+
+Bars: coordinates / indices / occupancy bit-exact; bilinear interpolation, per-pixel and per-voxel means bit-exact (every
+product and sum is rounded separately in the reference's order; sums run in ascending row order like the CPU scatter_mean);
+PFN outputs within 1e-5 relative; SE(3) transform: fp64 evaluation rounded once to fp32 (bit-exact up to the last-bit
+ambiguity of a BLAS FMA, allowed on < 1e-5 of the values, 1 ulp).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import next_oracle as no
+from oracle import pillar_oracle as po
+from tests.helpers import GOLDEN_DIR, assert_features_close, layers_from_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+# ------------------------------------------------------------------------------------------------ hunter_toolbox
+def test_interpolate_golden():
+    import pcp_b200
+    g = _load("next_hunter_small")
+    feat, coord = pcp_b200.interpolate_points_feat_from_bev_img(torch.from_numpy(g["bev_img"]).to(DEV), torch.from_numpy(g["points"]).to(DEV),
+                                                                torch.from_numpy(g["range6"]).to(DEV), torch.from_numpy(g["pixel"]).to(DEV),
+                                                                return_bev_coord=True)
+    assert np.array_equal(coord.cpu().numpy(), g["ref_bev_coord"])
+    assert np.array_equal(feat.cpu().numpy(), g["ref_points_feat"])
+    only = pcp_b200.interpolate_points_feat_from_bev_img(torch.from_numpy(g["bev_img"]).to(DEV), torch.from_numpy(g["points"]).to(DEV),
+                                                         g["range6"], g["pixel"])
+    assert torch.equal(only, feat)
+
+
+def test_bev_scatter_golden():
+    import pcp_b200
+    g = _load("next_hunter_small")
+    pts = torch.from_numpy(g["points"])
+    h, w = g["bev_img"].shape[2:]
+    bev = pcp_b200.bev_scatter(torch.from_numpy(g["ref_bev_coord"]).to(DEV), pts[:, 0].long().to(DEV),
+                               torch.from_numpy(g["points_feat"]).to(DEV), (h, w))
+    assert np.array_equal(bev.cpu().numpy(), g["ref_bev_scatter"])
+
+
+@pytest.mark.parametrize("n,b,c,h,w", [(50000, 4, 64, 128, 128), (3000, 1, 7, 33, 47), (1, 1, 3, 4, 4), (20000, 2, 32, 256, 256)])
+def test_hunter_round_trip_vs_oracle(n, b, c, h, w):
+    """image -> points -> image on seeded inputs; odd channel counts and image sizes; points on and outside the border."""
+    import pcp_b200
+    gen = torch.Generator().manual_seed(n + c)
+    img = torch.randn(b, c, h, w, generator=gen)
+    pts = torch.zeros(n, 6)
+    pts[:, 0] = torch.randint(0, b, (n,), generator=gen).float()
+    pts[:, 0][0] = b - 1                                           # the last frame is present
+    pix = np.asarray([0.4, 0.8], dtype=np.float32)
+    rng = np.asarray([-0.4 * w / 2, -0.8 * h / 2, -3.0], dtype=np.float32)
+    pts[:, 1] = (torch.rand(n, generator=gen) * 1.1 - 0.55) * (0.4 * w)
+    pts[:, 2] = (torch.rand(n, generator=gen) * 1.1 - 0.55) * (0.8 * h)
+    feat, coord = pcp_b200.interpolate_points_feat_from_bev_img(img.to(DEV), pts.to(DEV), rng, pix, return_bev_coord=True)
+    wf, wc = no.interpolate_points_feat_from_bev_img(img, pts, rng[:2], pix)
+    assert torch.equal(coord.cpu(), wc)
+    assert torch.equal(feat.cpu(), wf)
+    bev = pcp_b200.bev_scatter(coord, pts[:, 0].long().to(DEV), feat, (h, w))
+    want = no.bev_scatter(wc, pts[:, 0].long(), wf, (h, w))
+    assert tuple(bev.shape) == tuple(want.shape)
+    assert torch.equal(bev.cpu(), want)
+
+
+def test_bev_scatter_edges():
+    import pcp_b200
+    # every point outside the image: an all-zero image of the right shape; frame index of a culled point still counts (:74)
+    coord = torch.tensor([[-1.0, 2.0], [0.0, 0.5], [4.0, 1.0], [1.0, 4.0], [float("nan"), 1.0]])
+    bidx = torch.tensor([0, 2, 1, 0, 1])
+    feat = torch.ones(5, 3)
+    bev = pcp_b200.bev_scatter(coord.to(DEV), bidx.to(DEV), feat.to(DEV), (4, 4))
+    assert tuple(bev.shape) == (3, 3, 4, 4) and float(bev.abs().sum()) == 0.0
+    # many points in one pixel: sequential sum in row order
+    gen = torch.Generator().manual_seed(3)
+    for n in (4000, 9000):
+        coord = torch.rand(n, 2, generator=gen) * 0.9 + 1.05      # all in pixel (1, 1)
+        feat = torch.randn(n, 5, generator=gen) * 100
+        bidx = torch.zeros(n, dtype=torch.long)
+        bev = pcp_b200.bev_scatter(coord.to(DEV), bidx.to(DEV), feat.to(DEV), (3, 3), batch_size=1)
+        want = no.bev_scatter(coord, bidx, feat, (3, 3))
+        if n <= 4096:
+            assert torch.equal(bev.cpu(), want)                   # rows of a cell are visited in ascending order
+        else:
+            # above 4096 rows per cell the rows keep their arrival order: same mean within fp32 tolerance
+            assert_features_close(bev.cpu().numpy(), want.numpy(), "giant cell mean", rtol=1e-5, atol_scale=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ DynamicMeanVFE
+def _mean_vfe(points, c, vox, rng, grid, batch_size=None):
+    import pcp_b200
+    m = pcp_b200.DynamicMeanVFE(model_cfg=pcp_b200.CfgDict(), num_point_features=c, voxel_size=vox, grid_size=grid,
+                                point_cloud_range=rng)
+    bd = {"points": points.to(DEV)}
+    if batch_size is not None:
+        bd["batch_size"] = batch_size
+    return m(bd)
+
+
+def test_dynamic_mean_vfe_golden():
+    g = _load("next_meanvfe_small")
+    vox = [float(v) for v in g["voxel_size"]]
+    bd = _mean_vfe(torch.from_numpy(g["points"]), int(g["num_point_features"]), vox, g["point_cloud_range"], g["grid_size"])
+    assert bd["voxel_coords"].dtype == torch.int32
+    assert np.array_equal(bd["voxel_coords"].cpu().numpy(), g["ref_voxel_coords"])
+    assert np.array_equal(bd["voxel_features"].cpu().numpy(), g["ref_voxel_features"])
+
+
+@pytest.mark.parametrize("n,frames,c,ego", [(60000, 2, 5, False), (40000, 3, 11, True), (200, 1, 4, False)])
+def test_dynamic_mean_vfe_vs_oracle(n, frames, c, ego):
+    """SECOND-style grid (v2x_second_car.yaml: 0.1 m x 0.1 m x 0.2 m -> 1024 x 1024 x 40)."""
+    from pcp_b200 import synthetic as syn
+    vox = [0.1, 0.1, 0.2]
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    grid = syn.grid_size_of(rng, vox)
+    pts = syn.batch_of_frames(frames, n, 11, ego_columns=ego)
+    pts[::7, 3] += 1.0                                             # some z above the range: culled here
+    bd = _mean_vfe(pts, c, vox, rng, grid, batch_size=frames)
+    want = no.dynamic_mean_vfe(pts, c, vox, rng, grid)
+    assert torch.equal(bd["voxel_coords"].cpu(), want["voxel_coords"])
+    assert torch.equal(bd["voxel_features"].cpu(), want["voxel_features"])
+
+
+def test_dynamic_mean_vfe_dense_pillar_and_empty():
+    """hundreds of points in one pillar spread over every z cell; then a batch where everything is culled."""
+    vox, rng = [0.2, 0.2, 0.5], np.asarray([-0.8, -0.8, -8.0, 0.8, 0.8, 0.0], dtype=np.float32)
+    grid = np.asarray([8, 8, 16])
+    gen = torch.Generator().manual_seed(1)
+    n = 3000
+    pts = torch.zeros(n, 6)
+    pts[:, 1:3] = torch.rand(n, 2, generator=gen) * 0.19 + 0.2
+    pts[:, 3] = torch.rand(n, generator=gen) * -8.0
+    pts[:, 4:] = torch.randn(n, 2, generator=gen)
+    bd = _mean_vfe(pts, 5, vox, rng, grid)
+    want = no.dynamic_mean_vfe(pts, 5, vox, rng, grid)
+    assert torch.equal(bd["voxel_coords"].cpu(), want["voxel_coords"])
+    assert torch.equal(bd["voxel_features"].cpu(), want["voxel_features"])
+    far = pts.clone()
+    far[:, 1] += 10.0
+    bd = _mean_vfe(far, 5, vox, rng, grid, batch_size=1)
+    assert bd["voxel_coords"].shape == (0, 4) and bd["voxel_features"].shape == (0, 5)
+
+
+# ------------------------------------------------------------------------------------------------ Simple2D
+@pytest.mark.parametrize("tag", ["abs", "rel_dist"])
+def test_simple2d_golden(tag):
+    import pcp_b200
+    g = _load(f"next_simple2d_{tag}")
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")}
+    cfg = pcp_b200.CfgDict(USE_NORM=True, WITH_DISTANCE=bool(g["with_distance"]), USE_ABSLOTE_XYZ=bool(g["use_abs"]), NUM_FILTERS=[64, 64])
+    m = pcp_b200.DynamicPillarVFESimple2D(model_cfg=cfg, num_point_features=7, voxel_size=[float(v) for v in g["voxel_size"]],
+                                          grid_size=g["grid_size"], point_cloud_range=g["point_cloud_range"])
+    missing = m.load_state_dict(sd)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        bd = m({"points": torch.from_numpy(g["points"]).to(DEV)})
+    assert "voxel_coords" not in bd and "voxel_features" not in bd
+    assert np.array_equal(bd["pillar_coords"].cpu().numpy(), g["ref_pillar_coords"])
+    assert_features_close(bd["pillar_features"].cpu().numpy(), g["ref_pillar_features"], "pillar_features")
+
+
+# ------------------------------------------------------------------------------------------------ early fusion
+def _close_fp64_rounded(got, want):
+    assert got.shape == want.shape
+    same = got == want
+    frac = 1.0 - float(same.mean())
+    assert frac < 1e-5, f"{frac:.2e} of the values differ"
+    if frac:
+        ulp = np.abs(got[~same].view(np.int32).astype(np.int64) - want[~same].view(np.int32).astype(np.int64))
+        assert ulp.max() <= 1
+
+
+def test_early_fusion_golden():
+    import pcp_b200
+    g = _load("next_early_fusion_small")
+    clouds = [torch.from_numpy(g[f"cloud{a}"]).to(DEV) for a in range(4)]
+    tfs = [g[f"se3_{a}"] for a in range(1, 4)]
+    fused = pcp_b200.fuse_agent_points(clouds[0], clouds[1:], tfs, g["range6"], batch_idx=3).cpu().numpy()
+    assert np.all(fused[:, 0] == 3.0)
+    assert fused.shape[0] == g["ref_fused"].shape[0]
+    _close_fp64_rounded(fused[:, 1:], g["ref_fused"])
+    nomask = pcp_b200.fuse_agent_points(clouds[0], clouds[1:], tfs, None, batch_idx=None).cpu().numpy()
+    _close_fp64_rounded(nomask, g["ref_fused_nomask"])
+
+
+def test_early_fusion_feeds_the_pillar_path():
+    """BASELINE configs[2] shape in small: 6 clouds fused on the GPU, then DynamicPillarVFE + PointPillarScatter; checked
+    against the oracle chain on the CPU-fused cloud."""
+    import pcp_b200
+    from pcp_b200 import synthetic as syn
+    from tests.helpers import model_cfgs
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    vox = syn.V2X_VOXEL
+    grid = syn.grid_size_of(rng, vox)
+    clouds = [syn.lidar_frame(20000, 8100 + a)[:, 1:].contiguous() for a in range(6)]
+    tfs = [syn.modar_agent(8200 + a, n_boxes=1)["target_se3_agent"] for a in range(5)]
+    fused = pcp_b200.fuse_agent_points(clouds[0].to(DEV), [c.to(DEV) for c in clouds[1:]], tfs, rng, batch_idx=0)
+    want_pts = no.fuse_agent_points(clouds[0].numpy(), [c.numpy() for c in clouds[1:]], tfs, rng)
+    assert fused.shape == (want_pts.shape[0], 8)
+    got = fused.cpu().numpy()
+    _close_fp64_rounded(got[:, 1:], want_pts)
+    vfe_cfg, scat_cfg = model_cfgs(5)
+    sd = syn.pfn_state_dict(11)
+    vfe = pcp_b200.DynamicPillarVFE(model_cfg=vfe_cfg, num_point_features=5, voxel_size=vox, grid_size=grid, point_cloud_range=rng)
+    vfe.load_state_dict(sd)
+    vfe = vfe.to(DEV).eval()
+    scat = pcp_b200.PointPillarScatter(model_cfg=scat_cfg, grid_size=grid).to(DEV).eval()
+    with torch.no_grad():
+        bd = scat(vfe({"points": fused, "batch_size": 1}))
+    want = po.front_end(fused.cpu(), po.VFEConfig(5, vox, rng, grid), layers_from_state_dict(sd), unique_dim0=False)
+    assert torch.equal(bd["voxel_coords"].cpu(), want["voxel_coords"])
+    assert_features_close(bd["pillar_features"].cpu().numpy(), want["pillar_features"].numpy(), "pillar_features")
+    assert torch.equal((bd["spatial_features"].cpu() != 0).any(1), (want["spatial_features"] != 0).any(1))
