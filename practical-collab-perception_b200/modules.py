@@ -11,6 +11,7 @@ through the segment reductions, which are outside this path).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
 
 import numpy as np
@@ -19,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib
 from .config import cfg_get
-from .frontend import FrontEnd, GridSpec, generic_scatter
+from .frontend import FrontEnd, GridSpec, _ptr, _stream, generic_scatter
 
 CTX_KEY = "pcp_b200_ctx"   # private hand-off from the VFE to the scatter inside batch_dict
 
@@ -319,8 +320,6 @@ class DynamicMeanVFE(VFETemplate):
 
     @torch.no_grad()
     def forward(self, batch_dict, **kwargs):
-        import ctypes as C
-        from .frontend import _ptr, _stream
         lib = _lib.load()
         points = batch_dict["points"]
         if not points.is_cuda:
