@@ -164,13 +164,15 @@ int pcp_num_frames(const int32_t* voxel_coords, int64_t num_pillars, int32_t* nu
  *   foreground   (total_fg, 13) fp32: pt5 | sweep | inst | cls3 | flow3; may be NULL (no propagation)
  *   fg_offsets   int32[num_agents + 1]
  *   se3          (num_agents, 12) fp64: rows 0..2 of target_se3_agent, row-major
+ *   max_boxes_per_agent, max_fg_per_agent: largest per-agent counts (the host built the offsets, so it knows them): grid sizes
  *   scale        flow multiplier: 2.0 * latency / sweep interval; 2.0 in the reference (:213); 0 = EXCHANGE_NOW
  *   rows_out     (total_boxes, out_stride) fp32; with_batch_col != 0 prepends the frame index column
  *                (collate_batch layout), i.e. 14 columns instead of 13
  *   box_idx_out  (total_fg) int32 per-agent box index of each foreground point, -1 = none.  May be NULL.
  */
 int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreground, const int32_t* fg_offsets,
-              const double* se3, int32_t num_agents, float scale, float max_sweep_idx,
+              const double* se3, int32_t num_agents, int32_t max_boxes_per_agent, int32_t max_fg_per_agent,
+              float scale, float max_sweep_idx,
               int32_t with_batch_col, float batch_idx, float* rows_out, int64_t out_stride,
               int32_t* box_idx_out, void* stream);
 

@@ -1,8 +1,9 @@
 // modar.cu - MoDAR point synthesis (reference: v2x_sim_dataset_ego.py:203-232, visualize_collab.py:118-142).
 //
 // The reference runs, per agent: a points-in-boxes CUDA op, boolean masks, torch.unique, a scatter-mean,
-// an indexed add, a D2H copy, a numpy fp64 SE(3), and np.concatenate - ~15 launches and a device sync per
-// agent.  Here all agents of a frame are one launch, one CTA per agent, nothing leaves the device:
+// an indexed add, a D2H copy, a numpy fp64 SE(3), and np.concatenate - ~15 launches and a device sync per agent.
+// Here all agents of a frame are two launches (membership over point chunks x agents, rows over box chunks x agents) and
+// nothing leaves the device:
 //   1. boxes -> shared memory (with cos/sin of -heading evaluated once per box instead of once per pair)
 //   2. box membership of every foreground point (first containing box wins, default -1)
 //   3. per-box mean flow, summed in ascending point order (the CPU reference's order) by one warp per box
@@ -27,20 +28,24 @@ __device__ __forceinline__ bool point_in_box(float x, float y, float z, const Bo
   return ((double)fabsf(lx) < (double)b.hx / 2.0 + margin) & ((double)fabsf(ly) < (double)b.hy / 2.0 + margin);
 }
 
+// 1 + 2. membership of every foreground point: grid (point chunks, agents); the agent's boxes sit in shared memory
 __global__ void __launch_bounds__(256)
-modar_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_off,
-             const float* __restrict__ fg, const int32_t* __restrict__ fg_off, const double* __restrict__ se3,
-             float scale, float max_sweep_idx, int with_batch_col, float batch_idx,
-             float* __restrict__ rows_out, int64_t out_stride, int32_t* __restrict__ box_idx_out) {
+modar_membership_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_off,
+                        const float* __restrict__ fg, const int32_t* __restrict__ fg_off,
+                        int32_t* __restrict__ box_idx_out) {
   __shared__ BoxS s_box[kMaxBoxes];
-  const int a = blockIdx.x;
+  const int a = blockIdx.y;
   const int b0 = box_off[a], M = box_off[a + 1] - b0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  const bool propagate = (fg != nullptr) && (scale != 0.f);
-  const int f0 = propagate ? fg_off[a] : 0, F = propagate ? fg_off[a + 1] - f0 : 0;
-  const double* T = se3 + 12 * a;
-  const double yaw_T = atan2(T[4], T[0]);  // rotation_matrix_to_yaw: arctan2(R10, R00), nuscenes_temporal_utils.py:28-29
-
+  const int f0 = fg_off[a], F = fg_off[a + 1] - f0;
+  const int tid = threadIdx.x;
+  if ((int64_t)blockIdx.x * blockDim.x >= F) return;
+  const int i = blockIdx.x * blockDim.x + tid;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (i < F) {
+    const float* p = fg + (int64_t)(f0 + i) * 13;
+    x = p[0]; y = p[1]; z = p[2];
+  }
+  int hit = -1;
   for (int mb = 0; mb < M; mb += kMaxBoxes) {       // boxes in panels of kMaxBoxes (one panel in practice)
     const int mc = min(kMaxBoxes, M - mb);
     __syncthreads();
@@ -54,37 +59,52 @@ modar_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_of
       s_box[k] = s;
     }
     __syncthreads();
-    // 2. membership: first containing box wins (roiaware_pool3d_kernel.cu:329-335)
-    for (int i = tid; i < F; i += blockDim.x) {
-      const float* p = fg + (int64_t)(f0 + i) * 13;
-      const float x = p[0], y = p[1], z = p[2];
-      int hit = (mb == 0) ? -1 : box_idx_out[f0 + i];
-      if (hit < 0) {
-        for (int k = 0; k < mc; ++k)
-          if (point_in_box(x, y, z, s_box[k])) { hit = mb + k; break; }
-      }
-      box_idx_out[f0 + i] = hit;
+    // first containing box wins (roiaware_pool3d_kernel.cu:329-335)
+    if (i < F && hit < 0) {
+      for (int k = 0; k < mc; ++k)
+        if (point_in_box(x, y, z, s_box[k])) { hit = mb + k; break; }
     }
   }
-  __syncthreads();
-  __threadfence_block();
+  if (i < F) box_idx_out[f0 + i] = hit;
+}
 
-  // 3 + 4. one warp per box
-  for (int k = warp; k < M; k += nwarp) {
-    const float* bx = boxes + (int64_t)(b0 + k) * 9;
-    float ox = 0.f, oy = 0.f, oz = 0.f;
-    if (F > 0) {
-      float sx = 0.f, sy = 0.f, sz = 0.f;
-      int cnt = 0;
-      for (int i0 = 0; i0 < F; i0 += 32) {
+// 3 + 4. one warp per box: grid (box chunks, agents).  The agent's membership array is staged in shared memory in panels, so
+// the scan over the foreground points never waits on global memory; only the flow of the box's own points is gathered.
+constexpr int kIdxPanel = 8192;
+
+__global__ void __launch_bounds__(256)
+modar_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_off,
+                  const float* __restrict__ fg, const int32_t* __restrict__ fg_off, const double* __restrict__ se3,
+                  float scale, float max_sweep_idx, int with_batch_col, float batch_idx,
+                  float* __restrict__ rows_out, int64_t out_stride, const int32_t* __restrict__ box_idx) {
+  __shared__ int32_t s_idx[kIdxPanel];
+  const int a = blockIdx.y;
+  const int b0 = box_off[a], M = box_off[a + 1] - b0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  if (blockIdx.x * nwarp >= M) return;
+  const bool propagate = (fg != nullptr) && (scale != 0.f);
+  const int f0 = propagate ? fg_off[a] : 0, F = propagate ? fg_off[a + 1] - f0 : 0;
+  const double* T = se3 + 12 * a;
+  const double yaw_T = atan2(T[4], T[0]);  // rotation_matrix_to_yaw: arctan2(R10, R00), nuscenes_temporal_utils.py:28-29
+  const int k = blockIdx.x * nwarp + warp;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  int cnt = 0;
+  for (int p0 = 0; p0 < F; p0 += kIdxPanel) {
+    const int pc = min(kIdxPanel, F - p0);
+    __syncthreads();
+    for (int i = tid; i < pc; i += blockDim.x) s_idx[i] = box_idx[f0 + p0 + i];
+    __syncthreads();
+    if (k < M) {
+      for (int i0 = 0; i0 < pc; i0 += 32) {
         const int i = i0 + lane;
-        const bool mine = (i < F) && (box_idx_out[f0 + i] == k);
+        const bool mine = (i < pc) && (s_idx[i] == k);
+        unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (m == 0) continue;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (mine) {
-          const float* p = fg + (int64_t)(f0 + i) * 13;
+          const float* p = fg + (int64_t)(f0 + p0 + i) * 13;
           fx = p[10]; fy = p[11]; fz = p[12];     // flow3 = last three columns (v2x_sim_dataset_ego.py:213)
         }
-        unsigned m = __ballot_sync(0xffffffffu, mine);
         cnt += __popc(m);
         while (m) {                                // sequential fp32 adds in ascending point order
           const int l = __ffs(m) - 1;
@@ -94,32 +114,35 @@ modar_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_of
           sz = __fadd_rn(sz, __shfl_sync(0xffffffffu, fz, l));
         }
       }
-      if (cnt > 0) {
-        const float c = (float)cnt;
-        ox = __fmul_rn(__fdiv_rn(sx, c), scale);   // scatter(reduce='mean') * 2.  (:213)
-        oy = __fmul_rn(__fdiv_rn(sy, c), scale);
-        oz = __fmul_rn(__fdiv_rn(sz, c), scale);
-      }
     }
-    if (lane == 0) {
-      // modar[unq_box_idx, :3] += boxes_offset (:215); boxes without points are untouched
-      const float x = (F > 0) ? __fadd_rn(bx[0], ox) : bx[0];
-      const float y = (F > 0) ? __fadd_rn(bx[1], oy) : bx[1];
-      const float z = (F > 0) ? __fadd_rn(bx[2], oz) : bx[2];
-      // apply_se3_ boxes branch (nuscenes_temporal_utils.py:66-70): fp32 row @ fp64 R^T + t, stored as fp32
-      const double xd = x, yd = y, zd = z;
-      const float tx = (float)(xd * T[0] + yd * T[1] + zd * T[2] + T[3]);
-      const float ty = (float)(xd * T[4] + yd * T[5] + zd * T[6] + T[7]);
-      const float tz = (float)(xd * T[8] + yd * T[9] + zd * T[10] + T[11]);
-      float yaw = (float)((double)bx[6] + yaw_T);
-      yaw = atan2f(sinf(yaw), cosf(yaw));
-      float* o = rows_out + (int64_t)(b0 + k) * out_stride;
-      if (with_batch_col) *o++ = batch_idx;
-      // [x, y, z, 0, 0, dx, dy, dz, heading, score, label, max_sweep_idx, -1]  (v2x_sim_dataset_ego.py:221-226)
-      o[0] = tx; o[1] = ty; o[2] = tz; o[3] = 0.f; o[4] = 0.f;
-      o[5] = bx[3]; o[6] = bx[4]; o[7] = bx[5]; o[8] = yaw; o[9] = bx[7]; o[10] = bx[8];
-      o[11] = max_sweep_idx; o[12] = -1.f;
-    }
+  }
+  if (k >= M) return;
+  const float* bx = boxes + (int64_t)(b0 + k) * 9;
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+  if (cnt > 0) {
+    const float c = (float)cnt;
+    ox = __fmul_rn(__fdiv_rn(sx, c), scale);   // scatter(reduce='mean') * 2.  (:213)
+    oy = __fmul_rn(__fdiv_rn(sy, c), scale);
+    oz = __fmul_rn(__fdiv_rn(sz, c), scale);
+  }
+  if (lane == 0) {
+    // modar[unq_box_idx, :3] += boxes_offset (:215); boxes without points are untouched
+    const float x = (F > 0) ? __fadd_rn(bx[0], ox) : bx[0];
+    const float y = (F > 0) ? __fadd_rn(bx[1], oy) : bx[1];
+    const float z = (F > 0) ? __fadd_rn(bx[2], oz) : bx[2];
+    // apply_se3_ boxes branch (nuscenes_temporal_utils.py:66-70): fp32 row @ fp64 R^T + t, stored as fp32
+    const double xd = x, yd = y, zd = z;
+    const float tx = (float)(xd * T[0] + yd * T[1] + zd * T[2] + T[3]);
+    const float ty = (float)(xd * T[4] + yd * T[5] + zd * T[6] + T[7]);
+    const float tz = (float)(xd * T[8] + yd * T[9] + zd * T[10] + T[11]);
+    float yaw = (float)((double)bx[6] + yaw_T);
+    yaw = atan2f(sinf(yaw), cosf(yaw));
+    float* o = rows_out + (int64_t)(b0 + k) * out_stride;
+    if (with_batch_col) *o++ = batch_idx;
+    // [x, y, z, 0, 0, dx, dy, dz, heading, score, label, max_sweep_idx, -1]  (v2x_sim_dataset_ego.py:221-226)
+    o[0] = tx; o[1] = ty; o[2] = tz; o[3] = 0.f; o[4] = 0.f;
+    o[5] = bx[3]; o[6] = bx[4]; o[7] = bx[5]; o[8] = yaw; o[9] = bx[7]; o[10] = bx[8];
+    o[11] = max_sweep_idx; o[12] = -1.f;
   }
 }
 
@@ -128,7 +151,8 @@ modar_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_of
 using namespace pcp;
 
 extern "C" int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreground,
-                         const int32_t* fg_offsets, const double* se3, int32_t num_agents, float scale,
+                         const int32_t* fg_offsets, const double* se3, int32_t num_agents, int32_t max_boxes_per_agent,
+                         int32_t max_fg_per_agent, float scale,
                          float max_sweep_idx, int32_t with_batch_col, float batch_idx, float* rows_out,
                          int64_t out_stride, int32_t* box_idx_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -138,8 +162,17 @@ extern "C" int pcp_modar(const float* boxes, const int32_t* box_offsets, const f
   PCP_REQUIRE(out_stride >= 13 + (with_batch_col ? 1 : 0), PCP_E_INVALID, "pcp_modar: out_stride too small");
   PCP_REQUIRE(!foreground || (fg_offsets && box_idx_out), PCP_E_INVALID,
               "pcp_modar: foreground given without fg_offsets / box_idx_out");
-  modar_kernel<<<num_agents, 256, 0, stream>>>(boxes, box_offsets, foreground, fg_offsets, se3, scale, max_sweep_idx,
-                                               with_batch_col, batch_idx, rows_out, out_stride, box_idx_out);
-  PCP_LAUNCH_CHECK("modar_kernel");
+  PCP_REQUIRE(max_boxes_per_agent >= 0 && max_fg_per_agent >= 0 && num_agents <= 65535, PCP_E_INVALID, "pcp_modar: bad sizes");
+  if (max_boxes_per_agent == 0) return 0;
+  const bool propagate = foreground != nullptr && scale != 0.f && max_fg_per_agent > 0;
+  if (propagate) {
+    const dim3 grid((unsigned)((max_fg_per_agent + 255) / 256), (unsigned)num_agents);
+    modar_membership_kernel<<<grid, 256, 0, stream>>>(boxes, box_offsets, foreground, fg_offsets, box_idx_out);
+    PCP_LAUNCH_CHECK("modar_membership_kernel");
+  }
+  const dim3 grid((unsigned)((max_boxes_per_agent + 7) / 8), (unsigned)num_agents);
+  modar_rows_kernel<<<grid, 256, 0, stream>>>(boxes, box_offsets, propagate ? foreground : nullptr, fg_offsets, se3, scale,
+                                              max_sweep_idx, with_batch_col, batch_idx, rows_out, out_stride, box_idx_out);
+  PCP_LAUNCH_CHECK("modar_rows_kernel");
   return 0;
 }

@@ -129,51 +129,95 @@ pfn_finish_long_kernel(const int32_t* __restrict__ hdr, const int4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// standalone segmented mean / max over the pillars (torch_scatter.scatter_mean / scatter_max)
-// one warp per pillar, lanes over channels; rows are visited in ascending row order
+// standalone segmented mean / max over the pillars (torch_scatter.scatter_mean / scatter_max).
+// L lanes per pillar (a power of two), 32 / L pillars per warp side by side, kVec consecutive channels per lane; the rows of a
+// pillar are visited in ascending row order, four row gathers in flight per lane (the mean is summed sequentially in
+// that order: the CPU scatter_mean's rounding, bit for bit; the loads run ahead of the dependent adds).
 // ------------------------------------------------------------------------------------------------
-template <int kMode>
+template <int kMode, int kVec>
 __global__ void __launch_bounds__(256)
-segment_reduce_kernel(const float* __restrict__ values, int64_t vstride, int channels,
+segment_reduce_kernel(const float* __restrict__ values, int64_t vstride, int channels, int L,
                       const int32_t* __restrict__ hdr, const int32_t* __restrict__ seg_off,
                       const int32_t* __restrict__ sorted_idx, float* __restrict__ out) {
+  constexpr int kAhead = 4;
   const int P = hdr[PCP_COUNT_PILLARS];
   const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < P; r += gridDim.x * wpb) {
-    const int off = seg_off[r], n = seg_off[r + 1] - off;
-    for (int c0 = 0; c0 < channels; c0 += 32) {
-      const int c = c0 + lane;
-      float acc = 0.f;
-      bool first = true;
-      for (int j0 = 0; j0 < n; j0 += 32) {
-        const int my = (j0 + lane < n) ? sorted_idx[off + j0 + lane] : 0;
-        const int cnt = min(32, n - j0);
-        for (int j = 0; j < cnt; ++j) {
-          const int idx = __shfl_sync(0xffffffffu, my, j);
-          if (c < channels) {
-            const float v = __ldg(values + (int64_t)idx * vstride + c);
-            if (kMode == 0) acc = __fadd_rn(acc, v);
-            else { acc = first ? v : fmaxf(acc, v); }
-            first = false;
+  const int G = 32 / L, sub = lane / L, ln = lane - sub * L;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t base = warp_global * G; base < P; base += nwarps * G) {
+    const int64_t r = base + sub;
+    const bool valid = r < P;
+    const int off = valid ? seg_off[r] : 0;
+    const int n = valid ? seg_off[r + 1] - off : 0;
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    for (int c0 = 0; c0 < channels; c0 += L * kVec) {
+      const int c = c0 + ln * kVec;
+      const bool cok = c < channels;
+      float acc[kVec];
+#pragma unroll
+      for (int t = 0; t < kVec; ++t) acc[t] = (kMode == 0) ? 0.f : -INFINITY;
+      for (int j0 = 0; j0 < nmax; j0 += kAhead) {
+        float v[kAhead][kVec];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+          const bool on = cok && (j0 + u < n);
+          if (on) {
+            const float* src = values + (int64_t)sorted_idx[off + j0 + u] * vstride + c;
+            if (kVec == 4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+              v[u][0] = q.x; v[u][1 % kVec] = q.y; v[u][2 % kVec] = q.z; v[u][3 % kVec] = q.w;
+            } else {
+              v[u][0] = __ldg(src);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+          if (cok && (j0 + u < n)) {
+#pragma unroll
+            for (int t = 0; t < kVec; ++t) acc[t] = (kMode == 0) ? __fadd_rn(acc[t], v[u][t]) : fmaxf(acc[t], v[u][t]);
           }
         }
       }
-      if (c < channels) {
-        if (kMode == 0) acc = __fdiv_rn(acc, (float)max(n, 1));
-        out[(int64_t)r * channels + c] = acc;
+      if (valid && cok) {
+        float* dst = out + r * channels + c;
+        if (kMode == 0) {
+          const float d = (float)max(n, 1);
+#pragma unroll
+          for (int t = 0; t < kVec; ++t) acc[t] = __fdiv_rn(acc[t], d);
+        }
+        if (kVec == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1 % kVec], acc[2 % kVec], acc[3 % kVec]);
+        else dst[0] = acc[0];
       }
     }
   }
 }
 
+static int pow2_at_least(int v) {
+  int p = 1;
+  while (p < v && p < 32) p <<= 1;
+  return p;
+}
+
 int launch_segment_reduce(const float* values, int64_t value_stride, int32_t channels, int32_t mode, const WsView& W,
                           float* out, cudaStream_t stream) {
   const unsigned blocks = 148 * 8;
-  if (mode == 0)
-    segment_reduce_kernel<0><<<blocks, 256, 0, stream>>>(values, value_stride, channels, W.hdr, W.seg_off, W.sorted_idx, out);
-  else
-    segment_reduce_kernel<1><<<blocks, 256, 0, stream>>>(values, value_stride, channels, W.hdr, W.seg_off, W.sorted_idx, out);
+  const bool vec4 = (channels % 4 == 0) && (value_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(values) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec4) {
+    const int L = pow2_at_least(channels / 4);
+    if (mode == 0)
+      segment_reduce_kernel<0, 4><<<blocks, 256, 0, stream>>>(values, value_stride, channels, L, W.hdr, W.seg_off, W.sorted_idx, out);
+    else
+      segment_reduce_kernel<1, 4><<<blocks, 256, 0, stream>>>(values, value_stride, channels, L, W.hdr, W.seg_off, W.sorted_idx, out);
+  } else {
+    const int L = pow2_at_least(channels);
+    if (mode == 0)
+      segment_reduce_kernel<0, 1><<<blocks, 256, 0, stream>>>(values, value_stride, channels, L, W.hdr, W.seg_off, W.sorted_idx, out);
+    else
+      segment_reduce_kernel<1, 1><<<blocks, 256, 0, stream>>>(values, value_stride, channels, L, W.hdr, W.seg_off, W.sorted_idx, out);
+  }
   PCP_LAUNCH_CHECK("segment_reduce_kernel");
   return 0;
 }

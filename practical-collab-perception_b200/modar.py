@@ -50,6 +50,37 @@ def _as_boxes9(det: Union[Dict[str, torch.Tensor], torch.Tensor], device) -> tor
     return t
 
 
+_staging = {}   # device -> [pinned uint8 buffer, event of the last H2D that read it]
+
+
+def _upload(dev, arrays):
+    """One asynchronous H2D copy for all the small host-side arrays of a call (poses, offsets): they are packed into a
+    pinned staging buffer (8-byte aligned pieces) and come back as typed views of one device buffer."""
+    sizes = [(a.nbytes + 7) // 8 * 8 for a in arrays]
+    total = max(sum(sizes), 8)
+    st = _staging.get(dev)
+    if st is None or st[0].numel() < total:
+        st = [torch.empty(max(total, 4096), dtype=torch.uint8).pin_memory(), None]
+        _staging[dev] = st
+    if st[1] is not None:
+        st[1].synchronize()                      # the previous call's copy has left the staging buffer
+    host = st[0].numpy()
+    o = 0
+    for a, sz in zip(arrays, sizes):
+        host[o:o + a.nbytes] = np.frombuffer(a.tobytes(), dtype=np.uint8)
+        o += sz
+    d = torch.empty(total, dtype=torch.uint8, device=dev)
+    d.copy_(st[0][:total], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    st[1] = ev
+    views, o = [], 0
+    for a, sz in zip(arrays, sizes):
+        views.append(d[o:o + a.nbytes].view(torch.from_numpy(a[:0].copy()).dtype).reshape(a.shape))
+        o += sz
+    return views
+
+
 def modar_exchange(detections, foreground, target_se3_agent, t_detect: float, t_query: float,
                    ego_points: torch.Tensor, max_sweep_idx: Optional[float] = None, batch_idx: float = 0.0,
                    sample_interval: float = SAMPLE_INTERVAL_S, return_box_idx: bool = False):
@@ -110,13 +141,13 @@ def modar_exchange(detections, foreground, target_se3_agent, t_detect: float, t_
             raise ValueError("target_se3_agent must be (4, 4)")
     boxes_all = torch.cat(boxes, dim=0).contiguous()
     fg_all = torch.cat(fgs, dim=0).contiguous()
-    meta = torch.from_numpy(np.concatenate([box_off, fg_off])).to(dev)            # one small H2D
-    se3_d = torch.from_numpy(se3).to(dev)
+    se3_d, meta = _upload(dev, [se3, np.concatenate([box_off, fg_off])])          # one small asynchronous H2D
     box_idx = torch.empty((max(fg_all.shape[0], 1),), dtype=torch.int32, device=dev)
     have_fg = fg_all.shape[0] > 0
     rows = out[n_ego:]
     rc = lib.pcp_modar(_ptr(boxes_all), C.c_void_p(meta.data_ptr()), _ptr(fg_all) if have_fg else None,
                        C.c_void_p(meta.data_ptr() + 4 * (n_agents + 1)), _ptr(se3_d), n_agents,
+                       int(max(b.shape[0] for b in boxes)), int(max(f.shape[0] for f in fgs)),
                        C.c_float(scale), C.c_float(max_sweep_idx), int(with_b), C.c_float(batch_idx),
                        _ptr(rows), ncol, _ptr(box_idx), _stream())
     _lib.check(rc, "pcp_modar")

@@ -67,8 +67,8 @@ def test_argument_validation_returns_codes_not_crashes(lib):
     assert lib.pcp_pfn_param_floats(C.byref(PcpPfnDesc(5, 1, 0, 1, 0, 64))) == 2 * 16 * 64 + 128
     rc = lib.pcp_pack_pfn_params(C.byref(d), *([None] * 12), C.c_float(1e-3), None, None)
     assert rc == -3 and b"num_layers" in lib.pcp_last_error_string()
-    assert lib.pcp_modar(None, None, None, None, None, 0, 2.0, 10.0, 0, 0.0, None, 13, None, None) == 0
-    assert lib.pcp_modar(None, None, None, None, None, 2, 2.0, 10.0, 0, 0.0, None, 13, None, None) == -1
+    assert lib.pcp_modar(None, None, None, None, None, 0, 0, 0, 2.0, 10.0, 0, 0.0, None, 13, None, None) == 0
+    assert lib.pcp_modar(None, None, None, None, None, 2, 1, 1, 2.0, 10.0, 0, 0.0, None, 13, None, None) == -1
     assert lib.pcp_segment_reduce(None, 4, 4, 7, 10, 1, 8, 8, None, 0, None, 10, None) == -1
 
 
