@@ -32,16 +32,17 @@ __global__ void pack_params_kernel(int c_in, int num_layers, const float* w0, co
   const int k0 = pfn_k0(c_in);
   const int n0 = num_layers == 2 ? kHidden : kCout;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  // layer 0 panels [k0/4][n0][4]; a single layer is the last layer: its rows carry the sign of its BN scale
+  // layer 0 panels [k0/4][n0][4]; a single layer is the last layer: its rows carry the sign of its BN scale.
+  // Two layers with a spare K column (k0 > c_in, pfn_fold0): the BN of layer 0 goes INTO the operand - rows scaled by
+  // alpha, beta in column c_in, which the producers feed with 1.0 - so the layer-0 epilogue is a bare ReLU.
+  const bool fold = pfn_fold0(c_in, num_layers);
   for (int i = tid; i < k0 * n0; i += nth) {
     const int kc = i / (n0 * 4), n = (i / 4) % n0, k = kc * 4 + (i & 3);
-    float sgn = 1.f;
-    if (num_layers == 1) {
-      float a, b;
-      fold_bn(g0, be0, mu0, var0, lb0, eps, n, a, b);
-      sgn = (a < 0.f) ? -1.f : 1.f;
-    }
-    const float w = (k < c_in) ? sgn * w0[n * c_in + k] : 0.f;
+    float a, b;
+    fold_bn(g0, be0, mu0, var0, lb0, eps, n, a, b);
+    float w;
+    if (fold) w = (k < c_in) ? __fmul_rn(a, w0[n * c_in + k]) : (k == c_in ? b : 0.f);
+    else w = (k < c_in) ? ((num_layers == 1 && a < 0.f) ? -1.f : 1.f) * w0[n * c_in + k] : 0.f;
     float h, l;
     umma::split_tf32_rn(w, h, l);
     out[P.w0h + i] = h; out[P.w0l + i] = l;
@@ -49,8 +50,8 @@ __global__ void pack_params_kernel(int c_in, int num_layers, const float* w0, co
   for (int c = tid; c < n0; c += nth) {
     float a, b;
     fold_bn(g0, be0, mu0, var0, lb0, eps, c, a, b);
-    out[P.a0 + c] = (num_layers == 1) ? fabsf(a) : a;
-    out[P.b0 + c] = b;
+    out[P.a0 + c] = fold ? 1.f : ((num_layers == 1) ? fabsf(a) : a);
+    out[P.b0 + c] = fold ? 0.f : b;
   }
   if (num_layers == 2) {
     // layer 1: columns 0..31 act on x (per point), columns 32..63 on x_max (per pillar); rows whose BN scale is

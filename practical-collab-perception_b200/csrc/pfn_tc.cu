@@ -161,6 +161,9 @@ pfn_slot_kernel(const TcArgs A) {
   constexpr int NF = (kLayers == 2 && kCfg == 1) ? 4 : 2;        // depth of the front half (A0 / D0 buffers)
   constexpr uint32_t kFS = 128 / NF;                             // columns per A0 / D0 buffer
   constexpr uint32_t kA0Lo = 64 / NF;                            // offset of the lo part inside an A0 buffer
+  // the fixed row layouts have c_in = 11 / 17: a spare K column exists, pcp_pack_pfn_params folded layer 0's BN
+  constexpr bool kFold0 = (kLayers == 2) && (kCfg != 0);
+  static_assert(!kFold0 || RowCfg<kCfg>::k0 > RowCfg<kCfg>::n_raw + 6, "no spare K column for the folded bias");
   const int k0 = kCfg ? RowCfg<kCfg>::k0 : A.k0;
   const int n_raw = kCfg ? RowCfg<kCfg>::n_raw : A.n_raw;
   const int raw_col0 = kCfg ? 1 : A.raw_col0;
@@ -435,6 +438,7 @@ pfn_slot_kernel(const TcArgs A) {
     uint32_t c0 = 0;                                       // this set's slots built so far
     int id = 0;                                            // iteration number of cursor D
     const int n_feat = n_raw + (with_dist ? 7 : 6);
+    const bool fold0 = pfn_fold0(n_feat, kLayers);         // column n_feat carries 1.0 for the folded layer-0 bias
     TRACE_DECL(p == 0)
     while (true) {
       const uint32_t ud = s_curs[id & 7];                  // written by cursor B 2 * DEPTH iterations (or the prologue) ago
@@ -506,7 +510,7 @@ pfn_slot_kernel(const TcArgs A) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int f = cc8 + t;
-            float val = 0.f;
+            float val = (fold0 && f == n_feat) ? 1.f : 0.f;
             if (valid) {
               if (f < n_raw) {
                 if (kCfg) val = rw[(1 + f) < NREG ? (1 + f) : (NREG - 1)];
@@ -576,13 +580,18 @@ pfn_slot_kernel(const TcArgs A) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float hi[8], lo[8];
-            const float4 al0 = ld4(pa + 8 * half), al1 = ld4(pa + 8 * half + 4);
-            const float4 be0 = ld4(pb + 8 * half), be1 = ld4(pb + 8 * half + 4);
-            const float a8[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
-            const float b8[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+            float a8[8], b8[8];
+            if (!kFold0) {
+              const float4 al0 = ld4(pa + 8 * half), al1 = ld4(pa + 8 * half + 4);
+              const float4 be0 = ld4(pb + 8 * half), be1 = ld4(pb + 8 * half + 4);
+              a8[0] = al0.x; a8[1] = al0.y; a8[2] = al0.z; a8[3] = al0.w; a8[4] = al1.x; a8[5] = al1.y; a8[6] = al1.z; a8[7] = al1.w;
+              b8[0] = be0.x; b8[1] = be0.y; b8[2] = be0.z; b8[3] = be0.w; b8[4] = be1.x; b8[5] = be1.y; b8[6] = be1.z; b8[7] = be1.w;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float xv = fmaxf(fmaf(__uint_as_float(rr[8 * half + i]), a8[i], b8[i]), 0.f);
+              // kFold0: BN already sits in the operand (scaled rows + bias column), the epilogue is a bare ReLU
+              const float xv = kFold0 ? fmaxf(__uint_as_float(rr[8 * half + i]), 0.f)
+                                      : fmaxf(fmaf(__uint_as_float(rr[8 * half + i]), a8[i], b8[i]), 0.f);
               max0[8 * half + i] = fmaxf(max0[8 * half + i], xv);
               split_tf32(xv, hi[i], lo[i]);
             }

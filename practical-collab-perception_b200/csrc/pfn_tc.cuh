@@ -9,6 +9,8 @@ constexpr int kCout = 64;     // NUM_FILTERS[-1]
 constexpr int kMaxCin = 24;   // input features, rounded up to a multiple of 8 (K of the first MMA)
 
 __host__ __device__ inline int pfn_k0(int c_in) { return (c_in + 7) / 8 * 8; }
+// layer-0 BN folded into the operand (scaled rows + a bias column fed with 1.0): two-layer PFN with a spare K column
+__host__ __device__ inline bool pfn_fold0(int c_in, int num_layers) { return num_layers == 2 && pfn_k0(c_in) > c_in; }
 
 // Packed parameter block (floats).  Operand panels are the K-major "interleaved" layout of umma.cuh:
 // [K/4][rows][4], TF32 hi / lo (round-to-nearest split).  Rows of the LAST layer are multiplied by the sign of its
@@ -17,7 +19,8 @@ __host__ __device__ inline int pfn_k0(int c_in) { return (c_in + 7) / 8 * 8; }
 //               w1ah | w1al [8][64][4]        layer 1, columns 0..31  (the per-point half:  x . W1[:, :32]^T)
 //               w1bh | w1bl [8][64][4]        layer 1, columns 32..63 (the per-pillar half: x_max . W1[:, 32:]^T)
 //               w1sh | w1sl [8][64][4]        W1[:, :32] + W1[:, 32:]: one-point pillars (x_max == x) need a single product
-//               a0[32] b0[32]                 folded BN of layer 0 (signed scale, shift)
+//               a0[32] b0[32]                 folded BN of layer 0 (signed scale, shift); (1, 0) when pfn_fold0(): then w0 holds
+//                                             alpha * W0 and column c_in holds beta (the producers feed it with 1.0)
 //               a1[64] b1[64]                 |scale|, shift of layer 1
 //               w1b_f32 [64][32]              sign-folded fp32 copy of W1[:, 32:] for the long-pillar finishing kernel
 //   one layer:  w0h | w0l  [k0/4][64][4] (sign-folded) | a0[64] (|scale|) b0[64]
