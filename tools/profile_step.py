@@ -10,6 +10,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pcp_b200  # noqa: E402
+from pcp_b200 import _lib  # noqa: E402
+if os.environ.get("PCP_LIB"):                     # tuning aid: time an alternative build of the library
+    _lib.LIB_PATH = os.path.abspath(os.environ["PCP_LIB"])
 from pcp_b200 import synthetic as syn  # noqa: E402
 from pcp_b200.frontend import FrontEnd, GridSpec  # noqa: E402
 
