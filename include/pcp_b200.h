@@ -255,6 +255,30 @@ int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols
                           float* rows_out, int64_t out_stride, int32_t* count_out, void* stream);
 
 /*
+ * Pairwise BEV IoU of rotated boxes [x, y, z, dx, dy, dz, heading]: iou3d_nms_utils.boxes_iou_bev,
+ * pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:227-265.  iou_out (num_a, num_b) fp32.
+ */
+int pcp_boxes_iou_bev(const float* boxes_a, int64_t num_a, const float* boxes_b, int64_t num_b, float* iou_out, void* stream);
+
+/*
+ * Class-agnostic rotated-box NMS, entirely on the device.  Replaces the late-fusion box merge
+ * pcdet/models/detectors/v2x_late_fusion.py:21-35 -> model_nms_utils.class_agnostic_nms
+ * (pcdet/models/model_utils/model_nms_utils.py:6-27) -> iou3d_nms_utils.nms_gpu (iou3d_nms_utils.py:84-99,
+ * iou3d_nms_kernel.cu:267-312, and the HOST scan of iou3d_nms.cpp:100-135 with its cudaMalloc + D2H copy).
+ *   boxes (num_boxes, box_stride >= 7) fp32, scores (num_boxes) fp32
+ *   apply_score_thresh / score_thresh: keep scores >= thresh (:9); pre_max_size: top-k before NMS (:15, <= 0: all);
+ *   iou_thresh: suppress when IoU_bev > thresh; post_max_size: at most this many survivors (:20, <= 0: all)
+ *   scratch  pcp_nms_scratch_bytes(num_boxes) bytes, 256-byte aligned
+ *   keep_out int64[num_boxes]: indices into `boxes` of the survivors, highest score first (ties: lower index first)
+ *   count_out device int32: number of survivors; -1 if more than 4096 boxes pass the score mask (unsupported)
+ */
+size_t pcp_nms_scratch_bytes(int64_t num_boxes);
+int pcp_nms_bev(const float* boxes, int64_t box_stride, const float* scores, int64_t num_boxes,
+                int32_t apply_score_thresh, float score_thresh, float iou_thresh, int32_t pre_max_size,
+                int32_t post_max_size, void* scratch, size_t scratch_bytes, int64_t* keep_out, int32_t* count_out,
+                void* stream);
+
+/*
  * Diagnostic: C[128 x n] = A[128 x k] . B[n x k]^T through exactly the tensor-core path pcp_pfn() uses
  * (shared-memory operand panels, tcgen05.mma kind::tf32 with the 3xTF32 split, TMEM accumulator,
  * tcgen05.ld).  k multiple of 8 up to 64, n = 32 or 64, all row-major fp32 device pointers.

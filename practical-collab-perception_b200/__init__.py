@@ -21,6 +21,9 @@ def __getattr__(name):
     if name in ("bev_scatter", "interpolate_points_feat_from_bev_img"):
         from . import hunter_toolbox
         return getattr(hunter_toolbox, name)
+    if name in ("class_agnostic_nms", "nms_gpu", "boxes_iou_bev"):
+        from . import nms
+        return getattr(nms, name)
     if name in ("fuse_agent_points",):
         from . import early_fusion
         return getattr(early_fusion, name)
