@@ -24,6 +24,9 @@ def __getattr__(name):
     if name in ("class_agnostic_nms", "nms_gpu", "boxes_iou_bev"):
         from . import nms
         return getattr(nms, name)
+    if name in ("pack_exchange", "unpack_exchange", "read_exchange", "write_exchange", "ExchangeMessage"):
+        from . import exchange
+        return getattr(exchange, name)
     if name in ("fuse_agent_points",):
         from . import early_fusion
         return getattr(early_fusion, name)

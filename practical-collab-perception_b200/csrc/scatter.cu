@@ -134,6 +134,46 @@ canvas_v8_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_
   }
 }
 
+// Persistent form of canvas_v8_kernel for steady-state pipelining: a fixed number of CTAs per SM walk the patches, so the
+// canvas of batch i leaves room on every SM for the voxelize kernels of batch i + 1 (tools/overlap_probe.py).
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
+canvas_v8p_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
+                  float* __restrict__ canvas, int tiles_x, int tiles_y, int frames) {
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int64_t nxy = (int64_t)nx * ny;
+  const int n_tiles = tiles_x * tiles_y * frames;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+    const int y = by * kTileY + wy;
+    const int x0 = bx * kTileX + lane * 4;
+    if (y >= ny || x0 >= nx) continue;
+    int r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = __ldg(rank_map + b * nxy + (int64_t)(x0 + i) * ny + y);
+    float* dst = canvas + ((int64_t)b * channels) * nxy + (int64_t)y * nx + x0;
+    const bool any = (r[0] >= 0) | (r[1] >= 0) | (r[2] >= 0) | (r[3] >= 0);
+    if (!__any_sync(0xffffffffu, any)) {
+#pragma unroll 8
+      for (int c = 0; c < channels; ++c) st_stream_f4(dst + (int64_t)c * nxy, 0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    for (int c = 0; c < channels; c += 8) {
+      float8 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r[i] >= 0) v[i] = ldg_f8(pf + (int64_t)r[i] * channels + c);
+        else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[i].v[q] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) st_stream_f4(dst + (int64_t)(c + q) * nxy, v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]);
+    }
+  }
+}
+
 // generic path: canvas-ordered rank map from arbitrary voxel_coords rows (frame, z, y, x)
 __global__ void __launch_bounds__(256)
 coords_to_map_kernel(const int32_t* __restrict__ coords, int64_t P, int frames, int nx, int ny,
@@ -184,7 +224,11 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
     const int th = kTileY * 32;
     const bool fast8 = (channels % 8 == 0) && (grid->nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(pillar_features) & 31) == 0) &&
                        ((reinterpret_cast<uintptr_t>(canvas_out) & 15) == 0);
-    if ((variant == 0 || variant == 7) && fast8) {
+    static const int persist = getenv("PCP_CANVAS_PERSIST") ? atoi(getenv("PCP_CANVAS_PERSIST")) : 0;   // CTAs per SM, 0 = off
+    if (persist > 0 && fast8) {
+      canvas_v8p_kernel<3><<<148 * persist, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out,
+                                                             (int)cg.x, (int)cg.y, (int)cg.z);
+    } else if ((variant == 0 || variant == 7) && fast8) {
       canvas_v8_kernel<3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
     } else if (variant == 8 && fast8) {
       canvas_v8_kernel<4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);

@@ -214,6 +214,99 @@ class FrontEnd:
         return out["counts"].cpu().numpy()
 
 
+class PipelinedFrontEnd:
+    """Steady-state throughput mode of the chain: batch i + 1 is voxelised while the canvas of batch i is written.
+
+    voxelize + PFN run on a high-priority stream, the canvas writer on a low-priority one, over ``depth`` independent
+    buffer sets (workspace, pillar buffers, canvas).  The voxelize kernels are bound by scattered L1/L2 transactions and
+    the canvas by HBM writes, so the block scheduler can interleave them; results are bit-identical to the serial
+    ``FrontEnd.forward_device`` (tests/test_gpu_parity.py).  No host synchronisation: ``submit`` returns the buffer set
+    with a ``done`` event the consumer waits on; a set is reused ``depth`` submits later, after its canvas has been
+    written AND the consumer has had the chance to read it (``release`` records the consumer's stream).
+    """
+
+    def __init__(self, grid: GridSpec, c_raw: int, max_frames: int, depth: int = 2, **kwargs):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.max_frames = int(max_frames)
+        self.stages = [FrontEnd(grid, c_raw, **kwargs) for _ in range(depth)]
+        self.sets = [{} for _ in range(depth)]
+        self.grid = grid
+        self._n = 0
+        self._streams = None
+
+    def pack_params(self, *args, **kwargs):
+        packed = self.stages[0].pack_params(*args, **kwargs)
+        for fe in self.stages[1:]:
+            fe.packed = packed
+        return packed
+
+    def _ensure_streams(self, device):
+        if self._streams is None or self._streams[0].device != device:
+            # lower number = higher priority; CUDA clamps to the device's range
+            self._streams = (torch.cuda.Stream(device=device, priority=-5), torch.cuda.Stream(device=device, priority=0))
+        return self._streams
+
+    def submit(self, points: torch.Tensor, record=None) -> Dict[str, torch.Tensor]:
+        """Enqueue one batch.  ``record``: optional 6 timing events (voxelize / PFN / canvas begin and end)."""
+        _require_cuda(points, "points")
+        dev = points.device
+        s_main, s_canvas = self._ensure_streams(dev)
+        k = self._n % len(self.sets)
+        self._n += 1
+        fe, out = self.stages[k], self.sets[k]
+        caller = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(caller)                                # the caller's writes to `points` are ordered before us
+        s_main.wait_event(ready)
+        if out.get("done") is not None:
+            s_main.wait_event(out["done"])                  # this set's previous canvas has been written
+        if out.get("released") is not None:
+            s_main.wait_event(out["released"])              # ... and read by its consumer
+        with torch.cuda.stream(s_main):
+            if record:
+                record[0].record(s_main)
+            fe.voxelize(points, self.max_frames, out, want_point_pillar=False)
+            if record:
+                record[1].record(s_main)
+                record[2].record(s_main)
+            fe.pfn(points, out)
+            if record:
+                record[3].record(s_main)
+            e_p = torch.cuda.Event()
+            e_p.record(s_main)
+            if out.get("spatial_features") is None:
+                g = self.grid
+                out["spatial_features"] = torch.empty((self.max_frames, fe.c_out, g.ny, g.nx), dtype=torch.float32, device=dev)
+        s_canvas.wait_event(e_p)
+        with torch.cuda.stream(s_canvas):
+            if record:
+                record[4].record(s_canvas)
+            fe.scatter_ws(out["pillar_features_buf"], self.max_frames, out["spatial_features"])
+            if record:
+                record[5].record(s_canvas)
+            done = torch.cuda.Event()
+            done.record(s_canvas)
+        out["done"] = done
+        out["released"] = None
+        out["points"] = points                              # keep the input alive until the set is reused
+        return out
+
+    @staticmethod
+    def release(out: Dict[str, torch.Tensor]) -> None:
+        """Call on the consumer's stream after enqueuing its reads of ``out``."""
+        e = torch.cuda.Event()
+        e.record(torch.cuda.current_stream())
+        out["released"] = e
+
+    def drain(self) -> None:
+        """Make the caller's current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream()
+        for out in self.sets:
+            if out.get("done") is not None:
+                cur.wait_event(out["done"])
+
+
 def generic_scatter(pillar_features: torch.Tensor, voxel_coords: torch.Tensor, nx: int, ny: int,
                     num_frames: Optional[int] = None) -> torch.Tensor:
     """PointPillarScatter for arbitrary (pillar_features, voxel_coords) (pointpillar_scatter.py:14-37)."""

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .exchange import ExchangeMessage
 from .frontend import _ptr, _stream
 
 SAMPLE_INTERVAL_S = 0.2   # V2X-Sim key frames are 5 Hz (README.md:45-46); flow = displacement to the newest sweep
@@ -36,7 +37,9 @@ def flow_scale(t_detect: float, t_query: float, sample_interval: float = SAMPLE_
 
 def _as_boxes9(det: Union[Dict[str, torch.Tensor], torch.Tensor], device) -> torch.Tensor:
     """detections dict {'pred_boxes' (M,7), 'pred_scores' (M,), 'pred_labels' (M,)} (the layout CenterHead
-    emits, center_head.py:409-427) or an (M, 9) tensor box7|score|label."""
+    emits, center_head.py:409-427), an (M, 9) tensor box7|score|label, or an unpacked exchange.ExchangeMessage."""
+    if isinstance(det, ExchangeMessage):
+        det = det.boxes
     if isinstance(det, dict):
         b = det["pred_boxes"].to(device=device, dtype=torch.float32)
         s = det["pred_scores"].to(device=device, dtype=torch.float32).reshape(-1, 1)
@@ -87,7 +90,8 @@ def modar_exchange(detections, foreground, target_se3_agent, t_detect: float, t_
     """One frame of lately fusion.
 
     detections / foreground / target_se3_agent: one agent, or equal-length lists for several agents
-        (detections: dict or (M,9) tensor; foreground: (F,13) tensor or None; target_se3_agent: (4,4) float64).
+        (detections: dict, (M,9) tensor or an unpacked exchange.ExchangeMessage - whose foreground records are used when
+        `foreground` is None; foreground: (F,13) tensor or None; target_se3_agent: (4,4) float64).
     t_detect, t_query: when the agents detected and when the ego asks (seconds).
     ego_points: (N,13) ego sweep stack ``[pt5, 0 x6, sweep_idx, inst_idx]`` (v2x_sim_dataset_ego.py:162-165) or
         (N,14) with the collate_batch frame-index column in front; must live on the GPU.
@@ -100,8 +104,8 @@ def modar_exchange(detections, foreground, target_se3_agent, t_detect: float, t_
     dev = ego_points.device
     if not isinstance(detections, (list, tuple)):
         detections, foreground, target_se3_agent = [detections], [foreground], [target_se3_agent]
-    if foreground is None:
-        foreground = [None] * len(detections)
+    if foreground is None:          # messages carry their own foreground records
+        foreground = [d.foreground if isinstance(d, ExchangeMessage) and d.foreground.shape[0] else None for d in detections]
     if not (len(detections) == len(foreground) == len(target_se3_agent)):
         raise ValueError("detections, foreground and target_se3_agent must have the same length")
     ncol = ego_points.shape[1]

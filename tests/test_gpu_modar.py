@@ -136,3 +136,32 @@ def test_box_membership_bit_exact_against_reference_cuda_kernel():
                               return_box_idx=True, max_sweep_idx=0.0)
         assert torch.equal(got, want), f"{int((got != want).sum())} of {fg.shape[0]} box indices differ"
         assert int((want >= 0).sum()) > 1000
+
+
+def test_exchange_messages_packed_on_the_gpu_feed_modar_and_nms(tmp_path):
+    """the fixed-record wire format replaces the torch-pickled .pth hand-off.  Messages are packed on the
+    GPU, unpacked as views, and give bit-identical MoDAR rows / NMS survivors to passing the tensors directly."""
+    from pcp_b200 import synthetic as syn
+    import pcp_b200
+    ego14, agents = syn.modar_scene(2, 5, n_agents=3, n_ego_points=512)
+    ego13 = ego14[:, 1:].contiguous()
+    want = run_exchange(ego13, agents)
+    msgs = []
+    for i, a in enumerate(agents):
+        buf = pcp_b200.pack_exchange(a["modar"].to(DEV), a["foreground"].to(DEV), agent_id=i, timestamp=7.0)
+        assert buf.is_cuda
+        if i == 0:                                           # one of them through a file, as the offline database does
+            pcp_b200.write_exchange(tmp_path / "m.bin", buf)
+            msgs.append(pcp_b200.read_exchange(tmp_path / "m.bin", device=DEV))
+        else:
+            msgs.append(pcp_b200.unpack_exchange(buf))
+    assert [m.agent_id for m in msgs] == [0, 1, 2] and all(m.boxes.is_cuda for m in msgs)
+    got = pcp_b200.modar_exchange(msgs, None, [a["target_se3_agent"] for a in agents], msgs[0].timestamp, 7.2, ego13.to(DEV))
+    assert torch.equal(got, want)
+    # late fusion: NMS over every agent's records (v2x_late_fusion.py:21-35)
+    allb = torch.cat([m.boxes for m in msgs])
+    direct = torch.cat([a["modar"] for a in agents]).to(DEV)
+    cfg = pcp_b200.CfgDict(NMS_TYPE="nms_gpu", NMS_THRESH=0.2, NMS_PRE_MAXSIZE=1000, NMS_POST_MAXSIZE=100)
+    s1, sc1 = pcp_b200.class_agnostic_nms(allb[:, 7], allb[:, :7], cfg, score_thresh=0.3)
+    s2, sc2 = pcp_b200.class_agnostic_nms(direct[:, 7], direct[:, :7], cfg, score_thresh=0.3)
+    assert torch.equal(s1, s2) and torch.equal(sc1, sc2) and s1.numel() > 0

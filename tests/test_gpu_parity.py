@@ -314,3 +314,40 @@ def test_full_size_properties(n_frames, n_points, voxel, uniform):
     assert bool(torch.isfinite(pf).all()) and float(pf.min()) >= 0.0
     bd2 = run_modules(vfe, scat, pts, n_frames)
     assert torch.equal(bd2["pillar_features"], pf)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_pipelined_front_end_is_bit_identical_to_the_serial_one(depth):
+    """Steady-state mode (canvas of batch i under the voxelize kernels of batch i + 1, separate streams and buffer sets):
+    every batch of a stream of different-sized batches equals the serial chain bit for bit."""
+    from pcp_b200.frontend import FrontEnd, GridSpec, PipelinedFrontEnd
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    gs = GridSpec(vox, rng, grid)
+    bn = lambda i: [sd[f"pfn_layers.{i}.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")]
+    w = lambda i: sd[f"pfn_layers.{i}.linear.weight"].to(DEV)
+    B = 3
+    batches = [syn.batch_of_frames(B, n, 40 + j).to(DEV) for j, n in enumerate([60000, 1000, 90000, 250, 40000, 70000, 5])]
+    serial = FrontEnd(gs, 5)
+    serial.pack_params(w(0), bn(0), w(1), bn(1))
+    want = []
+    for pts in batches:
+        o = serial.forward_device(pts, B, {}, None)
+        torch.cuda.synchronize()
+        p = int(serial.read_counts(o)[0])
+        want.append((p, o["voxel_coords_buf"][:p].clone(), o["pillar_features_buf"][:p].clone(), o["spatial_features"].clone()))
+    pipe = PipelinedFrontEnd(gs, 5, B, depth=depth)
+    pipe.pack_params(w(0), bn(0), w(1), bn(1))
+    for rep in range(2):
+        got = []
+        for pts in batches:
+            o = pipe.submit(pts)
+            torch.cuda.current_stream().wait_event(o["done"])
+            # the consumer copies the results out on its own stream, then releases the buffer set
+            got.append((o["counts"].clone(), o["voxel_coords_buf"].clone(), o["pillar_features_buf"].clone(),
+                        o["spatial_features"].clone()))
+            pipe.release(o)
+        pipe.drain()
+        torch.cuda.synchronize()
+        for (p, vc, pf, sf), (cnt, gvc, gpf, gsf) in zip(want, got):
+            assert int(cnt[0]) == p
+            assert torch.equal(gvc[:p], vc) and torch.equal(gpf[:p], pf) and torch.equal(gsf, sf)
