@@ -107,7 +107,7 @@ __host__ __device__ inline void unpack_entry(unsigned long long e, int& r, int& 
 }
 
 struct WsLayout {
-  size_t hdr, tile_info, cell, cell_rank, key, within, seg_off, sorted_idx, sxyz, lists, mean, long_table, big_list, long_mean, long_acc, total;
+  size_t hdr, tile_info, cell, cell_rank, key, within, seg_off, sorted_idx, lists, mean, long_table, big_list, long_mean, long_acc, total;
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
   int64_t cells, cap, scan_tiles, seg_cap, long_cap;
   ListOffsets lo;
@@ -132,7 +132,6 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   L.within = o;      o = align_up(o + sizeof(int32_t) * (size_t)(n + 1), 256);
   L.seg_off = o;     o = align_up(o + sizeof(int32_t) * (size_t)(L.cap + 2), 256);
   L.sorted_idx = o;  o = align_up(o + sizeof(int32_t) * (size_t)(n + 1), 256);
-  L.sxyz = o;        o = align_up(o + 16 * (size_t)(n + 1), 256);   // (x, y, z, row number) grouped by pillar, arrival order
   L.lists = o;
   int64_t lo = 0;
   for (int k = 0; k < kNumClasses; ++k) {
@@ -162,7 +161,6 @@ struct WsView {
   int32_t* within;
   int32_t* seg_off;
   int32_t* sorted_idx;
-  float4* sxyz;
   unsigned long long* lists;
   float4* mean;
   int4* long_table;
@@ -182,7 +180,6 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.within = reinterpret_cast<int32_t*>(p + L.within);
   v.seg_off = reinterpret_cast<int32_t*>(p + L.seg_off);
   v.sorted_idx = reinterpret_cast<int32_t*>(p + L.sorted_idx);
-  v.sxyz = reinterpret_cast<float4*>(p + L.sxyz);
   v.lists = reinterpret_cast<unsigned long long*>(p + L.lists);
   v.mean = reinterpret_cast<float4*>(p + L.mean);
   v.long_table = reinterpret_cast<int4*>(p + L.long_table);

@@ -330,15 +330,11 @@ scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, i
 // ------------------------------------------------------------------------------------------------
 // 3. counting-sort scatter + point -> pillar map
 // ------------------------------------------------------------------------------------------------
-// kXyz: the rows' (x, y, z) travel with the row number - sxyz[sorted position] = (x, y, z, row) - so that pillar_prep_kernel
-// reads every pillar's coordinates as one contiguous run instead of gathering 32-byte rows at random a second time.
-template <bool kXyz, bool kVec4>
 __global__ void __launch_bounds__(256)
 place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within,
              const int32_t* __restrict__ cell, const int32_t* __restrict__ cell_rank, int64_t n,
              int32_t* __restrict__ sorted_idx, int32_t* __restrict__ point_pillar,
-             const int32_t* __restrict__ hdr, int32_t* __restrict__ counts_out,
-             const float* __restrict__ points, int64_t stride, float4* __restrict__ sxyz) {
+             const int32_t* __restrict__ hdr, int32_t* __restrict__ counts_out) {
   const int64_t base = (int64_t)blockIdx.x * (256 * kPtsPerThread) + threadIdx.x;
   if (base == 0 && counts_out) {
 #pragma unroll
@@ -354,30 +350,10 @@ place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within
   // one random 4-byte read per point: the cell's first sorted position (the scan left it in the histogram array)
 #pragma unroll
   for (int u = 0; u < kPtsPerThread; ++u) o[u] = (k[u] >= 0) ? __ldg(cell + k[u]) : -1;
-  float4 t[kPtsPerThread];
-  if (kXyz) {
-#pragma unroll
-    for (int u = 0; u < kPtsPerThread; ++u) {
-      const int64_t i = base + u * 256;
-      t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k[u] >= 0) {
-        const float* row = points + i * stride;
-        if (kVec4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(row));
-          t[u] = make_float4(v.y, v.z, v.w, __int_as_float((int32_t)i));
-        } else {
-          t[u] = make_float4(__ldg(row + 1), __ldg(row + 2), __ldg(row + 3), __int_as_float((int32_t)i));
-        }
-      }
-    }
-  }
 #pragma unroll
   for (int u = 0; u < kPtsPerThread; ++u) {
     const int64_t i = base + u * 256;
-    if (k[u] >= 0) {
-      if (kXyz) sxyz[o[u] + w[u]] = t[u];
-      else sorted_idx[o[u] + w[u]] = (int32_t)i;
-    }
+    if (k[u] >= 0) sorted_idx[o[u] + w[u]] = (int32_t)i;
     if (point_pillar && i < n) point_pillar[i] = (k[u] >= 0) ? __ldg(cell_rank + k[u]) : -1;
   }
 }
@@ -421,65 +397,28 @@ __device__ __forceinline__ float pack_cell(float x, float y, const pcp_grid& g) 
 
 // one pillar of at most NMAX rows (one length class) per thread: order the row numbers (a sum of two values does not
 // depend on the order, so classes 0 and 1 are left as they are), gather xyz, sum in ascending row order, divide
-// swap (key, tag) pairs so that the keys end up ascending
-__device__ __forceinline__ void cswap2(int32_t& ka, int32_t& kb, int32_t& ta, int32_t& tb) {
-  const bool sw = kb < ka;
-  const int32_t k0 = sw ? kb : ka, k1 = sw ? ka : kb, t0 = sw ? tb : ta, t1 = sw ? ta : tb;
-  ka = k0; kb = k1; ta = t0; tb = t1;
-}
-
-// kSx: the pillar's (x, y, z, row) records lie contiguously in sxyz[off, off + n) (arrival order, written by place_kernel):
-// one coalescable run instead of n random 32-byte row gathers; the row numbers are sorted with their positions as tags and
-// the records are re-read (L1 hits) in ascending row order for the sequential sum.
-template <int NMAX, bool kVec4, bool kSx>
+template <int NMAX, bool kVec4>
 __device__ __forceinline__ void prep_short_one(const float* __restrict__ points, int64_t stride, const pcp_grid& g,
                                                unsigned long long entry, int32_t* __restrict__ sorted_idx,
-                                               float4* __restrict__ mean, const float4* __restrict__ sxyz) {
+                                               float4* __restrict__ mean) {
   int r, off, n;
   unpack_entry(entry, r, off, n);
   int32_t v[NMAX];
-  float x[NMAX], y[NMAX], z[NMAX];
-  if (kSx) {
-    int32_t tag[NMAX];
 #pragma unroll
-    for (int j = 0; j < NMAX; ++j) {
-      v[j] = 0x7fffffff; tag[j] = j; x[j] = 0.f; y[j] = 0.f; z[j] = 0.f;
-      if (j < n) {
-        const float4 t = __ldg(sxyz + off + j);
-        v[j] = __float_as_int(t.w); x[j] = t.x; y[j] = t.y; z[j] = t.z;
-      }
-    }
-    if (NMAX > 2) {
+  for (int j = 0; j < NMAX; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
+  if (NMAX > 2) {
 #pragma unroll
-      for (int i = 1; i < NMAX; ++i)
+    for (int i = 1; i < NMAX; ++i)
 #pragma unroll
-        for (int j = i; j > 0; --j) cswap2(v[j - 1], v[j], tag[j - 1], tag[j]);
-#pragma unroll
-      for (int j = 0; j < NMAX; ++j)
-        if (j < n) {
-          const float4 t = __ldg(sxyz + off + tag[j]);
-          x[j] = t.x; y[j] = t.y; z[j] = t.z;
-        }
-    }
+      for (int j = i; j > 0; --j) cswap(v[j - 1], v[j]);
 #pragma unroll
     for (int j = 0; j < NMAX; ++j)
       if (j < n) sorted_idx[off + j] = v[j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < NMAX; ++j) v[j] = (j < n) ? sorted_idx[off + j] : 0x7fffffff;
-    if (NMAX > 2) {
-#pragma unroll
-      for (int i = 1; i < NMAX; ++i)
-#pragma unroll
-        for (int j = i; j > 0; --j) cswap(v[j - 1], v[j]);
-#pragma unroll
-      for (int j = 0; j < NMAX; ++j)
-        if (j < n) sorted_idx[off + j] = v[j];
-    }
-#pragma unroll
-    for (int j = 0; j < NMAX; ++j)
-      if (j < n) load_xyz<kVec4>(points, stride, v[j], x[j], y[j], z[j]);
   }
+  float x[NMAX], y[NMAX], z[NMAX];
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j)
+    if (j < n) load_xyz<kVec4>(points, stride, v[j], x[j], y[j], z[j]);
   float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
   for (int j = 0; j < NMAX; ++j)
@@ -491,12 +430,11 @@ __device__ __forceinline__ void prep_short_one(const float* __restrict__ points,
 // W lanes per pillar (two length classes of at most W rows, walked back to back), items [w_begin, w_end) of the
 // concatenated lists: rank by counting against the warp's shared-memory copy, lanes 0, 1, 2 of the group run the
 // sequential sums of x, y, z.  warp_smem: 4 x 32 words of this warp.
-template <int W, bool kVec4, bool kSx>
+template <int W, bool kVec4>
 __device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64_t stride, const pcp_grid& g,
                                          const unsigned long long* __restrict__ list_a, int count_a,
                                          const unsigned long long* __restrict__ list_b, int count_b, int w_begin, int w_end,
-                                         int32_t* __restrict__ sorted_idx, float4* __restrict__ mean, int32_t* warp_smem,
-                                         const float4* __restrict__ sxyz) {
+                                         int32_t* __restrict__ sorted_idx, float4* __restrict__ mean, int32_t* warp_smem) {
   constexpr int kPer = 32 / W;                          // pillars per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / W, ln = lane & (W - 1);
   const int total = min(count_a + count_b, w_end);
@@ -506,16 +444,7 @@ __device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64
     const int w = w0 + sub;
     int r = 0, off = 0, n = 0;
     if (w < total) unpack_entry(__ldg(w < count_a ? list_a + w : list_b + (w - count_a)), r, off, n);
-    int32_t v = 0x7fffffff;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (kSx) {
-      if (ln < n) {
-        const float4 t = __ldg(sxyz + off + ln);                     // the pillar's records: one contiguous run
-        v = __float_as_int(t.w); x = t.x; y = t.y; z = t.z;
-      }
-    } else if (ln < n) {
-      v = sorted_idx[off + ln];
-    }
+    const int32_t v = (ln < n) ? sorted_idx[off + ln] : 0x7fffffff;
     sv[ln] = v;
     __syncwarp();
     int rank = 0;
@@ -524,9 +453,10 @@ __device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64
       const int4 t = *reinterpret_cast<const int4*>(sv + i);       // padding lanes hold INT_MAX: never smaller
       rank += (t.x < v) + (t.y < v) + (t.z < v) + (t.w < v);
     }
+    float x = 0.f, y = 0.f, z = 0.f;
     if (ln < n) {
       sorted_idx[off + rank] = v;
-      if (!kSx) load_xyz<kVec4>(points, stride, v, x, y, z);
+      load_xyz<kVec4>(points, stride, v, x, y, z);
       sx[rank] = x; sx[32 + rank] = y; sx[64 + rank] = z;
     }
     __syncwarp();
@@ -557,15 +487,12 @@ struct PrepSmem {
   };
 };
 
-template <bool kVec4, bool kSx>
+template <bool kVec4>
 __global__ void __launch_bounds__(kPrepThreads, 4)
 pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __restrict__ hdr,
                    unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
                    const int32_t* __restrict__ big_list, int32_t* __restrict__ sorted_idx, float4* __restrict__ mean,
-                   float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, const pcp_grid g, int phase_mask,
-                   const float4* __restrict__ sxyz) {
-  // row number at arrival position q of the grouped order (kSx: place_kernel left it next to the coordinates)
-  auto row_at = [&](int q) -> int32_t { return kSx ? __float_as_int(__ldg(&sxyz[q].w)) : sorted_idx[q]; };
+                   float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, const pcp_grid g, int phase_mask) {
   __shared__ __align__(16) PrepSmem sm;
   __shared__ float s_red[3][8];
   __shared__ int s_chunk;
@@ -595,7 +522,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       if (n <= kCountSortMax) {
         int32_t* s2 = sm.cta.scratch;
         const int n4 = (n + 3) & ~3;
-        for (int i = tid; i < n4; i += kPrepThreads) s[i] = (i < n) ? row_at(off + i) : 0x7fffffff;
+        for (int i = tid; i < n4; i += kPrepThreads) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
         __syncthreads();
         for (int i = tid; i < n; i += kPrepThreads) {
           const int32_t v = s[i];
@@ -612,7 +539,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       } else {
         int m = 2048;
         while (m < n) m <<= 1;
-        for (int i = tid; i < m; i += kPrepThreads) s[i] = (i < n) ? row_at(off + i) : 0x7fffffff;
+        for (int i = tid; i < m; i += kPrepThreads) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
         __syncthreads();
         for (int k = 2; k <= m; k <<= 1) {
           for (int j = k >> 1; j > 0; j >>= 1) {
@@ -659,9 +586,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
       for (int i = tid; i < n; i += kPrepThreads) {
         float x, y, z;
-        const int32_t idx = row_at(off + i);
-        if (kSx) sorted_idx[off + i] = idx;
-        load_xyz<kVec4>(points, stride, idx, x, y, z);
+        load_xyz<kVec4>(points, stride, sorted_idx[off + i], x, y, z);
         a0 += x; a1 += y; a2 += z;
       }
 #pragma unroll
@@ -679,7 +604,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
       if (tid == 0) {
         float x, y, z;
-        load_xyz<kVec4>(points, stride, row_at(off), x, y, z);
+        load_xyz<kVec4>(points, stride, sorted_idx[off], x, y, z);
         s_red[0][1] = pack_cell(x, y, g);
       }
     }
@@ -706,19 +631,10 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
     int32_t* s1 = sm.warp_words[warp][1];
     const int n4 = (n + 3) & ~3;
     int32_t v[kWarpLongMax / 32];
-    float x[kWarpLongMax / 32], y[kWarpLongMax / 32], z[kWarpLongMax / 32];
 #pragma unroll
     for (int k = 0; k < kWarpLongMax / 32; ++k) {
       const int i = k * 32 + lane;
-      v[k] = 0x7fffffff;
-      if (i < n) {
-        if (kSx) {
-          const float4 t = __ldg(sxyz + off + i);
-          v[k] = __float_as_int(t.w); x[k] = t.x; y[k] = t.y; z[k] = t.z;
-        } else {
-          v[k] = sorted_idx[off + i];
-        }
-      }
+      v[k] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
       if (i < n4) s0[i] = v[k];
     }
     __syncwarp();
@@ -731,40 +647,28 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       for (int k = 0; k < kWarpLongMax / 32; ++k)
         rank[k] += (t.x < v[k]) + (t.y < v[k]) + (t.z < v[k]) + (t.w < v[k]);
     }
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k)
+      if (k * 32 + lane < n) s1[rank[k]] = v[k];
+    __syncwarp();
     float* fx = reinterpret_cast<float*>(sm.warp_words[warp][0]);
     float* fy = reinterpret_cast<float*>(sm.warp_words[warp][2]);
+    float x[kWarpLongMax / 32], y[kWarpLongMax / 32], z[kWarpLongMax / 32];
+#pragma unroll
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      if (i < n) {
+        const int32_t idx = s1[i];
+        sorted_idx[off + i] = idx;
+        load_xyz<kVec4>(points, stride, idx, x[k], y[k], z[k]);
+      }
+    }
+    __syncwarp();                       // every lane has read its sorted row numbers: s1 can be reused for z
     float* fz = reinterpret_cast<float*>(sm.warp_words[warp][1]);
-    float x0 = 0.f, y0 = 0.f;           // coordinates of the pillar's first row (any row gives the same cell)
-    if (kSx) {
-      __syncwarp();                     // every lane has finished reading the row numbers in s0
 #pragma unroll
-      for (int k = 0; k < kWarpLongMax / 32; ++k)
-        if (k * 32 + lane < n) {
-          sorted_idx[off + rank[k]] = v[k];
-          fx[rank[k]] = x[k]; fy[rank[k]] = y[k]; fz[rank[k]] = z[k];
-        }
-      x0 = x[0]; y0 = y[0];
-    } else {
-#pragma unroll
-      for (int k = 0; k < kWarpLongMax / 32; ++k)
-        if (k * 32 + lane < n) s1[rank[k]] = v[k];
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < kWarpLongMax / 32; ++k) {
-        const int i = k * 32 + lane;
-        if (i < n) {
-          const int32_t idx = s1[i];
-          sorted_idx[off + i] = idx;
-          load_xyz<kVec4>(points, stride, idx, x[k], y[k], z[k]);
-        }
-      }
-      __syncwarp();                       // every lane has read its sorted row numbers: s1 can be reused for z
-#pragma unroll
-      for (int k = 0; k < kWarpLongMax / 32; ++k) {
-        const int i = k * 32 + lane;
-        if (i < n) { fx[i] = x[k]; fy[i] = y[k]; fz[i] = z[k]; }
-      }
-      x0 = x[0]; y0 = y[0];
+    for (int k = 0; k < kWarpLongMax / 32; ++k) {
+      const int i = k * 32 + lane;
+      if (i < n) { fx[i] = x[k]; fy[i] = y[k]; fz[i] = z[k]; }
     }
     __syncwarp();
     float acc = 0.f;
@@ -775,7 +679,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
     }
     const float my = __shfl_sync(0xffffffffu, acc, 1), mz = __shfl_sync(0xffffffffu, acc, 2);
     if (lane == 0) {
-      const float cw = pack_cell(x0, y0, g);
+      const float cw = pack_cell(x[0], y[0], g);
       long_mean[li] = make_float4(acc, my, mz, cw);
       mean[r] = make_float4(acc, my, mz, cw);
     }
@@ -789,15 +693,15 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       const int ca = hdr[kHdrListCount + 6], cb = hdr[kHdrListCount + 7];
       constexpr int kChunk = kPrepWarps * 2 * 4;          // 4 rounds of the CTA
       for (int w0 = grab(1, kChunk); w0 < ca + cb; w0 = grab(1, kChunk))
-        prep_mid<16, kVec4, kSx>(points, stride, g, lists + lo.off[6], ca, lists + lo.off[7], cb, w0, w0 + kChunk, sorted_idx, mean,
-                                 &sm.warp_words[warp][0][0], sxyz);
+        prep_mid<16, kVec4>(points, stride, g, lists + lo.off[6], ca, lists + lo.off[7], cb, w0, w0 + kChunk, sorted_idx, mean,
+                            &sm.warp_words[warp][0][0]);
     }
     {
       const int ca = hdr[kHdrListCount + 8], cb = hdr[kHdrListCount + 9];
       constexpr int kChunk = kPrepWarps * 4;
       for (int w0 = grab(2, kChunk); w0 < ca + cb; w0 = grab(2, kChunk))
-        prep_mid<32, kVec4, kSx>(points, stride, g, lists + lo.off[8], ca, lists + lo.off[9], cb, w0, w0 + kChunk, sorted_idx, mean,
-                                 &sm.warp_words[warp][0][0], sxyz);
+        prep_mid<32, kVec4>(points, stride, g, lists + lo.off[8], ca, lists + lo.off[9], cb, w0, w0 + kChunk, sorted_idx, mean,
+                            &sm.warp_words[warp][0][0]);
     }
   }
 
@@ -813,12 +717,12 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       for (int u = 0; u < 2; ++u) {
         const int w = w0 + u * kPrepThreads + tid;
         if (w >= pre[6]) continue;
-        if (w < pre[1]) prep_short_one<1, kVec4, kSx>(points, stride, g, __ldg(lists + lo.off[0] + w), sorted_idx, mean, sxyz);
-        else if (w < pre[2]) prep_short_one<2, kVec4, kSx>(points, stride, g, __ldg(lists + lo.off[1] + (w - pre[1])), sorted_idx, mean, sxyz);
-        else if (w < pre[3]) prep_short_one<3, kVec4, kSx>(points, stride, g, __ldg(lists + lo.off[2] + (w - pre[2])), sorted_idx, mean, sxyz);
-        else if (w < pre[4]) prep_short_one<4, kVec4, kSx>(points, stride, g, __ldg(lists + lo.off[3] + (w - pre[3])), sorted_idx, mean, sxyz);
-        else if (w < pre[5]) prep_short_one<6, kVec4, kSx>(points, stride, g, __ldg(lists + lo.off[4] + (w - pre[4])), sorted_idx, mean, sxyz);
-        else prep_short_one<8, kVec4, kSx>(points, stride, g, __ldg(lists + lo.off[5] + (w - pre[5])), sorted_idx, mean, sxyz);
+        if (w < pre[1]) prep_short_one<1, kVec4>(points, stride, g, __ldg(lists + lo.off[0] + w), sorted_idx, mean);
+        else if (w < pre[2]) prep_short_one<2, kVec4>(points, stride, g, __ldg(lists + lo.off[1] + (w - pre[1])), sorted_idx, mean);
+        else if (w < pre[3]) prep_short_one<3, kVec4>(points, stride, g, __ldg(lists + lo.off[2] + (w - pre[2])), sorted_idx, mean);
+        else if (w < pre[4]) prep_short_one<4, kVec4>(points, stride, g, __ldg(lists + lo.off[3] + (w - pre[3])), sorted_idx, mean);
+        else if (w < pre[5]) prep_short_one<6, kVec4>(points, stride, g, __ldg(lists + lo.off[4] + (w - pre[4])), sorted_idx, mean);
+        else prep_short_one<8, kVec4>(points, stride, g, __ldg(lists + lo.off[5] + (w - pre[5])), sorted_idx, mean);
       }
     }
   }
@@ -842,13 +746,8 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
   PCP_LAUNCH_CHECK("scan_cells_kernel");
   {
     const unsigned blocks = (unsigned)((n + 256 * kPtsPerThread - 1) / (256 * kPtsPerThread));
-    const bool v4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
-#define PCP_PLACE(XYZ, V4) place_kernel<XYZ, V4><<<blocks ? blocks : 1, 256, 0, stream>>>( \
-        W.key, W.within, W.cell, W.cell_rank, n, W.sorted_idx, point_pillar_out, W.hdr, counts_out, points, stride, W.sxyz)
-    if (points == nullptr) PCP_PLACE(false, false);
-    else if (v4) PCP_PLACE(true, true);
-    else PCP_PLACE(true, false);
-#undef PCP_PLACE
+    place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.cell_rank, n, W.sorted_idx,
+                                                          point_pillar_out, W.hdr, counts_out);
     PCP_LAUNCH_CHECK("place_kernel");
   }
   if (n > 0) {
@@ -859,12 +758,12 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
     static const bool split = getenv("PCP_PREP_SPLIT") != nullptr;
     for (int ph = 0; ph < (split ? 4 : 1); ++ph) {
       const int mask = split ? (1 << ph) : 15;
-#define PCP_PREP(V4, SX) pillar_prep_kernel<V4, SX><<<blocks, kPrepThreads, 0, stream>>>( \
-          points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, mask, W.sxyz)
-      if (points == nullptr) PCP_PREP(false, false);
-      else if (vec4) PCP_PREP(true, true);
-      else PCP_PREP(false, true);
-#undef PCP_PREP
+      if (vec4)
+        pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                     W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, mask);
+      else
+        pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, mask);
     }
     PCP_LAUNCH_CHECK("pillar_prep_kernel");
   }
