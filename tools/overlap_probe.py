@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--points", type=int, default=300_000)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--l2-persist", type=float, default=0.0,
+                    help="fraction of the input rows pinned in L2 (access policy window on the voxelize / PFN streams); 0 = off")
     args = ap.parse_args()
     from pcp_b200 import synthetic as syn
     from pcp_b200.frontend import FrontEnd, GridSpec
@@ -59,6 +61,35 @@ def main():
         torch.cuda.synchronize()
         truth.append((canvases[0].double().sum().item(), canvases[0].view(torch.int32).to(torch.int64).sum().item()))
 
+    # ---- optional: L2 persistence for the point rows (cudaStreamAttributeAccessPolicyWindow) ----
+    import ctypes
+
+    class _Win(ctypes.Structure):
+        _fields_ = [("base_ptr", ctypes.c_void_p), ("num_bytes", ctypes.c_size_t), ("hitRatio", ctypes.c_float),
+                    ("hitProp", ctypes.c_int), ("missProp", ctypes.c_int)]
+
+    class _Attr(ctypes.Union):
+        _fields_ = [("win", _Win), ("pad", ctypes.c_char * 64)]
+
+    rt = None
+    if args.l2_persist > 0:
+        rt = ctypes.CDLL("libcudart.so.12")
+        mx, mw = ctypes.c_int(), ctypes.c_int()
+        rt.cudaDeviceGetAttribute(ctypes.byref(mx), 108, 0)      # cudaDevAttrMaxPersistingL2CacheSize
+        rt.cudaDeviceGetAttribute(ctypes.byref(mw), 109, 0)      # cudaDevAttrMaxAccessPolicyWindowSize
+        rc = rt.cudaDeviceSetLimit(6, ctypes.c_size_t(mx.value))  # cudaLimitPersistingL2CacheSize
+        print(json.dumps({"max_persisting_l2": mx.value, "max_window": mw.value, "set_limit_rc": rc}), flush=True)
+        max_persist, max_window = mx.value, mw.value
+
+    def set_window(stream, t):
+        if rt is None:
+            return
+        a = _Attr()
+        nbytes = min(t.numel() * 4, max_window)
+        a.win = _Win(t.data_ptr(), nbytes, min(1.0, args.l2_persist * max_persist / nbytes), 2, 1)   # persisting / streaming
+        rc = rt.cudaStreamSetAttribute(ctypes.c_void_p(stream.cuda_stream), 1, ctypes.byref(a))
+        assert rc == 0, rc
+
     # torch.cuda.Stream: lower number = higher priority; CUDA clamps values outside the device's range
     greatest, least = -5, 0
 
@@ -73,6 +104,7 @@ def main():
                     fes[0].forward_device(batches[i & 1], B, outs[0], canvases[0])
                 t0.record(s)
                 for i in range(steps):
+                    set_window(s, batches[i & 1])
                     fes[0].forward_device(batches[i & 1], B, outs[0], canvases[0])
                 t1.record(s)
             torch.cuda.synchronize()
@@ -91,6 +123,9 @@ def main():
                 pts = batches[i & 1]
                 if done_c[k] is not None:
                     sv.wait_event(done_c[k])            # buffer set k is free again
+                set_window(sv, pts)
+                if sp is not sv:
+                    set_window(sp, pts)
                 with torch.cuda.stream(sv):
                     fes[k].voxelize(pts, B, outs[k], want_point_pillar=False)
                     e_v = torch.cuda.Event()
@@ -134,6 +169,8 @@ def main():
         plans += [("vp_c", least, least, least, nb), ("vp_c", greatest, greatest, least, nb), ("vp_c", least, least, greatest, nb)]
     plans += [("v_p_c", least, least, least, 3), ("v_p_c", greatest, least, least, 3), ("v_p_c", greatest, greatest, least, 3),
               ("v_p_c", least, greatest, least, 3), ("v_p_c", greatest, least, greatest, 3)]
+    if args.l2_persist > 0:
+        plans = [("serial", 0, 0, 0, 1), ("vp_c", greatest, greatest, least, 2), ("vp_c", greatest, greatest, least, 3)]
     for mode, pv, pp, pc, nb in plans:
         us, ok = run(mode, pv, pp, pc, nb, args.steps)
         r = {"mode": mode, "prio_voxelize": pv, "prio_pfn": pp, "prio_canvas": pc, "buffers": nb, "us_per_step": us,
