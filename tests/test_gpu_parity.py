@@ -351,3 +351,48 @@ def test_pipelined_front_end_is_bit_identical_to_the_serial_one(depth):
         for (p, vc, pf, sf), (cnt, gvc, gpf, gsf) in zip(want, got):
             assert int(cnt[0]) == p
             assert torch.equal(gvc[:p], vc) and torch.equal(gpf[:p], pf) and torch.equal(gsf, sf)
+
+
+def test_graph_captured_steady_state_is_bit_identical_to_the_serial_chain():
+    """PipelinedFrontEnd.capture(): one CUDA graph per buffer set (voxelize + PFN of set k beside the canvas of set k - 1);
+    a stream of batches copied into the static input buffers gives the serial chain's results bit for bit."""
+    from pcp_b200.frontend import FrontEnd, GridSpec, PipelinedFrontEnd
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    gs = GridSpec(vox, rng, grid)
+    bn = lambda i: [sd[f"pfn_layers.{i}.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")]
+    w = lambda i: sd[f"pfn_layers.{i}.linear.weight"].to(DEV)
+    B, N = 2, 50000
+    batches = [syn.batch_of_frames(B, N, 60 + j).to(DEV) for j in range(5)]
+    # a shorter batch: the tail of the static buffer is filled with out-of-range rows, which the cull drops
+    short = syn.batch_of_frames(B, N // 2, 70).to(DEV)
+    pad = short.new_full((N * B - short.shape[0], short.shape[1]), 1.0e6)
+    pad[:, 0] = 0
+    batches.append(torch.cat([short, pad]))
+    serial = FrontEnd(gs, 5)
+    serial.pack_params(w(0), bn(0), w(1), bn(1))
+    want = []
+    for pts in batches[:5] + [short]:
+        o = serial.forward_device(pts, B, {}, None)
+        torch.cuda.synchronize()
+        p = int(serial.read_counts(o)[0])
+        want.append((p, o["voxel_coords_buf"][:p].clone(), o["pillar_features_buf"][:p].clone(), o["spatial_features"].clone()))
+    pipe = PipelinedFrontEnd(gs, 5, B, depth=2)
+    pipe.pack_params(w(0), bn(0), w(1), bn(1))
+    static = [torch.empty_like(batches[0]) for _ in range(2)]
+    static[0].copy_(batches[0])
+    static[1].copy_(batches[1])
+    pipe.capture(static)
+    got = []
+    for i, pts in enumerate(batches):
+        k = i % 2
+        static[k].copy_(pts)
+        o = pipe.replay(k)
+        pillars = (o["counts"].clone(), o["voxel_coords_buf"].clone(), o["pillar_features_buf"].clone())
+        if i > 0:
+            got[-1].append(pipe.sets[1 - k]["spatial_features"].clone())      # canvas of the previous batch
+        got.append(list(pillars))
+    got[-1].append(pipe.flush((len(batches) - 1) % 2)["spatial_features"].clone())
+    torch.cuda.synchronize()
+    for (p, vc, pf, sf), (cnt, gvc, gpf, gsf) in zip(want, got):
+        assert int(cnt[0]) == p
+        assert torch.equal(gvc[:p], vc) and torch.equal(gpf[:p], pf) and torch.equal(gsf, sf)
