@@ -6,6 +6,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'quantise_count|place_kernel|pillar_prep|scan_cells|tile_sums' -c 5 -o gpurun_out/vox_v14 -f python tools/profile_step.py --steps 1 > gpurun_out/ncu_vox.log 2>&1
 python tools/config_sweep.py --iters 20 > gpurun_out/config_sweep.json 2> gpurun_out/config_sweep.err
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_nms.py tests/test_gpu_modar.py -x -q -k "not reference_kernel" > gpurun_out/memcheck_nms.log 2>&1
-timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -x -q -k "golden or long_pillars or pipelined or ordering" > gpurun_out/memcheck_parity.log 2>&1
-tail -3 gpurun_out/memcheck_nms.log gpurun_out/memcheck_parity.log
+timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -x -q -k "golden or long_pillars or pipelined or ordering or graph" > gpurun_out/memcheck_parity.log 2>&1
+tail -n 3 gpurun_out/memcheck_nms.log; tail -n 3 gpurun_out/memcheck_parity.log
 cat gpurun_out/bench.json | cut -c1-300
