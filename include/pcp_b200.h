@@ -119,6 +119,19 @@ int pcp_pfn(const float* points, int64_t row_stride, int64_t n_points, int32_t m
             float* pillar_features_out, float* pillar_mean_out, int64_t pillar_capacity, void* stream);
 
 /*
+ * pcp_pfn() in two separately schedulable stages (same arguments plus a stage mask): PCP_PFN_STAGE_SLOTS is the tensor-core
+ * kernel (every pillar of at most 32 points complete, partial maxima of the longer ones), PCP_PFN_STAGE_LONG finishes the
+ * pillars above 32 points (a few thousand per batch, latency bound).  A pipelined caller enqueues the second stage on the
+ * stream that writes the canvas, so that the next batch's voxelize kernels start right behind the tensor-core kernel.
+ */
+#define PCP_PFN_STAGE_SLOTS 1
+#define PCP_PFN_STAGE_LONG  2
+#define PCP_PFN_STAGE_ALL   3
+int pcp_pfn_stages(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames, const pcp_grid* grid,
+                   const pcp_pfn_desc* desc, const float* packed_params, const void* workspace, size_t workspace_bytes,
+                   float* pillar_features_out, float* pillar_mean_out, int64_t pillar_capacity, int32_t stages, void* stream);
+
+/*
  * Segmented reduction of arbitrary per-point values over the pillars found by pcp_voxelize():
  * torch_scatter.scatter_mean / scatter_max (call sites dynamic_pillar_vfe.py:40,110).
  *   values (n_points, value_stride) fp32 indexed by ORIGINAL row number, first `channels` columns reduced

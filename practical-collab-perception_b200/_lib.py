@@ -37,6 +37,8 @@ _SIGNATURES = {
                                _P, _P, _P, C.c_int64, _P, _P]),
     "pcp_pfn": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(PcpGrid), C.POINTER(PcpPfnDesc), _P,
                           _P, C.c_size_t, _P, _P, C.c_int64, _P]),
+    "pcp_pfn_stages": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(PcpGrid), C.POINTER(PcpPfnDesc), _P,
+                                 _P, C.c_size_t, _P, _P, C.c_int64, C.c_int32, _P]),
     "pcp_segment_reduce": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                      _P, C.c_size_t, _P, C.c_int64, _P]),
     "pcp_bev_scatter_ws": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(PcpGrid),

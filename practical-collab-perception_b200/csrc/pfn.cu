@@ -271,7 +271,16 @@ extern "C" int pcp_pfn(const float* points, int64_t row_stride, int64_t n_points
                        const pcp_grid* grid, const pcp_pfn_desc* desc, const float* packed_params,
                        const void* workspace, size_t workspace_bytes, float* pillar_features_out,
                        float* pillar_mean_out, int64_t pillar_capacity, void* stream_) {
+  return pcp_pfn_stages(points, row_stride, n_points, max_frames, grid, desc, packed_params, workspace, workspace_bytes,
+                        pillar_features_out, pillar_mean_out, pillar_capacity, PCP_PFN_STAGE_ALL, stream_);
+}
+
+extern "C" int pcp_pfn_stages(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
+                              const pcp_grid* grid, const pcp_pfn_desc* desc, const float* packed_params,
+                              const void* workspace, size_t workspace_bytes, float* pillar_features_out,
+                              float* pillar_mean_out, int64_t pillar_capacity, int32_t stages, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(stages != 0 && (stages & ~PCP_PFN_STAGE_ALL) == 0, PCP_E_INVALID, "pcp_pfn_stages: bad stage mask %d", stages);
   int c_in = 0;
   if (int rc = check_desc(desc, &c_in)) return rc;
   PCP_REQUIRE(grid && packed_params && workspace && pillar_features_out, PCP_E_INVALID, "pcp_pfn: null argument");
@@ -293,8 +302,9 @@ extern "C" int pcp_pfn(const float* points, int64_t row_stride, int64_t n_points
   t.hdr = W.hdr; t.seg_off = W.seg_off; t.sorted_idx = W.sorted_idx; t.lists = W.lists; t.lo = L.lo;
   t.mean = W.mean; t.long_mean = W.long_mean; t.long_acc = W.long_acc; t.long_table = W.long_table;
   t.out = pillar_features_out; t.mean_out = pillar_mean_out;
-  if (int rc = launch_pfn_tc(t, n_points, stream)) return rc;
-  if (n_points > kSegRows) {
+  if (stages & PCP_PFN_STAGE_SLOTS)
+    if (int rc = launch_pfn_tc(t, n_points, stream)) return rc;
+  if ((stages & PCP_PFN_STAGE_LONG) && n_points > kSegRows) {
     const int64_t want = (n_points / (kSegRows + 1) + 7) / 8;
     const unsigned blocks = (unsigned)(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4);
     pfn_finish_long_kernel<<<blocks, 256, 0, stream>>>(W.hdr, W.long_table, W.long_acc, W.long_mean, packed_params, c_in,

@@ -146,7 +146,9 @@ class FrontEnd:
         out["capacity"] = cap
         return out
 
-    def pfn(self, points: torch.Tensor, out: Dict[str, torch.Tensor], want_mean: bool = False) -> Dict[str, torch.Tensor]:
+    def pfn(self, points: torch.Tensor, out: Dict[str, torch.Tensor], want_mean: bool = False,
+            stages: int = 3) -> Dict[str, torch.Tensor]:
+        """stages: 1 = the tensor-core kernel, 2 = the pillars above 32 points, 3 = both (pcp_pfn_stages)."""
         if self.packed is None:
             raise RuntimeError("pack_params() must be called before pfn()")
         n, stride = points.shape[0], points.stride(0)
@@ -162,9 +164,9 @@ class FrontEnd:
                 mean = torch.empty((cap, 3), dtype=torch.float32, device=points.device)
                 out["pillar_mean_buf"] = mean
         ws = self.ws.buf
-        rc = self.lib.pcp_pfn(_ptr(points), stride, n, self.ws.max_frames, C.byref(self.grid.c), C.byref(self.desc),
-                              _ptr(self.packed), _ptr(ws), ws.numel(), _ptr(pf), _ptr(mean), cap, _stream())
-        _lib.check(rc, "pcp_pfn")
+        rc = self.lib.pcp_pfn_stages(_ptr(points), stride, n, self.ws.max_frames, C.byref(self.grid.c), C.byref(self.desc),
+                                     _ptr(self.packed), _ptr(ws), ws.numel(), _ptr(pf), _ptr(mean), cap, int(stages), _stream())
+        _lib.check(rc, "pcp_pfn_stages")
         return out
 
     def scatter_ws(self, pillar_features: torch.Tensor, num_frames: int,
@@ -270,7 +272,7 @@ class PipelinedFrontEnd:
             if record:
                 record[1].record(s_main)
                 record[2].record(s_main)
-            fe.pfn(points, out)
+            fe.pfn(points, out, stages=1)
             if record:
                 record[3].record(s_main)
             e_p = torch.cuda.Event()
@@ -280,6 +282,7 @@ class PipelinedFrontEnd:
                 out["spatial_features"] = torch.empty((self.max_frames, fe.c_out, g.ny, g.nx), dtype=torch.float32, device=dev)
         s_canvas.wait_event(e_p)
         with torch.cuda.stream(s_canvas):
+            fe.pfn(points, out, stages=2)                   # the few pillars above 32 points: off the main stream's critical path
             if record:
                 record[4].record(s_canvas)
             fe.scatter_ws(out["pillar_features_buf"], self.max_frames, out["spatial_features"])
@@ -299,8 +302,9 @@ class PipelinedFrontEnd:
         per batch instead of nine launches and a dozen event operations (the host stops being the bottleneck when eight ranks
         share one CPU).  ``static_points[k]`` is the device buffer set k always reads: the server copies each batch into it
         (rows past the batch's length filled with out-of-range points, which the cull drops) before ``replay(k)``.
-        After ``replay(k)`` the pillar outputs of set k and the canvas of set k - 1 are complete on the current stream;
-        ``flush(k)`` writes the canvas of the last batch."""
+        After ``replay(k)`` every output of set k - 1 (pillar features, coordinates, canvas) is complete on the current stream;
+        of set k the pillars of up to 32 points are (the few longer ones are finished on the canvas branch of the next graph).
+        ``flush(k)`` completes the last batch."""
         depth = len(self.sets)
         if depth < 2:
             raise ValueError("capture() needs depth >= 2 (the canvas of one set runs beside the voxelize kernels of the next)")
@@ -322,12 +326,13 @@ class PipelinedFrontEnd:
                 fork.record(s_main)
                 s_canvas.wait_event(fork)
                 with torch.cuda.stream(s_canvas):
+                    self.stages[prev].pfn(static_points[prev], self.sets[prev], stages=2)
                     self.stages[prev].scatter_ws(self.sets[prev]["pillar_features_buf"], self.max_frames,
                                                  self.sets[prev]["spatial_features"])
                     join = torch.cuda.Event()
                     join.record(s_canvas)
                 self.stages[k].voxelize(static_points[k], self.max_frames, self.sets[k], want_point_pillar=False)
-                self.stages[k].pfn(static_points[k], self.sets[k])
+                self.stages[k].pfn(static_points[k], self.sets[k], stages=1)
                 s_main.wait_event(join)
             graphs.append(g)
         self._graphs = graphs
@@ -337,12 +342,13 @@ class PipelinedFrontEnd:
             out["released"] = None
 
     def replay(self, k: int) -> Dict[str, torch.Tensor]:
-        """One batch through graph k on the current stream; returns buffer set k (canvas valid after the NEXT replay / flush)."""
+        """One batch through graph k on the current stream; returns buffer set k (complete after the NEXT replay / flush)."""
         self._graphs[k].replay()
         return self.sets[k]
 
     def flush(self, k: int) -> Dict[str, torch.Tensor]:
-        """Canvas of the batch last replayed through graph k (end of a stream of batches)."""
+        """Long pillars + canvas of the batch last replayed through graph k (end of a stream of batches)."""
+        self.stages[k].pfn(self._static[k], self.sets[k], stages=2)
         self.stages[k].scatter_ws(self.sets[k]["pillar_features_buf"], self.max_frames, self.sets[k]["spatial_features"])
         return self.sets[k]
 

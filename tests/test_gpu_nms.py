@@ -152,3 +152,23 @@ def test_nms_edges():
     keep, _ = pcp_b200.nms_gpu(far[:, :7].contiguous(), far[:, 7].contiguous(), 0.1)
     assert keep.shape[0] == far.shape[0]
     assert torch.equal(far[keep, 7], torch.sort(far[:, 7], descending=True)[0])
+
+
+def test_nms_empty_input_and_capacity_limit():
+    import pcp_b200
+    keep, _ = pcp_b200.nms_gpu(torch.zeros((0, 7), device=DEV), torch.zeros((0,), device=DEV), 0.2)
+    assert keep.shape == (0,) and keep.dtype == torch.int64
+    assert pcp_b200.boxes_iou_bev(torch.zeros((0, 7), device=DEV), torch.zeros((3, 7), device=DEV)).shape == (0, 3)
+    # the one-CTA ordering stage holds 4096 candidates: more is rejected loudly, a score threshold that brings the count down is fine
+    many = scene(8, n_obj=1500, per_obj=(3, 3)).to(DEV)                   # 4500 boxes
+    assert many.shape[0] > 4096
+    with pytest.raises(RuntimeError, match="4096"):
+        pcp_b200.nms_gpu(many[:, :7].contiguous(), many[:, 7].contiguous(), 0.2)
+    cfg = pcp_b200.CfgDict(NMS_TYPE="nms_gpu", NMS_THRESH=0.2, NMS_PRE_MAXSIZE=1000, NMS_POST_MAXSIZE=100)
+    sel, _ = pcp_b200.class_agnostic_nms(many[:, -2], many[:, :7], cfg, score_thresh=0.5)
+    assert 0 < sel.shape[0] <= 100
+    with pytest.raises(RuntimeError):
+        pcp_b200.nms_gpu(many[:, :7].cpu(), many[:, 7].cpu(), 0.2)         # no CPU path
+    with pytest.raises(NotImplementedError):
+        pcp_b200.class_agnostic_nms(many[:, -2], many[:, :7], pcp_b200.CfgDict(NMS_TYPE="nms_normal_gpu", NMS_THRESH=0.2,
+                                                                              NMS_PRE_MAXSIZE=10, NMS_POST_MAXSIZE=10))

@@ -383,15 +383,14 @@ def test_graph_captured_steady_state_is_bit_identical_to_the_serial_chain():
     static[1].copy_(batches[1])
     pipe.capture(static)
     got = []
+    snap = lambda o: (o["counts"].clone(), o["voxel_coords_buf"].clone(), o["pillar_features_buf"].clone(), o["spatial_features"].clone())
     for i, pts in enumerate(batches):
         k = i % 2
         static[k].copy_(pts)
-        o = pipe.replay(k)
-        pillars = (o["counts"].clone(), o["voxel_coords_buf"].clone(), o["pillar_features_buf"].clone())
+        pipe.replay(k)
         if i > 0:
-            got[-1].append(pipe.sets[1 - k]["spatial_features"].clone())      # canvas of the previous batch
-        got.append(list(pillars))
-    got[-1].append(pipe.flush((len(batches) - 1) % 2)["spatial_features"].clone())
+            got.append(snap(pipe.sets[1 - k]))                # batch i - 1 is complete once graph i has run
+    got.append(snap(pipe.flush((len(batches) - 1) % 2)))
     torch.cuda.synchronize()
     for (p, vc, pf, sf), (cnt, gvc, gpf, gsf) in zip(want, got):
         assert int(cnt[0]) == p
