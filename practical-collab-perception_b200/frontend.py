@@ -321,7 +321,8 @@ class PipelinedFrontEnd:
         for k in range(depth):
             prev = (k - 1) % depth
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=s_main):
+            # thread_local: other host threads (NCCL watchdog, clock sampler) may keep calling the CUDA runtime during the capture
+            with torch.cuda.graph(g, stream=s_main, capture_error_mode="thread_local"):
                 fork = torch.cuda.Event()
                 fork.record(s_main)
                 s_canvas.wait_event(fork)
