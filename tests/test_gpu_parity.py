@@ -316,18 +316,20 @@ def test_full_size_properties(n_frames, n_points, voxel, uniform):
     assert torch.equal(bd2["pillar_features"], pf)
 
 
-@pytest.mark.parametrize("depth", [1, 2, 3])
-def test_pipelined_front_end_is_bit_identical_to_the_serial_one(depth):
+@pytest.mark.parametrize("depth,ego", [(1, False), (2, False), (3, False), (2, True)])
+def test_pipelined_front_end_is_bit_identical_to_the_serial_one(depth, ego):
     """Steady-state mode (canvas of batch i under the voxelize kernels of batch i + 1, separate streams and buffer sets):
     every batch of a stream of different-sized batches equals the serial chain bit for bit."""
     from pcp_b200.frontend import FrontEnd, GridSpec, PipelinedFrontEnd
-    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    c_raw = 11 if ego else 5                      # ego: the 14-column lately-fusion rows (PFN row layout 2)
+    syn, rng, vox, grid, sd, cfg = v2x_setup(c_raw)
     gs = GridSpec(vox, rng, grid)
     bn = lambda i: [sd[f"pfn_layers.{i}.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")]
     w = lambda i: sd[f"pfn_layers.{i}.linear.weight"].to(DEV)
     B = 3
-    batches = [syn.batch_of_frames(B, n, 40 + j).to(DEV) for j, n in enumerate([60000, 1000, 90000, 250, 40000, 70000, 5])]
-    serial = FrontEnd(gs, 5)
+    batches = [syn.batch_of_frames(B, n, 40 + j, ego_columns=ego).to(DEV)
+               for j, n in enumerate([60000, 1000, 90000, 250, 40000, 70000, 5])]
+    serial = FrontEnd(gs, c_raw)
     serial.pack_params(w(0), bn(0), w(1), bn(1))
     want = []
     for pts in batches:
@@ -335,7 +337,7 @@ def test_pipelined_front_end_is_bit_identical_to_the_serial_one(depth):
         torch.cuda.synchronize()
         p = int(serial.read_counts(o)[0])
         want.append((p, o["voxel_coords_buf"][:p].clone(), o["pillar_features_buf"][:p].clone(), o["spatial_features"].clone()))
-    pipe = PipelinedFrontEnd(gs, 5, B, depth=depth)
+    pipe = PipelinedFrontEnd(gs, c_raw, B, depth=depth)
     pipe.pack_params(w(0), bn(0), w(1), bn(1))
     for rep in range(2):
         got = []
