@@ -171,6 +171,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
   unsigned long long remv[2] = {0ull, 0ull};                 // words lane and lane + 32 (col_blocks <= 64)
   int kept = 0;
   const int limit = post_max > 0 ? post_max : n;
+  const int nblk = (n + 63) >> 6;                            // column blocks nms_mask_kernel wrote
   for (int i = 0; i < n && kept < limit; ++i) {
     const int w = i >> 6;
     const unsigned long long word = __shfl_sync(0xffffffffu, w < 32 ? remv[0] : remv[1], w & 31);
@@ -178,8 +179,9 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
       if (lane == 0) keep_out[kept] = order[i];
       ++kept;
       // only words at or after the diagonal block were written by nms_mask_kernel
-      if (lane >= w && lane < col_blocks) remv[0] |= mask[(int64_t)i * col_blocks + lane];
-      if (lane + 32 >= w && lane + 32 < col_blocks) remv[1] |= mask[(int64_t)i * col_blocks + lane + 32];
+      // (and only the column blocks that hold candidates: n may be far below the capacity col_blocks was sized for)
+      if (lane >= w && lane < nblk) remv[0] |= mask[(int64_t)i * col_blocks + lane];
+      if (lane + 32 >= w && lane + 32 < nblk) remv[1] |= mask[(int64_t)i * col_blocks + lane + 32];
     }
   }
   if (lane == 0) *count_out = (hdr[1] > kNmsMaxBoxes) ? -1 : kept;      // -1: more boxes pass the score mask than one CTA can order
