@@ -6,6 +6,7 @@ PyTorch is used for device memory and streams only; every arithmetic step runs i
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
@@ -246,7 +247,8 @@ class PipelinedFrontEnd:
     def _ensure_streams(self, device):
         if self._streams is None or self._streams[0].device != device:
             # lower number = higher priority; CUDA clamps to the device's range
-            self._streams = (torch.cuda.Stream(device=device, priority=-5), torch.cuda.Stream(device=device, priority=0))
+            pa, pb = (int(v) for v in os.environ.get("PCP_PIPE_PRIO", "-5,0").split(","))     # tuning aid
+            self._streams = (torch.cuda.Stream(device=device, priority=pa), torch.cuda.Stream(device=device, priority=pb))
         return self._streams
 
     def submit(self, points: torch.Tensor, record=None) -> Dict[str, torch.Tensor]:
