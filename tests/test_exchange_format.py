@@ -80,3 +80,20 @@ def test_file_round_trip(tmp_path):
     assert p.stat().st_size == ex.message_bytes(11, 70)
     msg = ex.read_exchange(p)
     assert msg.agent_id == 2 and msg.timestamp == 3.2 and torch.equal(msg.boxes, boxes) and torch.equal(msg.foreground, fg)
+
+
+def test_round_trip_property():
+    """hypothesis: any record counts, agent ids and timestamps survive pack -> bytes -> unpack bit for bit."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(m=st.integers(0, 90), f=st.integers(0, 300), agent=st.integers(-2**31, 2**31 - 1),
+           ts=st.floats(allow_nan=False, allow_infinity=False, width=64), seed=st.integers(0, 1000))
+    def check(m, f, agent, ts, seed):
+        boxes, fg = _msg(m, f, seed)
+        raw = ex.pack_exchange(boxes, fg if f else None, agent_id=agent, timestamp=ts).numpy().tobytes()
+        msg = ex.unpack_exchange(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        assert (msg.agent_id, msg.timestamp) == (agent, ts)
+        assert torch.equal(msg.boxes, boxes) and (f == 0 or torch.equal(msg.foreground, fg))
+
+    check()

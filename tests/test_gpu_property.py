@@ -108,3 +108,47 @@ def test_dynamic_mean_vfe_matches_oracle(seed, n, frames, c, snap):
     want = no.dynamic_mean_vfe(pts, c, vox, RNG, grid)
     assert torch.equal(bd["voxel_coords"].cpu(), want["voxel_coords"])
     assert torch.equal(bd["voxel_features"].cpu(), want["voxel_features"])
+
+
+# ---- late-fusion NMS: random clustered boxes vs the float64 oracle ------------------------------------
+def _boxes(seed, n_obj, per_obj, degenerate):
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for _ in range(n_obj):
+        c = (torch.rand(2, generator=g) * 2 - 1) * 20
+        dims = torch.tensor([4.0, 1.8, 1.5]) + torch.rand(3, generator=g)
+        yaw = float((torch.rand(1, generator=g) * 2 - 1) * 3.2)
+        for _ in range(per_obj):
+            j = torch.randn(7, generator=g) * torch.tensor([0.4, 0.4, 0.1, 0.2, 0.1, 0.05, 0.15])
+            rows.append(torch.cat([c + j[:2], torch.tensor([-1.0]) + j[2:3], dims + j[3:6], torch.tensor([yaw]) + j[6:7],
+                                   torch.rand(1, generator=g)]))
+    b = torch.stack(rows).float()
+    if degenerate:                        # exact duplicates, axis-aligned boxes, equal scores
+        b[1] = b[0]
+        b[2, 6] = 0.0
+        b[3, 6] = float(np.pi / 2)
+        b[4, 7] = b[5, 7]
+    return b[torch.randperm(b.shape[0], generator=g)].contiguous()
+
+
+@settings(**SETTINGS)
+@given(seed=st.integers(0, 10_000), n_obj=st.integers(1, 8), per_obj=st.integers(1, 5),
+       thresh=st.sampled_from([0.01, 0.1, 0.2, 0.5, 0.7]), degenerate=st.booleans(),
+       score_thresh=st.sampled_from([None, 0.3]), pre=st.sampled_from([1000, 7]), post=st.sampled_from([100, 3]))
+def test_nms_random_scenes_against_the_oracle(seed, n_obj, per_obj, thresh, degenerate, score_thresh, pre, post):
+    import pcp_b200
+    from oracle import nms_oracle as nmo
+    b = _boxes(seed, max(n_obj, 6 if degenerate else 1), per_obj, degenerate)
+    bn = b.numpy().astype(np.float64)
+    iou = nmo.boxes_iou_bev(bn[:, :7], bn[:, :7])
+    got_iou = pcp_b200.boxes_iou_bev(b[:, :7].contiguous().to(DEV), b[:, :7].contiguous().to(DEV)).cpu().numpy()
+    assert np.abs(got_iou - iou).max() < 1e-5
+    off = iou[~np.eye(len(iou), dtype=bool)]
+    if off.size and np.any(np.abs(off - thresh) < 1e-4):
+        return                                                    # a pair sits on the threshold: fp32 vs fp64 may differ
+    cfg = pcp_b200.CfgDict(NMS_TYPE="nms_gpu", NMS_THRESH=thresh, NMS_PRE_MAXSIZE=pre, NMS_POST_MAXSIZE=post)
+    bd = b.to(DEV)
+    sel, sc = pcp_b200.class_agnostic_nms(bd[:, 7], bd[:, :7], cfg, score_thresh=score_thresh)
+    want = nmo.class_agnostic_nms(b[:, 7].numpy(), b[:, :7].numpy(), thresh, pre, post, score_thresh, iou)
+    assert sel.cpu().tolist() == want.tolist()
+    assert torch.equal(sc, bd[sel, 7])
