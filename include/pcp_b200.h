@@ -270,6 +270,8 @@ int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols
 /*
  * Pairwise BEV IoU of rotated boxes [x, y, z, dx, dy, dz, heading]: iou3d_nms_utils.boxes_iou_bev,
  * pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:227-265.  iou_out (num_a, num_b) fp32.
+ * The overlap follows the reference kernel's arithmetic (box_overlap, :107-225: edge-pair intersections, corner test with
+ * its 1e-2 m margin, ordering by atan2, fan area): results are bit-equal to the reference kernel's on the same GPU.
  */
 int pcp_boxes_iou_bev(const float* boxes_a, int64_t num_a, const float* boxes_b, int64_t num_b, float* iou_out, void* stream);
 
@@ -283,13 +285,20 @@ int pcp_boxes_iou_bev(const float* boxes_a, int64_t num_a, const float* boxes_b,
  *   iou_thresh: suppress when IoU_bev > thresh; post_max_size: at most this many survivors (:20, <= 0: all)
  *   scratch  pcp_nms_scratch_bytes(num_boxes) bytes, 256-byte aligned
  *   keep_out int64[num_boxes]: indices into `boxes` of the survivors, highest score first (ties: lower index first)
- *   count_out device int32: number of survivors; -1 if more than 4096 boxes pass the score mask (unsupported)
+ *   count_out device int32: number of survivors; -1 if more than 4096 boxes pass the score mask AND no pre_max_size
+ *            in [1, 4096] narrows them (with one, the top pre_max_size are selected first by a radix select: any num_boxes)
+ * pcp_nms_normal() is the same pipeline with the axis-aligned IoU of nms_normal_gpu (iou3d_nms_utils.py:102-116,
+ * iou3d_nms_kernel.cu:316-327).
  */
 size_t pcp_nms_scratch_bytes(int64_t num_boxes);
 int pcp_nms_bev(const float* boxes, int64_t box_stride, const float* scores, int64_t num_boxes,
                 int32_t apply_score_thresh, float score_thresh, float iou_thresh, int32_t pre_max_size,
                 int32_t post_max_size, void* scratch, size_t scratch_bytes, int64_t* keep_out, int32_t* count_out,
                 void* stream);
+int pcp_nms_normal(const float* boxes, int64_t box_stride, const float* scores, int64_t num_boxes,
+                   int32_t apply_score_thresh, float score_thresh, float iou_thresh, int32_t pre_max_size,
+                   int32_t post_max_size, void* scratch, size_t scratch_bytes, int64_t* keep_out, int32_t* count_out,
+                   void* stream);
 
 /*
  * Diagnostic: C[128 x n] = A[128 x k] . B[n x k]^T through exactly the tensor-core path pcp_pfn() uses

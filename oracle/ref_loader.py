@@ -28,7 +28,46 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("PCP_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the git-ignored copies build() leaves under oracle/_ref/py
+# (same relative paths), which travel with the snapshot like the compiled oracle/_ref/*.so
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "py")
+REFERENCE_FILES = (
+    "pcdet/models/backbones_3d/vfe/vfe_template.py",
+    "pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py",
+    "pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py",
+    "pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py",
+    "pcdet/models/bev_layers/hunter_toolbox.py",
+    "pcdet/datasets/nuscenes/nuscenes_temporal_utils.py",
+)
+
+
+def _default_root() -> str:
+    env = os.environ.get("PCP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", REFERENCE_FILES[1])):
+        return "/root/reference"
+    return _LOCAL_COPY
+
+
+REFERENCE_ROOT = _default_root()
+
+
+def stage_reference_files(src_root: str = "/root/reference") -> int:
+    """Copy the reference's own .py files of the path (unmodified) into oracle/_ref/py so that `bench.py --impl reference`
+    and tests/test_oracle_vs_reference.py can run them where /root/reference does not exist.  The directory is
+    git-ignored: the sources never enter this repository's history.  Returns the number of files copied."""
+    import shutil
+    n = 0
+    for rel in REFERENCE_FILES:
+        src = os.path.join(src_root, rel)
+        if not os.path.isfile(src):
+            continue
+        dst = os.path.join(_LOCAL_COPY, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(src, dst)
+        n += 1
+    return n
 
 
 def reference_available() -> bool:

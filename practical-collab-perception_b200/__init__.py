@@ -21,7 +21,7 @@ def __getattr__(name):
     if name in ("bev_scatter", "interpolate_points_feat_from_bev_img"):
         from . import hunter_toolbox
         return getattr(hunter_toolbox, name)
-    if name in ("class_agnostic_nms", "nms_gpu", "boxes_iou_bev"):
+    if name in ("class_agnostic_nms", "multi_classes_nms", "nms_gpu", "nms_normal_gpu", "boxes_iou_bev"):
         from . import nms
         return getattr(nms, name)
     if name in ("pack_exchange", "unpack_exchange", "read_exchange", "write_exchange", "ExchangeMessage"):

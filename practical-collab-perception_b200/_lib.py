@@ -63,6 +63,8 @@ _SIGNATURES = {
     "pcp_nms_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "pcp_nms_bev": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, C.c_size_t,
                               _P, _P, _P]),
+    "pcp_nms_normal": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, C.c_size_t,
+                                 _P, _P, _P]),
     "pcp_modar": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,
                             _P, C.c_int64, _P, _P]),
 }

@@ -9,69 +9,144 @@
 //   nms_order_kernel  : one CTA - score mask, bitonic sort by (score desc, index asc) in shared memory, pre-NMS top-k
 //   nms_mask_kernel   : 64 x 64 tiles of the upper triangle: bit j of mask[i][j / 64] = IoU_bev(i, j) > thresh
 //   nms_scan_kernel   : one warp - greedy scan in score order with the removal words in registers, post-NMS max size
-// The BEV IoU is evaluated differently from the reference (which intersects all edge pairs, collects inside corners and
-// sorts the points by angle): box A's corners are taken into box B's frame, where B is axis-aligned, clipped against B's
-// four sides (Sutherland-Hodgman) and the polygon area is a shoelace sum.  Same quantity, fp32, agrees to ~1e-6.
+// The BEV overlap RESTATES THE REFERENCE'S ARITHMETIC (iou3d_nms_kernel.cu:39-225), operation for operation: rotated corners,
+// the 16 edge-pair intersections (bounding-rectangle rejection, strict straddle test, EPS = 1e-8 branch), the corner-in-box
+// test with its MARGIN = 1e-2 m, the centroid, the ordering by atan2 and the fan area - because that kernel is only an
+// approximation of the true overlap (errors up to a few 1e-3 in IoU), so a kept-index list identical to the reference's
+// needs the same rounding, not a better area.  Expressions keep the reference's shape so that nvcc contracts them into
+// the same FMAs; tests/test_gpu_nms.py holds the IoU matrix BIT-EQUAL to the reference kernel compiled from its source.
 #include "internal.cuh"
 
 namespace pcp {
 
-constexpr int kNmsMaxBoxes = 4096;      // boxes after the score mask that one CTA can order in shared memory
+constexpr int kNmsMaxBoxes = 4096;      // candidates that one CTA can order in shared memory (after score mask + top-k)
 
 struct P2 { float x, y; };
 
-// clip polygon (n <= 8 vertices) against the half-plane  s * coord <= lim  (coord = x if axis == 0 else y)
-__device__ __forceinline__ int clip_axis(const P2* in, int n, P2* out, int axis, float s, float lim) {
-  int m = 0;
-  for (int i = 0; i < n; ++i) {
-    const P2 a = in[i], b = in[(i + 1 == n) ? 0 : i + 1];
-    const float da = s * (axis ? a.y : a.x) - lim, db = s * (axis ? b.y : b.x) - lim;   // <= 0 : inside
-    if (da <= 0.f) out[m++] = a;
-    if ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f)) {
-      const float t = da / (da - db);
-      P2 c;
-      c.x = a.x + t * (b.x - a.x);
-      c.y = a.y + t * (b.y - a.y);
-      out[m++] = c;
-    }
+__device__ __forceinline__ P2 p2_add(const P2& a, const P2& b) { P2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+__device__ __forceinline__ P2 p2_sub(const P2& a, const P2& b) { P2 r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+// :35-37
+__device__ __forceinline__ float cross2(const P2& a, const P2& b) { return a.x * b.y - a.y * b.x; }
+// :39-41
+__device__ __forceinline__ float cross3(const P2& p1, const P2& p2, const P2& p0) {
+  return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+// :43-49 bounding rectangles of the two segments overlap
+__device__ __forceinline__ bool rect_cross(const P2& p1, const P2& p2, const P2& q1, const P2& q2) {
+  return min(p1.x, p2.x) <= max(q1.x, q2.x) && min(q1.x, q2.x) <= max(p1.x, p2.x) &&
+         min(p1.y, p2.y) <= max(q1.y, q2.y) && min(q1.y, q2.y) <= max(p1.y, p2.y);
+}
+// :51-62 point inside the rotated rectangle, 1e-2 m margin
+__device__ __forceinline__ bool in_box2d(const float* box, const P2& p) {
+  const float MARGIN = 1e-2;
+  float center_x = box[0], center_y = box[1];
+  float angle_cos = cos(-box[6]), angle_sin = sin(-box[6]);
+  float rot_x = (p.x - center_x) * angle_cos + (p.y - center_y) * (-angle_sin);
+  float rot_y = (p.x - center_x) * angle_sin + (p.y - center_y) * angle_cos;
+  return (fabs(rot_x) < box[3] / 2 + MARGIN && fabs(rot_y) < box[4] / 2 + MARGIN);
+}
+// :64-95 intersection of segments p0-p1 and q0-q1
+__device__ __forceinline__ bool seg_intersection(const P2& p1, const P2& p0, const P2& q1, const P2& q0, P2& ans) {
+  const float EPS = 1e-8;
+  if (!rect_cross(p0, p1, q0, q1)) return false;
+  float s1 = cross3(q0, p1, p0);
+  float s2 = cross3(p1, q1, p0);
+  float s3 = cross3(p0, q1, q0);
+  float s4 = cross3(q1, p1, q0);
+  if (!(s1 * s2 > 0 && s3 * s4 > 0)) return false;
+  float s5 = cross3(q1, p1, p0);
+  if (fabs(s5 - s1) > EPS) {
+    ans.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+    ans.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+  } else {
+    float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+    float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+    float D = a0 * b1 - a1 * b0;
+    ans.x = (b0 * c1 - b1 * c0) / D;
+    ans.y = (a1 * c0 - a0 * c1) / D;
   }
-  return m;
+  return true;
+}
+// :97-101
+__device__ __forceinline__ void rotate_about(const P2& center, float angle_cos, float angle_sin, P2& p) {
+  float new_x = (p.x - center.x) * angle_cos + (p.y - center.y) * (-angle_sin) + center.x;
+  float new_y = (p.x - center.x) * angle_sin + (p.y - center.y) * angle_cos + center.y;
+  p.x = new_x; p.y = new_y;
 }
 
-// overlap area of two BEV boxes [x, y, z, dx, dy, dz, heading]
-__device__ float bev_overlap(const float* __restrict__ a, const float* __restrict__ b) {
-  const float ca = cosf(a[6]), sa = sinf(a[6]), cb = cosf(b[6]), sb = sinf(b[6]);
-  const float hax = 0.5f * a[3], hay = 0.5f * a[4], hbx = 0.5f * b[3], hby = 0.5f * b[4];
-  const float dx = a[0] - b[0], dy = a[1] - b[1];
-  P2 p[10], q[10];
-  const float lx[4] = {-hax, hax, hax, -hax}, ly[4] = {-hay, -hay, hay, hay};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    // corner of A in the world frame (relative to B's centre), then rotated by -heading_b
-    const float wx = lx[k] * ca - ly[k] * sa + dx, wy = lx[k] * sa + ly[k] * ca + dy;
-    p[k].x = wx * cb + wy * sb;
-    p[k].y = -wx * sb + wy * cb;
+// overlap area of two BEV boxes [x, y, z, dx, dy, dz, heading]: :107-225
+__device__ float bev_overlap(const float* box_a, const float* box_b) {
+  float a_angle = box_a[6], b_angle = box_b[6];
+  float a_dx_half = box_a[3] / 2, b_dx_half = box_b[3] / 2, a_dy_half = box_a[4] / 2, b_dy_half = box_b[4] / 2;
+  float a_x1 = box_a[0] - a_dx_half, a_y1 = box_a[1] - a_dy_half;
+  float a_x2 = box_a[0] + a_dx_half, a_y2 = box_a[1] + a_dy_half;
+  float b_x1 = box_b[0] - b_dx_half, b_y1 = box_b[1] - b_dy_half;
+  float b_x2 = box_b[0] + b_dx_half, b_y2 = box_b[1] + b_dy_half;
+  P2 center_a, center_b;
+  center_a.x = box_a[0]; center_a.y = box_a[1];
+  center_b.x = box_b[0]; center_b.y = box_b[1];
+  P2 ca[5], cb[5];
+  ca[0].x = a_x1; ca[0].y = a_y1; ca[1].x = a_x2; ca[1].y = a_y1; ca[2].x = a_x2; ca[2].y = a_y2; ca[3].x = a_x1; ca[3].y = a_y2;
+  cb[0].x = b_x1; cb[0].y = b_y1; cb[1].x = b_x2; cb[1].y = b_y1; cb[2].x = b_x2; cb[2].y = b_y2; cb[3].x = b_x1; cb[3].y = b_y2;
+  float a_angle_cos = cos(a_angle), a_angle_sin = sin(a_angle);
+  float b_angle_cos = cos(b_angle), b_angle_sin = sin(b_angle);
+  for (int k = 0; k < 4; k++) {
+    rotate_about(center_a, a_angle_cos, a_angle_sin, ca[k]);
+    rotate_about(center_b, b_angle_cos, b_angle_sin, cb[k]);
   }
-  int n = 4;
-  n = clip_axis(p, n, q, 0, 1.f, hbx);
-  if (n < 3) return 0.f;
-  n = clip_axis(q, n, p, 0, -1.f, hbx);
-  if (n < 3) return 0.f;
-  n = clip_axis(p, n, q, 1, 1.f, hby);
-  if (n < 3) return 0.f;
-  n = clip_axis(q, n, p, 1, -1.f, hby);
-  if (n < 3) return 0.f;
-  float area = 0.f;
-  for (int i = 1; i + 1 < n; ++i)
-    area += (p[i].x - p[0].x) * (p[i + 1].y - p[0].y) - (p[i].y - p[0].y) * (p[i + 1].x - p[0].x);
-  return 0.5f * fabsf(area);
+  ca[4] = ca[0];
+  cb[4] = cb[0];
+  // polygon vertices: edge intersections (a-edge major), then corners of b inside a / of a inside b, interleaved per k
+  P2 pts[16];
+  P2 centre;
+  centre.x = 0; centre.y = 0;
+  int cnt = 0;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      if (seg_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], pts[cnt])) {
+        centre = p2_add(centre, pts[cnt]);
+        cnt++;
+      }
+  for (int k = 0; k < 4; k++) {
+    if (in_box2d(box_a, cb[k])) { centre = p2_add(centre, cb[k]); pts[cnt] = cb[k]; cnt++; }
+    if (in_box2d(box_b, ca[k])) { centre = p2_add(centre, ca[k]); pts[cnt] = ca[k]; cnt++; }
+  }
+  centre.x /= cnt;
+  centre.y /= cnt;
+  // :198-207 bubble sort by the angle around the centroid (the angle of a vertex never changes: evaluated once here,
+  // compared in the reference's order, so the permutation is the reference's)
+  float ang[16];
+  for (int i = 0; i < cnt; i++) ang[i] = atan2(pts[i].y - centre.y, pts[i].x - centre.x);
+  for (int j = 0; j < cnt - 1; j++)
+    for (int i = 0; i < cnt - j - 1; i++)
+      if (ang[i] > ang[i + 1]) {
+        const P2 tp = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = tp;
+        const float ta = ang[i]; ang[i] = ang[i + 1]; ang[i + 1] = ta;
+      }
+  float area = 0;
+  for (int k = 0; k < cnt - 1; k++) area += cross2(p2_sub(pts[k], pts[0]), p2_sub(pts[k + 1], pts[0]));
+  return fabs(area) / 2.0;
 }
 
-// iou3d_nms_kernel.cu:227-234
-__device__ __forceinline__ float bev_iou(const float* a, const float* b) {
-  const float sa = a[3] * a[4], sb = b[3] * b[4];
-  const float so = bev_overlap(a, b);
-  return so / fmaxf(sa + sb - so, 1e-8f);
+// :227-234
+__device__ __forceinline__ float bev_iou(const float* box_a, const float* box_b) {
+  const float EPS = 1e-8;
+  float sa = box_a[3] * box_a[4];
+  float sb = box_b[3] * box_b[4];
+  float s_overlap = bev_overlap(box_a, box_b);
+  return s_overlap / fmaxf(sa + sb - s_overlap, EPS);
+}
+
+// axis-aligned IoU of nms_normal_gpu: :316-327
+__device__ __forceinline__ float normal_iou(const float* a, const float* b) {
+  const float EPS = 1e-8;
+  float left = fmaxf(a[0] - a[3] / 2, b[0] - b[3] / 2), right = fminf(a[0] + a[3] / 2, b[0] + b[3] / 2);
+  float top = fmaxf(a[1] - a[4] / 2, b[1] - b[4] / 2), bottom = fminf(a[1] + a[4] / 2, b[1] + b[4] / 2);
+  float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
+  float interS = width * height;
+  float Sa = a[3] * a[4];
+  float Sb = b[3] * b[4];
+  return interS / fmaxf(Sa + Sb - interS, EPS);
 }
 
 __global__ void __launch_bounds__(256)
@@ -82,30 +157,101 @@ boxes_iou_bev_kernel(const float* __restrict__ boxes_a, int64_t na, const float*
   out[i] = bev_iou(boxes_a + (i / nb) * 7, boxes_b + (i % nb) * 7);
 }
 
-// ---- 1. order: score mask + sort by (score desc, index asc) + top-k -------------------------------------------------
+// ---- 1. order: score mask + (top-k pre-selection) + sort by (score desc, index asc) ------------------------------------
+// Candidates = boxes that pass the score mask (model_nms_utils.py:9).  Up to kNmsMaxBoxes of them are ordered in shared
+// memory.  When more pass and the caller asked for a pre-NMS top-k of at most kNmsMaxBoxes (torch.topk, :15 - every shipped
+// config does: NMS_PRE_MAXSIZE 1000 .. 4096), the k best are selected first by a radix select on the order-preserving
+// integer image of the score (4 passes of 8 bits over the candidates); ties at the k-th score keep the lower indices.
 __global__ void __launch_bounds__(1024)
 nms_order_kernel(const float* __restrict__ scores, int64_t n, float score_thresh, int apply_thresh, int pre_max,
                  int32_t* __restrict__ order, int32_t* __restrict__ hdr) {
   __shared__ float s_key[kNmsMaxBoxes];
   __shared__ int32_t s_idx[kNmsMaxBoxes];
-  __shared__ int s_cnt;
+  __shared__ int s_cnt, s_all;
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_prefix, s_need;
+  __shared__ int s_warp[32];
   const int tid = threadIdx.x;
-  if (tid == 0) s_cnt = 0;
+  if (tid == 0) { s_cnt = 0; s_all = 0; }
   __syncthreads();
-  // compaction in index order is not needed: the sort key carries the index
+  auto passes = [&](float s) { return !apply_thresh || s >= score_thresh; };
+  {
+    int mine = 0;
+    for (int64_t i = tid; i < n; i += blockDim.x) mine += passes(scores[i]) ? 1 : 0;
+    atomicAdd(&s_all, mine);
+  }
+  __syncthreads();
+  const int all = s_all;
+  unsigned cut = 0;            // candidates are the boxes with ord_enc(score) > cut, plus the first s_need with == cut
+  bool select = false;
+  if (all > kNmsMaxBoxes) {
+    if (pre_max <= 0 || pre_max > kNmsMaxBoxes) {             // reported to the host through hdr[1]
+      if (tid == 0) { hdr[0] = 0; hdr[1] = all; }
+      return;
+    }
+    // radix select of the pre_max-th largest key
+    if (tid == 0) { s_prefix = 0; s_need = (unsigned)pre_max; }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      if (tid < 256) s_hist[tid] = 0;
+      __syncthreads();
+      const unsigned prefix = s_prefix;
+      const unsigned himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+      for (int64_t i = tid; i < n; i += blockDim.x) {
+        const float s = scores[i];
+        if (!passes(s)) continue;
+        const unsigned k = ord_enc(s);
+        if ((k & himask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned need = s_need, d = 255;
+        for (;; --d) {                                         // walk the digits from the largest
+          if (s_hist[d] >= need || d == 0) break;
+          need -= s_hist[d];
+        }
+        s_prefix = prefix | (d << shift);
+        s_need = need;                                         // how many of the keys with this prefix are still wanted
+      }
+      __syncthreads();
+    }
+    cut = s_prefix;
+    select = true;
+  }
+  // gather the candidates (any order: the sort key carries the index)
+  const unsigned need_eq = select ? s_need : 0u;
   for (int64_t i = tid; i < n; i += blockDim.x) {
     const float s = scores[i];
-    if (!apply_thresh || s >= score_thresh) {                 // model_nms_utils.py:9
+    if (passes(s) && (!select || ord_enc(s) > cut)) {
       const int pos = atomicAdd(&s_cnt, 1);
-      if (pos < kNmsMaxBoxes) { s_key[pos] = s; s_idx[pos] = (int32_t)i; }
+      s_key[pos] = s; s_idx[pos] = (int32_t)i;
+    }
+  }
+  __syncthreads();
+  if (select) {
+    // the first need_eq boxes (in index order) whose key equals the cut: ordered block compaction
+    int taken = 0;
+    for (int64_t base = 0; base < n && taken < (int)need_eq; base += blockDim.x) {
+      const int64_t i = base + tid;
+      bool hit = false;
+      float s = 0.f;
+      if (i < n) { s = scores[i]; hit = passes(s) && ord_enc(s) == cut; }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int w = 0; w < 32; ++w) { if (w < (tid >> 5)) before += s_warp[w]; total += s_warp[w]; }
+      const int rank = taken + before + __popc(bal & ((1u << (tid & 31)) - 1u));
+      if (hit && rank < (int)need_eq) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        s_key[pos] = s; s_idx[pos] = (int32_t)i;
+      }
+      taken += total;
+      __syncthreads();
     }
   }
   __syncthreads();
   const int cnt = s_cnt;
-  if (cnt > kNmsMaxBoxes) {                                   // reported to the host through hdr[1]
-    if (tid == 0) { hdr[0] = 0; hdr[1] = cnt; }
-    return;
-  }
   int m = 1;
   while (m < cnt) m <<= 1;
   for (int i = cnt + tid; i < m; i += blockDim.x) { s_key[i] = -INFINITY; s_idx[i] = 0x7fffffff; }
@@ -128,10 +274,11 @@ nms_order_kernel(const float* __restrict__ scores, int64_t n, float score_thresh
   }
   const int keep = min(cnt, pre_max > 0 ? pre_max : cnt);     // torch.topk(k = min(NMS_PRE_MAXSIZE, n)), :15
   for (int i = tid; i < keep; i += blockDim.x) order[i] = s_idx[i];
-  if (tid == 0) { hdr[0] = keep; hdr[1] = cnt; }
+  if (tid == 0) { hdr[0] = keep; hdr[1] = min(all, kNmsMaxBoxes); }
 }
 
 // ---- 2. suppression mask (upper triangle) -----------------------------------------------------------------------------
+template <bool kNormal>
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float* __restrict__ boxes, int64_t box_stride, const int32_t* __restrict__ order,
                 const int32_t* __restrict__ hdr, float thresh, int col_blocks, unsigned long long* __restrict__ mask) {
@@ -157,7 +304,7 @@ nms_mask_kernel(const float* __restrict__ boxes, int64_t box_stride, const int32
   const int ncol = min(64, n - cbk * 64);
   const int start = (rb == cbk) ? t + 1 : 0;
   for (int j = start; j < ncol; ++j)
-    if (bev_iou(a, s_col + j * 7) > thresh) bits |= 1ull << j;
+    if ((kNormal ? normal_iou(a, s_col + j * 7) : bev_iou(a, s_col + j * 7)) > thresh) bits |= 1ull << j;   // a = the higher-scored box, as the reference
   mask[(int64_t)ri * col_blocks + cbk] = bits;
 }
 
@@ -211,10 +358,10 @@ extern "C" size_t pcp_nms_scratch_bytes(int64_t num_boxes) {
   return 256 + align_up(4 * (size_t)(n + 1), 256) + 8 * (size_t)(n * col_blocks + 1);
 }
 
-extern "C" int pcp_nms_bev(const float* boxes, int64_t box_stride, const float* scores, int64_t num_boxes,
-                           int32_t apply_score_thresh, float score_thresh, float iou_thresh, int32_t pre_max_size,
-                           int32_t post_max_size, void* scratch, size_t scratch_bytes, int64_t* keep_out,
-                           int32_t* count_out, void* stream_) {
+static int nms_launch(bool normal, const float* boxes, int64_t box_stride, const float* scores, int64_t num_boxes,
+                      int32_t apply_score_thresh, float score_thresh, float iou_thresh, int32_t pre_max_size,
+                      int32_t post_max_size, void* scratch, size_t scratch_bytes, int64_t* keep_out,
+                      int32_t* count_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PCP_REQUIRE(count_out && num_boxes >= 0 && num_boxes < (1ll << 31), PCP_E_INVALID, "pcp_nms_bev: bad argument");
   if (num_boxes == 0) {
@@ -232,10 +379,27 @@ extern "C" int pcp_nms_bev(const float* boxes, int64_t box_stride, const float* 
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(sp);
   nms_order_kernel<<<1, 1024, 0, stream>>>(scores, num_boxes, score_thresh, apply_score_thresh, pre_max_size, order, hdr);
   PCP_LAUNCH_CHECK("nms_order_kernel");
-  nms_mask_kernel<<<dim3((unsigned)col_blocks, (unsigned)col_blocks), 64, 0, stream>>>(boxes, box_stride, order, hdr, iou_thresh,
-                                                                                      col_blocks, mask);
+  const dim3 mg((unsigned)col_blocks, (unsigned)col_blocks);
+  if (normal) nms_mask_kernel<true><<<mg, 64, 0, stream>>>(boxes, box_stride, order, hdr, iou_thresh, col_blocks, mask);
+  else nms_mask_kernel<false><<<mg, 64, 0, stream>>>(boxes, box_stride, order, hdr, iou_thresh, col_blocks, mask);
   PCP_LAUNCH_CHECK("nms_mask_kernel");
   nms_scan_kernel<<<1, 32, 0, stream>>>(mask, order, hdr, col_blocks, post_max_size, keep_out, count_out);
   PCP_LAUNCH_CHECK("nms_scan_kernel");
   return 0;
+}
+
+extern "C" int pcp_nms_bev(const float* boxes, int64_t box_stride, const float* scores, int64_t num_boxes,
+                           int32_t apply_score_thresh, float score_thresh, float iou_thresh, int32_t pre_max_size,
+                           int32_t post_max_size, void* scratch, size_t scratch_bytes, int64_t* keep_out,
+                           int32_t* count_out, void* stream) {
+  return nms_launch(false, boxes, box_stride, scores, num_boxes, apply_score_thresh, score_thresh, iou_thresh, pre_max_size,
+                    post_max_size, scratch, scratch_bytes, keep_out, count_out, stream);
+}
+
+extern "C" int pcp_nms_normal(const float* boxes, int64_t box_stride, const float* scores, int64_t num_boxes,
+                              int32_t apply_score_thresh, float score_thresh, float iou_thresh, int32_t pre_max_size,
+                              int32_t post_max_size, void* scratch, size_t scratch_bytes, int64_t* keep_out,
+                              int32_t* count_out, void* stream) {
+  return nms_launch(true, boxes, box_stride, scores, num_boxes, apply_score_thresh, score_thresh, iou_thresh, pre_max_size,
+                    post_max_size, scratch, scratch_bytes, keep_out, count_out, stream);
 }

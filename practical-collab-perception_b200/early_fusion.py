@@ -14,9 +14,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from .frontend import _ptr, _require_cuda, _stream
+from .frontend import _ptr, _require_cuda, _stream, device_guard
 
 
+@device_guard
 def fuse_agent_points(ego_points: torch.Tensor, agent_points: Sequence[torch.Tensor],
                       target_se3_agents: Sequence[np.ndarray], point_cloud_range: Optional[Sequence[float]] = None,
                       batch_idx: Optional[int] = 0) -> torch.Tensor:

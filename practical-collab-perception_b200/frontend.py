@@ -6,6 +6,7 @@ PyTorch is used for device memory and streams only; every arithmetic step runs i
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
@@ -27,7 +28,39 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream() -> C.c_void_p:
+    """The current stream of the CURRENT device: every public wrapper runs under ``device_guard``, which makes the
+    device of its tensor arguments current, so this is the stream torch itself would launch on for them."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_devices(obj, found, depth=0):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            found.add(obj.device)
+    elif isinstance(obj, dict) and depth < 3:
+        for v in obj.values():
+            _cuda_devices(v, found, depth + 1)
+    elif isinstance(obj, (list, tuple)) and depth < 3:
+        for v in obj:
+            _cuda_devices(v, found, depth + 1)
+
+
+def device_guard(fn):
+    """Run ``fn`` with the GPU of its tensor arguments as the current device (the library launches on the current
+    device's current stream and never calls cudaSetDevice).  Tensors on two different GPUs raise: the reference's
+    torch ops would raise there too, these kernels would silently dereference a foreign pointer."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        found = set()
+        _cuda_devices(args, found)
+        _cuda_devices(kwargs, found)
+        if len(found) > 1:
+            raise RuntimeError(f"{fn.__qualname__}: tensors on different GPUs {sorted(str(d) for d in found)}")
+        if not found:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(next(iter(found))):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 @dataclass
@@ -90,6 +123,7 @@ class FrontEnd:
         self.packed: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ parameters
+    @device_guard
     def pack_params(self, w0, bn0, w1=None, bn1=None, lin_bias0=None, lin_bias1=None, eps: float = 1e-3):
         """bn = (weight, bias, running_mean, running_var) or None.  Runs pcp_pack_pfn_params on the GPU."""
         dev = w0.device
@@ -116,6 +150,7 @@ class FrontEnd:
     def capacity(self, n_points: int, max_frames: int) -> int:
         return max(1, min(int(n_points), int(max_frames) * self.grid.nx * self.grid.ny))
 
+    @device_guard
     def voxelize(self, points: torch.Tensor, max_frames: int, out: Optional[Dict[str, torch.Tensor]] = None,
                  want_point_pillar: bool = True, want_counts_per_pillar: bool = False) -> Dict[str, torch.Tensor]:
         _require_cuda(points, "points")
@@ -147,6 +182,7 @@ class FrontEnd:
         out["capacity"] = cap
         return out
 
+    @device_guard
     def pfn(self, points: torch.Tensor, out: Dict[str, torch.Tensor], want_mean: bool = False,
             stages: int = 3) -> Dict[str, torch.Tensor]:
         """stages: 1 = the tensor-core kernel, 2 = the pillars above 32 points, 3 = both (pcp_pfn_stages)."""
@@ -170,6 +206,7 @@ class FrontEnd:
         _lib.check(rc, "pcp_pfn_stages")
         return out
 
+    @device_guard
     def scatter_ws(self, pillar_features: torch.Tensor, num_frames: int,
                    canvas: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Dense canvas from the workspace the last voxelize() left (no search, no memset)."""
@@ -183,6 +220,7 @@ class FrontEnd:
         _lib.check(rc, "pcp_bev_scatter_ws")
         return canvas
 
+    @device_guard
     def segment_reduce(self, values: torch.Tensor, mode: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """scatter_mean / scatter_max of per-point ``values`` (indexed by original row) over the pillars of
         the last voxelize().  Returns the (capacity, C) buffer; the first P rows are valid."""
@@ -201,6 +239,7 @@ class FrontEnd:
         return out
 
     # ------------------------------------------------------------------ whole chain
+    @device_guard
     def forward_device(self, points: torch.Tensor, max_frames: int, out: Optional[Dict[str, torch.Tensor]] = None,
                        canvas: Optional[torch.Tensor] = None, want_point_pillar: bool = False):
         """voxelize -> PFN -> canvas for ``max_frames`` frames, all enqueued, nothing read back.
@@ -251,6 +290,7 @@ class PipelinedFrontEnd:
             self._streams = (torch.cuda.Stream(device=device, priority=pa), torch.cuda.Stream(device=device, priority=pb))
         return self._streams
 
+    @device_guard
     def submit(self, points: torch.Tensor, record=None) -> Dict[str, torch.Tensor]:
         """Enqueue one batch.  ``record``: optional 6 timing events (voxelize / PFN / canvas begin and end)."""
         _require_cuda(points, "points")
@@ -298,6 +338,7 @@ class PipelinedFrontEnd:
         return out
 
     # ------------------------------------------------------------------ CUDA graphs
+    @device_guard
     def capture(self, static_points: Sequence[torch.Tensor]) -> None:
         """Steady state as CUDA graphs (one per buffer set): graph k holds voxelize + PFN of set k on the high-priority branch
         beside the canvas of set k - 1 on the low-priority branch, i.e. exactly the overlap ``submit`` produces, in ONE launch
@@ -346,7 +387,8 @@ class PipelinedFrontEnd:
 
     def replay(self, k: int) -> Dict[str, torch.Tensor]:
         """One batch through graph k on the current stream; returns buffer set k (complete after the NEXT replay / flush)."""
-        self._graphs[k].replay()
+        with torch.cuda.device(self._static[k].device):
+            self._graphs[k].replay()
         return self.sets[k]
 
     def flush(self, k: int) -> Dict[str, torch.Tensor]:
@@ -370,6 +412,7 @@ class PipelinedFrontEnd:
                 cur.wait_event(out["done"])
 
 
+@device_guard
 def generic_scatter(pillar_features: torch.Tensor, voxel_coords: torch.Tensor, nx: int, ny: int,
                     num_frames: Optional[int] = None) -> torch.Tensor:
     """PointPillarScatter for arbitrary (pillar_features, voxel_coords) (pointpillar_scatter.py:14-37)."""

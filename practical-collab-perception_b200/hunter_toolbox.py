@@ -12,7 +12,15 @@ import numpy as np
 import torch
 
 from . import _lib
-from .frontend import _ptr, _require_cuda, _stream
+from .frontend import _ptr, _require_cuda, _stream, device_guard
+
+
+def _no_autograd(name: str, *tensors) -> None:
+    """These kernels have no backward: fail loudly instead of silently cutting the graph of a training caller
+    (hunter_jr.py trains through both functions)."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise RuntimeError(f"pcp_b200.{name} is inference-only (no autograd): call it under torch.no_grad() "
+                           "or detach its inputs")
 
 
 def _f32(v) -> float:
@@ -22,12 +30,14 @@ def _f32(v) -> float:
     return float(np.float32(v))
 
 
+@device_guard
 def bev_scatter(points_bev_coord: torch.Tensor, points_batch_idx: torch.Tensor, points_feat: torch.Tensor,
                 bev_img_size: Sequence[int], batch_size: Optional[int] = None) -> torch.Tensor:
     """hunter_toolbox.py:65-96.  (N, 2) bev_x/bev_y, (N,) batch index, (N, C) features, (height, width) ->
     (B, C, H, W) per-pixel mean of the features of the points that fall strictly inside the image, zeros elsewhere.
     ``batch_size`` skips the reference's ``torch.max(points_batch_idx).item() + 1`` synchronisation (:74)."""
     lib = _lib.load()
+    _no_autograd("bev_scatter", points_bev_coord, points_feat)
     for t, name in ((points_bev_coord, "points_bev_coord"), (points_batch_idx, "points_batch_idx"), (points_feat, "points_feat")):
         _require_cuda(t, name)
     dev = points_feat.device
@@ -59,6 +69,7 @@ def bev_scatter(points_bev_coord: torch.Tensor, points_batch_idx: torch.Tensor, 
     return out
 
 
+@device_guard
 def interpolate_points_feat_from_bev_img(bev_img: torch.Tensor, points: torch.Tensor,
                                          point_cloud_range: Union[torch.Tensor, Sequence[float]],
                                          bev_pixel_size: Union[torch.Tensor, Sequence[float]],
@@ -66,6 +77,7 @@ def interpolate_points_feat_from_bev_img(bev_img: torch.Tensor, points: torch.Te
     """hunter_toolbox.py:99-131.  (B, C, H, W) image, (N, 1 + ...) points [batch_idx, x, y, ...] -> (N, C) bilinear
     features (and the (N, 2) BEV coordinates when ``return_bev_coord``)."""
     lib = _lib.load()
+    _no_autograd("interpolate_points_feat_from_bev_img", bev_img, points)
     _require_cuda(bev_img, "bev_img")
     _require_cuda(points, "points")
     img = bev_img.detach()

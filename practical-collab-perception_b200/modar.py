@@ -98,12 +98,23 @@ def modar_exchange(detections, foreground, target_se3_agent, t_detect: float, t_
     max_sweep_idx: written to every MoDAR row (:225); default = ego_points[:, sweep column].max().
     Returns (N + sum M, same columns) fp32 on the GPU.
     """
-    lib = _lib.load()
     if not ego_points.is_cuda:
         raise RuntimeError("ego_points must be on the GPU: pcp_b200 has no CPU path")
+    # received records may live anywhere (host, another GPU): they are moved to the ego cloud's GPU, which is made current
+    with torch.cuda.device(ego_points.device):
+        return _modar_exchange(detections, foreground, target_se3_agent, t_detect, t_query, ego_points, max_sweep_idx,
+                               batch_idx, sample_interval, return_box_idx)
+
+
+def _modar_exchange(detections, foreground, target_se3_agent, t_detect, t_query, ego_points, max_sweep_idx, batch_idx,
+                    sample_interval, return_box_idx):
+    lib = _lib.load()
     dev = ego_points.device
-    if not isinstance(detections, (list, tuple)):
+    # ExchangeMessage is a NamedTuple: test for it before the list / tuple test, or one message reads as four agents
+    if isinstance(detections, ExchangeMessage) or not isinstance(detections, (list, tuple)):
         detections, foreground, target_se3_agent = [detections], [foreground], [target_se3_agent]
+        if foreground[0] is None:
+            foreground = None
     if foreground is None:          # messages carry their own foreground records
         foreground = [d.foreground if isinstance(d, ExchangeMessage) and d.foreground.shape[0] else None for d in detections]
     if not (len(detections) == len(foreground) == len(target_se3_agent)):

@@ -145,6 +145,10 @@ class DynamicPillarVFE(VFETemplate):
         points = batch_dict["points"]
         if not points.is_cuda:
             raise RuntimeError("batch_dict['points'] must be on the GPU (load_data_to_gpu): no CPU path")
+        with torch.cuda.device(points.device):      # the kernels launch on the current device's current stream
+            return self._forward(batch_dict, points)
+
+    def _forward(self, batch_dict, points):
         if points.dtype != torch.float32 or not points.is_contiguous():
             points = points.float().contiguous()
         if points.shape[1] < 1 + self.num_raw_point_features:
@@ -191,6 +195,12 @@ class PointPillarScatter(nn.Module):
         pillar_features, coords = batch_dict["pillar_features"], batch_dict["voxel_coords"]
         if not pillar_features.is_cuda:
             raise RuntimeError("pillar_features must be on the GPU: pcp_b200 has no CPU path")
+        if coords.device != pillar_features.device:
+            raise RuntimeError(f"pillar_features on {pillar_features.device}, voxel_coords on {coords.device}")
+        with torch.cuda.device(pillar_features.device):
+            return self._forward(batch_dict, pillar_features, coords)
+
+    def _forward(self, batch_dict, pillar_features, coords):
         if coords.shape[0] == 0:
             # the reference fails here too: coords[:, 0].max() of an empty tensor (pointpillar_scatter.py:17)
             raise RuntimeError("PointPillarScatter: no pillars (max() of an empty voxel_coords)")
@@ -320,10 +330,14 @@ class DynamicMeanVFE(VFETemplate):
 
     @torch.no_grad()
     def forward(self, batch_dict, **kwargs):
-        lib = _lib.load()
         points = batch_dict["points"]
         if not points.is_cuda:
             raise RuntimeError("batch_dict['points'] must be on the GPU (load_data_to_gpu): no CPU path")
+        with torch.cuda.device(points.device):
+            return self._forward(batch_dict, points)
+
+    def _forward(self, batch_dict, points):
+        lib = _lib.load()
         if points.dtype != torch.float32 or not points.is_contiguous():
             points = points.float().contiguous()
         c = self.num_raw_point_features

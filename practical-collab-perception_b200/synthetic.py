@@ -159,3 +159,13 @@ def modar_scene(config_id: int = 2, frame: int = 0, n_agents: int = 5, n_ego_poi
     ego = lidar_frame(n_ego_points, 1000 * config_id + frame, batch_idx=0, ego_columns=True)
     agents: List[Dict[str, torch.Tensor]] = [modar_agent(100000 * config_id + 100 * frame + a) for a in range(n_agents)]
     return ego, agents
+
+
+def model_cfgs(c_raw, num_filters=(64, 64), use_norm=True, with_distance=False, use_abs=True):
+    """(VFE cfg, scatter cfg) with the keys of tools/cfgs/v2x_sim_models/v2x_pointpillar_basic_*.yaml (MODEL.VFE,
+    MODEL.MAP_TO_BEV)."""
+    from .config import CfgDict
+    vfe = CfgDict(NAME="DynPillarVFE", NUM_RAW_POINT_FEATURES=int(c_raw), USE_NORM=bool(use_norm),
+                  WITH_DISTANCE=bool(with_distance), USE_ABSLOTE_XYZ=bool(use_abs), NUM_FILTERS=list(num_filters))
+    scat = CfgDict(NAME="PointPillarScatter", NUM_BEV_FEATURES=int(num_filters[-1]))
+    return vfe, scat

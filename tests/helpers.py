@@ -45,12 +45,9 @@ def layers_from_state_dict(sd, use_norm=True):
     return layers
 
 
-def model_cfgs(c_raw, num_filters=(64, 64), use_norm=True, with_distance=False, use_abs=True):
-    from pcp_b200 import CfgDict
-    vfe = CfgDict(NAME="DynPillarVFE", NUM_RAW_POINT_FEATURES=int(c_raw), USE_NORM=bool(use_norm),
-                  WITH_DISTANCE=bool(with_distance), USE_ABSLOTE_XYZ=bool(use_abs), NUM_FILTERS=list(num_filters))
-    scat = CfgDict(NAME="PointPillarScatter", NUM_BEV_FEATURES=int(num_filters[-1]))
-    return vfe, scat
+def model_cfgs(*args, **kwargs):
+    from pcp_b200.synthetic import model_cfgs as f
+    return f(*args, **kwargs)
 
 
 def assert_features_close(got, want, what, rtol=1e-5, atol_scale=1e-5):

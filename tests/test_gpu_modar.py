@@ -165,3 +165,100 @@ def test_exchange_messages_packed_on_the_gpu_feed_modar_and_nms(tmp_path):
     s1, sc1 = pcp_b200.class_agnostic_nms(allb[:, 7], allb[:, :7], cfg, score_thresh=0.3)
     s2, sc2 = pcp_b200.class_agnostic_nms(direct[:, 7], direct[:, :7], cfg, score_thresh=0.3)
     assert torch.equal(s1, s2) and torch.equal(sc1, sc2) and s1.numel() > 0
+
+
+def test_single_message_call_forms():
+    """The documented one-agent forms: a bare ExchangeMessage (a NamedTuple - it must not be iterated as four agents),
+    a bare detections dict and a bare (M, 9) tensor, each with a bare (4, 4) pose."""
+    from pcp_b200 import synthetic as syn
+    import pcp_b200
+    ego14, agents = syn.modar_scene(2, 7, n_agents=1, n_ego_points=300)
+    ego13 = ego14[:, 1:].contiguous()
+    a = agents[0]
+    want = run_exchange(ego13, agents)
+    msg = pcp_b200.unpack_exchange(pcp_b200.pack_exchange(a["modar"].to(DEV), a["foreground"].to(DEV), agent_id=3, timestamp=1.0))
+    got = pcp_b200.modar_exchange(msg, None, a["target_se3_agent"], msg.timestamp, 1.2, ego13.to(DEV))
+    assert torch.equal(got, want)
+    got = pcp_b200.modar_exchange(msg, a["foreground"], a["target_se3_agent"], 1.0, 1.2, ego13.to(DEV))
+    assert torch.equal(got, want)
+    got = pcp_b200.modar_exchange(a["modar"], a["foreground"], a["target_se3_agent"], 1.0, 1.2, ego13.to(DEV))
+    assert torch.equal(got, want)
+    got = pcp_b200.modar_exchange(msg.detections, a["foreground"], a["target_se3_agent"], 1.0, 1.2, ego13.to(DEV))
+    assert torch.equal(got, want)
+
+
+def test_hunter_toolbox_refuses_to_cut_an_autograd_graph():
+    import pcp_b200
+    from pcp_b200 import hunter_toolbox as ht
+    coord = torch.rand(64, 2, device=DEV) * 16
+    feat = torch.rand(64, 4, device=DEV, requires_grad=True)
+    bidx = torch.zeros(64, dtype=torch.long, device=DEV)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        ht.bev_scatter(coord, bidx, feat, (16, 16), batch_size=1)
+    with torch.no_grad():
+        out = ht.bev_scatter(coord, bidx, feat, (16, 16), batch_size=1)
+    assert out.shape == (1, 4, 16, 16)
+    out = ht.bev_scatter(coord, bidx, feat.detach(), (16, 16), batch_size=1)
+    assert not out.requires_grad
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_a_non_current_gpu_run_on_their_own_device():
+    """Advisor finding: the library launches on the current device's stream.  With cuda:0 current, a model and a cloud
+    on cuda:1 must give the same result as on cuda:0; tensors on two GPUs in one call must raise."""
+    import pcp_b200
+    from pcp_b200 import synthetic as syn
+    from pcp_b200.frontend import FrontEnd, GridSpec
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    gs = GridSpec(syn.V2X_VOXEL, rng, syn.grid_size_of(rng, syn.V2X_VOXEL))
+    pts = syn.batch_of_frames(1, 20000, 1)
+    outs = []
+    torch.cuda.set_device(0)
+    for dev in ("cuda:0", "cuda:1"):
+        fe = FrontEnd(gs, 5)
+        o = fe.voxelize(pts.to(dev), 1)
+        torch.cuda.synchronize(dev)
+        p = int(fe.read_counts(o)[0])
+        outs.append(o["voxel_coords_buf"][:p].cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.cuda.current_device() == 0
+    with pytest.raises(RuntimeError, match="different GPUs"):
+        pcp_b200.boxes_iou_bev(torch.zeros(1, 7, device="cuda:0"), torch.zeros(1, 7, device="cuda:1"))
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_SO), reason="oracle/_ref/libroiaware_ref.so not built (make -C oracle)")
+def test_propagation_against_the_reference_composition():
+    """v2x_sim_dataset_ego.py:203-215 composed literally: the REFERENCE'S OWN points_in_boxes kernel (compiled unmodified)
+    -> torch.unique(return_inverse) -> torch_scatter.scatter(reduce='mean') * 2 (pure-torch restatement of the absent
+    third-party op) -> modar[unq, :3] += offset.  Both the oracle and the product must reproduce it: the product sums each
+    box's flow in ascending point order, which is the CPU scatter's order, so the comparison is bit for bit."""
+    from pcp_b200 import synthetic as syn
+    from oracle import pillar_oracle as po
+    ref = ctypes.CDLL(REF_SO)
+    launcher = getattr(ref, "_Z24points_in_boxes_launcheriiiPKfS0_Pi")
+    launcher.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+    launcher.restype = None
+    for seed in range(4):
+        ag = syn.modar_agent(1300 + seed, n_boxes=40 + 10 * seed, fg_per_box=(30, 200), stray_fraction=0.25)
+        modar, foregr = ag["modar"].clone(), ag["foreground"].clone()
+        b_dev, f_dev = modar[:, :7].contiguous().to(DEV), foregr[:, :3].contiguous().to(DEV)
+        idx = torch.full((foregr.shape[0],), -1, dtype=torch.int32, device=DEV)
+        torch.cuda.synchronize()
+        launcher(1, modar.shape[0], foregr.shape[0], b_dev.data_ptr(), f_dev.data_ptr(), idx.data_ptr())
+        torch.cuda.synchronize()
+        # ---- the literal lines :203-215 ----
+        box_idx_of_foregr = idx.cpu().long()
+        mask_valid_foregr = box_idx_of_foregr > -1
+        fg = foregr[mask_valid_foregr]
+        box_idx_of_foregr = box_idx_of_foregr[mask_valid_foregr]
+        unq_box_idx, inv_unq_box_idx = torch.unique(box_idx_of_foregr, return_inverse=True)
+        boxes_offset = po.scatter_mean(fg[:, -3:], inv_unq_box_idx, unq_box_idx.shape[0]) * 2.
+        want = modar.clone()
+        want[unq_box_idx, :3] += boxes_offset
+        # ---- oracle ----
+        got_oracle = mo.propagate_modar(modar.numpy(), foregr.numpy(), 2.0)
+        assert np.array_equal(got_oracle, want.numpy()), "oracle differs from the reference composition"
+        # ---- product (identity pose: the fp64 SE(3) is exact, heading wrap leaves |yaw| < pi unchanged up to 1 ulp) ----
+        rows = run_exchange(torch.zeros(1, 13), [{"modar": modar, "foreground": foregr, "target_se3_agent": np.eye(4)}],
+                            max_sweep_idx=0.0).cpu()[1:]
+        assert torch.equal(rows[:, :3], want[:, :3]), "product differs from the reference composition"
+        assert int((unq_box_idx.shape[0])) > 10

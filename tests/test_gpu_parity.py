@@ -397,3 +397,36 @@ def test_graph_captured_steady_state_is_bit_identical_to_the_serial_chain():
     for (p, vc, pf, sf), (cnt, gvc, gpf, gsf) in zip(want, got):
         assert int(cnt[0]) == p
         assert torch.equal(gvc[:p], vc) and torch.equal(gpf[:p], pf) and torch.equal(gsf, sf)
+
+
+@pytest.mark.parametrize("alt", [0, 1])
+def test_bench_workload_against_oracle(alt):
+    """The workload bench.py times (8 early-fusion frames of 300 k points, both alternating batches), through the
+    modules, against the oracle with the sort-based unique: pillar coordinates, point->pillar map, occupancy bit-exact,
+    pillar features within the path's fp32 tolerance, canvas an exact copy."""
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    pts = syn.batch_of_frames(8, 300000, 3, first_frame=alt * 1000)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    bd = run_modules(vfe, scat, pts, 8)
+    want = oracle_want(pts, cfg, layers_from_state_dict(sd))
+    check_against(bd, want, pts.shape[0])
+    # frame by frame: the pillars of frame b are exactly the oracle's pillars of that frame run alone
+    vc = bd["voxel_coords"].cpu()
+    for b in (0, 7):
+        one = pts[pts[:, 0] == b].clone()
+        one[:, 0] = 0
+        w1 = po.front_end(one, cfg, layers_from_state_dict(sd), unique_dim0=False)
+        sel = vc[:, 0] == b
+        assert torch.equal(vc[sel][:, 1:], w1["voxel_coords"][:, 1:])
+        assert_features_close(bd["pillar_features"].cpu()[sel].numpy(), w1["pillar_features"].numpy(), f"frame {b}")
+
+
+@pytest.mark.parametrize("n_points,uniform", [(1000000, False), (1000000, True)])
+def test_stress_config_against_oracle(n_points, uniform):
+    """BASELINE config 5 at 1 M points (0.1 m pillars, 1024 x 1024 canvas): full comparison with the oracle."""
+    voxel = [0.1, 0.1, 8.0]
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5, voxel=voxel)
+    pts = syn.batch_of_frames(1, n_points, 5, uniform_xy=uniform)
+    vfe, scat = build_modules(5, vox, rng, grid, sd)
+    bd = run_modules(vfe, scat, pts, 1)
+    check_against(bd, oracle_want(pts, cfg, layers_from_state_dict(sd)), pts.shape[0])

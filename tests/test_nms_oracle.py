@@ -41,3 +41,24 @@ def test_greedy_suppression_and_class_agnostic_wrapper():
     assert no.class_agnostic_nms(scores, boxes, 0.5, 10, 10, score_thresh=0.99).shape == (0,)
     # ties: lower index first
     assert no.nms(boxes[:2], np.array([0.5, 0.5]), 0.5).tolist() == [0]
+
+
+def test_reference_procedure_restatement_agrees_with_the_exact_overlap():
+    """ref_overlap_f32 follows the reference kernel's procedure: away from its 1e-2 m corner margin it is the exact area
+    to float32 rounding; a corner within the margin of the other box's side shows the kernel's known error."""
+    a = box(0, 0, 4, 2, 0)
+    assert abs(no.ref_overlap_f32(a, box(2, 0, 4, 2, 0.0)) - 4.0) < 1e-5
+    sq = box(0, 0, 2, 2, 0)
+    assert abs(no.ref_overlap_f32(sq, box(0, 0, 2, 2, np.pi / 4)) - 8.0 * (np.sqrt(2.0) - 1.0)) < 1e-5
+    assert no.ref_overlap_f32(a, box(10, 0, 4, 2, 0.3)) == 0.0
+    g = np.random.default_rng(3)
+    worst = 0.0
+    for _ in range(60):
+        b1 = box(g.uniform(-2, 2), g.uniform(-2, 2), g.uniform(2, 5), g.uniform(1, 3), g.uniform(-3, 3))
+        b2 = box(g.uniform(-2, 2), g.uniform(-2, 2), g.uniform(2, 5), g.uniform(1, 3), g.uniform(-3, 3))
+        worst = max(worst, abs(no.ref_overlap_f32(b1, b2) - no.bev_overlap(b1, b2)))
+    assert worst < 0.1                                   # bounded by margin x side length
+    iou = no.ref_iou_f32(np.stack([a, box(2, 0, 4, 2, 0)]), np.stack([a]))
+    assert abs(iou[0, 0] - 1.0) < 1e-6 and abs(iou[1, 0] - 4.0 / 12.0) < 1e-6
+    n = no.iou_normal_f32(np.stack([a, box(2, 0, 4, 2, 1.0)]), np.stack([a]))
+    assert abs(n[0, 0] - 1.0) < 1e-6 and abs(n[1, 0] - 4.0 / 12.0) < 1e-6   # heading is ignored
