@@ -50,9 +50,16 @@ def measured_peak_gbs():
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full`
-    capture of this workload (profiles/r01_traffic.json, written from the capture's summary); None if absent."""
+    capture of this workload (profiles/r02_traffic.json / r01_traffic.json, written from the captures' summaries); None if
+    absent."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]["dram_bytes"]
+        for name in ("r02_traffic.json", "r01_traffic.json"):       # newest capture that has this kernel
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.isfile(path):
+                d = json.load(open(path))
+                if kernel in d:
+                    return d[kernel]["dram_bytes"]
+        return None
     except Exception:
         return None
 
@@ -112,6 +119,26 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+def pin_to_gpu_numa(phys_index: int):
+    """Bind this process to the CPUs next to its GPU (NVML's ideal CPU affinity) BEFORE any pinned allocation, so that the
+    pinned input buffers live on the GPU's own NUMA node and the H2D copies do not cross the socket interconnect.  Returns
+    the number of CPUs bound to, or None when NVML / sched_setaffinity are unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def physical_gpu_index(local_rank: int) -> int:
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -123,47 +150,74 @@ def physical_gpu_index(local_rank: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference's DynamicPillarVFE + PointPillarScatter
+# CPU baseline: the REFERENCE'S OWN DynamicPillarVFE + PointPillarScatter (unmodified files, loaded by path)
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_frames_per_s(steps: int, warmup: int, frame_seed: int = 0):
-    """Times the CPU restatement of the reference path (oracle/, same ATen ops incl. torch.unique(dim=0))
-    on ONE early-fusion frame per step, all host threads."""
+    """Times the reference's own modules (pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py:94-147 +
+    pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-37) on ONE early-fusion frame per step, all host threads.
+    The files are the unmodified reference sources: /root/reference in the build container, the git-ignored copies build()
+    leaves under oracle/_ref/py on the GPU box (oracle/ref_loader.py).  torch_scatter - third party, absent from the image and
+    unpinned by the reference - is its pure-torch restatement (oracle/pillar_oracle.py), as in every parity test.  If the
+    reference files are not available the oracle port of the same lines is timed instead and `kind` says "port".
+    Returns (frames/s, s/frame, cores, threads, kind)."""
     from oracle import pillar_oracle as po
+    from oracle import ref_loader as rl
     from pcp_b200 import synthetic as syn
     from tests.helpers import layers_from_state_dict
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
     grid = syn.grid_size_of(rng, syn.V2X_VOXEL)
-    cfg = po.VFEConfig(C_RAW, syn.V2X_VOXEL, rng, grid)
-    layers = layers_from_state_dict(syn.pfn_state_dict(C_RAW + 6))
+    sd = syn.pfn_state_dict(C_RAW + 6)
     pts = syn.batch_of_frames(1, POINTS_PER_FRAME, CONFIG_ID, first_frame=frame_seed)
+    kind = "port"
+    if rl.reference_available():
+        try:
+            vfe, scat = rl.build_reference_front_end(C_RAW, syn.V2X_VOXEL, rng, grid)
+            vfe.load_state_dict(sd)
+            with torch.no_grad():
+                scat(vfe({"points": pts[:1000].clone()}))          # the unmodified modules run here: use them
+            kind = "reference"
+        except Exception as exc:                                    # fall back to the port rather than lose the line
+            print(f"reference modules unusable on this host ({exc!r}); timing the oracle port", file=sys.stderr)
+    if kind == "reference":
+        def step():
+            return scat(vfe({"points": pts}))
+    else:
+        cfg = po.VFEConfig(C_RAW, syn.V2X_VOXEL, rng, grid)
+        layers = layers_from_state_dict(sd)
+
+        def step():
+            return po.front_end(pts, cfg, layers, unique_dim0=True)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            po.front_end(pts, cfg, layers, unique_dim0=True)
+            step()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     mean = sum(times) / len(times)
-    return 1.0 / mean, mean, cores, torch.get_num_threads()
+    return 1.0 / mean, mean, cores, torch.get_num_threads(), kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fps, sec, cores, threads = cpu_reference_frames_per_s(max(args.steps, 1), max(min(args.warmup, 2), 1))
-    sample = f"1 frame of {POINTS_PER_FRAME} points per step (1/{FRAMES_PER_GPU} of one GPU's batch)"
+    fps, sec, cores, threads, kind = cpu_reference_frames_per_s(max(args.steps, 1), max(min(args.warmup, 2), 1))
+    sample = (f"1 frame of {POINTS_PER_FRAME} points per step (1/{FRAMES_PER_GPU} of one GPU's batch) through the reference's own "
+              "DynamicPillarVFE.forward + PointPillarScatter.forward on the host cores" if kind == "reference" else
+              f"1 frame of {POINTS_PER_FRAME} points per step, oracle port (reference files not staged)")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "one CPU process on rank 0 whatever --gpus says: a ratio against an N-GPU value compares N GPUs with one host",
     }
     emit(line)
 
@@ -173,6 +227,7 @@ def workload_config(n_gpus):
                         f"0.2 m pillars, 512x512 canvas, C_raw {C_RAW}, PFN 11->32,64->64",
             "frames_per_gpu": FRAMES_PER_GPU, "points_per_frame": POINTS_PER_FRAME, "global_frames": FRAMES_PER_GPU * n_gpus,
             "parallelism": f"frames sharded over {n_gpus} GPU(s), no hot-path collective",
+            "voxelize": "pcp_voxelize_method AUTO = dense-histogram compaction (the radix-sort method is selectable and slower)",
             "pipelining": "steady state: canvas of batch i on a low-priority stream beside voxelize of batch i+1, 2 buffer sets, "
                           "one CUDA graph launch per step",
             "l2": "per-step working set ~0.95 GB >> 126 MB L2 (537 MB canvas streamed every step); 2 input batches alternate"}
@@ -195,6 +250,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = pin_to_gpu_numa(physical_gpu_index(local_rank))
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
@@ -267,12 +323,17 @@ def run_ours(args):
     eager_ms_per_step = e0.elapsed_time(e1) / args.steps
     counts = pipe.stages[0].read_counts(out)
     n_pillars, n_kept = int(counts[0]), int(counts[1])
+    # pillars of the batch each buffer set holds (set k is fed dev_batches[k] by the graphs below)
+    n_pillars_expect = {}
 
     # (b) THE TIMED REGION: the steady state captured as two CUDA graphs (graph k = voxelize + PFN of buffer set k beside the
     #     canvas of set k - 1): one launch per step, K steps = K voxelize + K PFN + K canvas passes
     pipe.capture([dev_batches[0], dev_batches[1]])
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 2)):
         pipe.replay(i & 1)
+    torch.cuda.synchronize()
+    for k in range(2):
+        n_pillars_expect[k] = int(pipe.sets[k]["counts"].cpu()[0])
     barrier()
     with ClockSampler(physical_gpu_index(local_rank)) as clk:
         t_start, t_end = ev(), ev()
@@ -284,6 +345,35 @@ def run_ours(args):
     elapsed_ms = t_start.elapsed_time(t_end)
     barrier()
 
+    # (c) the same region with the 32-byte counts block of every step read back by the host (SURVEY 8d "P read-back included"):
+    #     the consumer learns P before it slices the pillar tensors, so every step ends in a stream synchronisation
+    counts_pinned = torch.empty(_lib.PCP_COUNTS_LEN, dtype=torch.int32).pin_memory()
+    rb0, rb1 = ev(), ev()
+    t0 = time.perf_counter()
+    rb0.record()
+    for i in range(args.steps):
+        k = (args.warmup + i) & 1
+        o = pipe.replay(k)
+        counts_pinned.copy_(o["counts"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        assert int(counts_pinned[0]) == n_pillars_expect[k]
+    rb1.record()
+    torch.cuda.synchronize()
+    readback_ms = max(rb0.elapsed_time(rb1), (time.perf_counter() - t0) * 1e3)
+    barrier()
+
+    # (d) sustained: the same graphs replayed for >= 1.2 s, clocks sampled throughout
+    sus_steps = max(args.steps, int(1200.0 / max(elapsed_ms / args.steps, 1e-3)) + 1)
+    with ClockSampler(physical_gpu_index(local_rank), period_s=0.02) as sus_clk:
+        su0, su1 = ev(), ev()
+        su0.record()
+        for i in range(sus_steps):
+            pipe.replay(i & 1)
+        su1.record()
+        torch.cuda.synchronize()
+    sus_ms = su0.elapsed_time(su1)
+    barrier()
+
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -292,27 +382,78 @@ def run_ours(args):
         elapsed_max = elapsed_ms
     ms_per_step = elapsed_max / args.steps
     value = world * B * args.steps / (elapsed_max * 1e-3)
+    if world > 1:
+        t = torch.tensor([readback_ms, sus_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        readback_ms, sus_ms = float(t[0].item()), float(t[1].item())
+    value_with_readback = world * B * args.steps / (readback_ms * 1e-3)
+    sustained_value = world * B * sus_steps / (sus_ms * 1e-3)
 
     # per-stage device time inside the timed region (CUDA events on the stream each stage is launched on; the canvas of one
     # batch runs beside the voxelize kernels of the next, so these include the contention and do not add up to the step)
     stage_ms = [statistics.mean(stage_ev[i][2 * j].elapsed_time(stage_ev[i][2 * j + 1]) for i in range(args.steps)) for j in range(3)]
-    stage_names = ["voxelize(5 launches)", "pfn_kernel", "canvas_kernel"]
+    stage_names = ["voxelize", "pfn_kernel", "canvas_kernel"]
     row_bytes = 4 * dev_batches[0].shape[1]
     alg = {
-        "voxelize(5 launches)": n_points * row_bytes + n_pillars * 16,
+        "voxelize": n_points * row_bytes + n_pillars * 16,
         "pfn_kernel": n_kept * row_bytes + n_pillars * 64 * 4,
         "canvas_kernel": B * 64 * gs.ny * gs.nx * 4 + n_pillars * 64 * 4,
     }
     chain_bytes = n_points * row_bytes + n_pillars * 64 * 4 + n_pillars * 16 + B * 64 * gs.ny * gs.nx * 4
     peak, peak_src = measured_peak_gbs()
-    # dominant KERNEL: the voxelize stage is five short launches, the other two stages are one kernel each
-    # (chosen on the un-overlapped times; its duration is the one measured inside the timed region, on its own stream)
-    # The PFN is the kernel that has the GPU to itself in steady state (the canvas is hidden beside voxelize): it is the one
-    # reported unless the canvas is clearly longer (the two are within run-to-run noise of each other when run alone).
-    dom = 2 if serial_stage_ms[2] > 1.1 * serial_stage_ms[1] else 1
+    # every stage against the measured copy bandwidth; `roofline` (the contract's single object) is the stage that takes
+    # the longest inside the timed region
+    stage_roofline = {}
+    for j, name in enumerate(stage_names):
+        ach = alg[name] / (stage_ms[j] * 1e-3) / 1e9
+        stage_roofline[name] = {"ms": stage_ms[j], "ms_alone": serial_stage_ms[j], "algorithmic_bytes": alg[name], "achieved": ach,
+                                "frac": ach / peak, "frac_alone": alg[name] / (serial_stage_ms[j] * 1e-3) / 1e9 / peak,
+                                "traffic": ncu_traffic(name)}
+    dom = max(range(3), key=lambda j: stage_ms[j])
     dom_name = stage_names[dom]
-    achieved = alg[dom_name] / (stage_ms[dom] * 1e-3) / 1e9
+    achieved = stage_roofline[dom_name]["achieved"]
     chain_achieved = chain_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- sharded correctness: NCCL all-gather of the per-rank BEV blocks, checked on rank 0 (BASELINE configs[3]) ----
+    # Outside the timed region.  Every rank runs the serial chain on its own batch 0; the (B, 64, ny, nx) blocks are all-gathered;
+    # rank 0 regenerates every rank's frames, runs them on its own GPU and compares bit for bit.
+    gather = {"gather_validated": None}
+    try:
+        fe_v = FrontEnd(gs, C_RAW)
+        fe_v.packed = pipe.stages[0].packed
+        o_v = fe_v.forward_device(dev_batches[0], B, {}, None)
+        mine = o_v["spatial_features"]
+        torch.cuda.synchronize()
+        if world > 1:
+            full = torch.empty((world * B,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=dev)
+            dist.all_gather_into_tensor(full, mine)                # warm-up: communicator setup
+            g0, g1 = ev(), ev()
+            g0.record()
+            dist.all_gather_into_tensor(full, mine)
+            g1.record()
+            torch.cuda.synchronize()
+            gather["gather_bus_GBps"] = full.numel() * 4 * (world - 1) / world / (g0.elapsed_time(g1) * 1e-3) / 1e9
+        else:
+            full = mine
+            gather["gather_bus_GBps"] = None
+        if rank == 0:
+            mism = 0
+            for r in range(world):
+                if r == 0 and world == 1:
+                    blk = dev_batches[0]
+                else:
+                    blk = syn.batch_of_frames(B, POINTS_PER_FRAME, CONFIG_ID, first_frame=r * B).to(dev)
+                o_r = fe_v.forward_device(blk, B, {}, None)
+                mism += int((full[r * B:(r + 1) * B] != o_r["spatial_features"]).sum().item())
+                del o_r
+            occ = int((full != 0).any(1).sum().item())
+            gather.update({"gather_validated": bool(mism == 0 and occ > 0), "gather_mismatches": mism,
+                           "gather_shape": list(full.shape), "gather_occupied_cells": occ})
+        del fe_v, o_v, mine, full
+        torch.cuda.empty_cache()
+    except Exception as exc:                                        # never lose the bench line to the validation step
+        gather = {"gather_validated": False, "gather_error": repr(exc)[:200]}
+    barrier()
 
     # ---------------- e2e: drop-in modules, pinned host input, H2D + counts D2H inside the timed region ----------------
     vfe_cfg, scat_cfg = model_cfgs(C_RAW)
@@ -378,16 +519,26 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 or True:
-            fps, sec, cores, threads = cpu_reference_frames_per_s(steps=3, warmup=1)
-            cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"1 frame of {POINTS_PER_FRAME} points x 3 runs (oracle port, torch.unique(dim=0) as the reference calls it)"}
+            fps, sec, cores, threads, kind = cpu_reference_frames_per_s(steps=3, warmup=1)
+            cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"1 frame of {POINTS_PER_FRAME} points x 3 runs through "
+                             + ("the reference's own DynamicPillarVFE.forward + PointPillarScatter.forward (unmodified files, "
+                                "torch_scatter = its pure-torch restatement)" if kind == "reference" else "the oracle port")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "mpts_per_s": value * POINTS_PER_FRAME / 1e6,
             "pillars_per_step": n_pillars, "kept_points_per_step": n_kept,
+            "value_with_readback": value_with_readback,
+            "readback": {"ms_per_step": readback_ms / args.steps, "d2h_bytes_per_step": 4 * _lib.PCP_COUNTS_LEN,
+                         "note": "the timed graphs with the 32-byte counts block copied to pinned host memory and the stream "
+                                 "synchronised after every step (the consumer learns P before slicing the outputs)"},
+            "sustained": {"value": sustained_value, "ms_per_step": sus_ms / sus_steps, "steps": sus_steps, "seconds": sus_ms * 1e-3,
+                          "clocks": sus_clk.summary()},
             "stage_ms": dict(zip(stage_names, stage_ms)),
+            "roofline_stages": stage_roofline,
+            "numa_cpus_bound": numa_cpus,
             "eager_pipelined_ms_per_step": eager_ms_per_step,
             "serial": {"ms_per_step": serial_ms_per_step, "stage_ms": dict(zip(stage_names, serial_stage_ms)), "steps": serial_steps,
                        "note": "one batch at a time on one stream (no overlap between batches)"},
@@ -404,6 +555,7 @@ def run_ours(args):
                            "H2D copy is prefetched on a copy stream"},
             # quantise, tile sums, cell scan, place, pillar prep, pfn, long-pillar finish, canvas (+1 memset) per step
             "gpu_launches": 8 * args.steps,
+            **gather,
             "clocks": clk.summary(),
         }
         emit(line)

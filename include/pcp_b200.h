@@ -108,6 +108,28 @@ int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int3
                  int64_t pillar_capacity, int32_t* counts_out, void* stream);
 
 /*
+ * pcp_voxelize() with the compaction algorithm chosen by the caller (pillars, maps, counts identical bit for bit; means
+ * identical for pillars of up to 4096 points):
+ *   PCP_VOXELIZE_HISTOGRAM  dense per-cell histogram with one L2 atomic per point + cell scan + counting-sort placement + an
+ *                           ordering pass per pillar (csrc/voxelize.cu); any size.  The faster one on the B200 at every size
+ *                           measured (profiles/r02_voxelize_time_*.json), hence:
+ *   PCP_VOXELIZE_AUTO       = HISTOGRAM (what pcp_voxelize() does).
+ *   PCP_VOXELIZE_RADIX      stable two-digit MSD radix sort on the linear key: partition into bins of 512 / 1024 consecutive
+ *                           cells, then a counting sort + run-length per bin in shared memory (csrc/voxelize_radix.cu).  No
+ *                           global atomics, no gathers; rows ascend inside every pillar by construction, so the per-pillar
+ *                           mean is the sequential sum in row order for pillars of ANY length (the histogram path falls back
+ *                           to arrival order above 4096 points).  Covers key spaces of at most 4 M cells (16 frames of
+ *                           512 x 512) and 1 .. 16.6 M rows; PCP_E_UNSUPPORTED outside.
+ */
+#define PCP_VOXELIZE_AUTO      0
+#define PCP_VOXELIZE_HISTOGRAM 1
+#define PCP_VOXELIZE_RADIX     2
+int pcp_voxelize_method(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
+                        const pcp_grid* grid, void* workspace, size_t workspace_bytes,
+                        int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
+                        int64_t pillar_capacity, int32_t* counts_out, int32_t method, void* stream);
+
+/*
  * Pillar feature network.  Replaces dynamic_pillar_vfe.py:110-129 (scatter_mean, f_cluster, f_center,
  * concat) and PFNLayerV2.forward :35-46 for every layer, fused: no per-point intermediate reaches HBM.
  *   pillar_features_out (pillar_capacity, c_out) fp32, first P rows valid.
@@ -271,7 +293,8 @@ int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols
  * Pairwise BEV IoU of rotated boxes [x, y, z, dx, dy, dz, heading]: iou3d_nms_utils.boxes_iou_bev,
  * pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:227-265.  iou_out (num_a, num_b) fp32.
  * The overlap follows the reference kernel's arithmetic (box_overlap, :107-225: edge-pair intersections, corner test with
- * its 1e-2 m margin, ordering by atan2, fan area): results are bit-equal to the reference kernel's on the same GPU.
+ * its 1e-2 m margin, ordering by atan2, fan area): results agree with the reference kernel's to 1e-5 (> 99 % bit-equal; FMA
+ * fusion is ptxas's choice), NMS keep lists are identical.
  */
 int pcp_boxes_iou_bev(const float* boxes_a, int64_t num_a, const float* boxes_b, int64_t num_b, float* iou_out, void* stream);
 

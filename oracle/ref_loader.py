@@ -115,9 +115,10 @@ def _load(name: str, relpath: str, package: str | None = None):
 
 
 @contextlib.contextmanager
-def _cuda_is_identity():
-    """dynamic_pillar_vfe.py:87-89 call .cuda() unconditionally; make that a no-op on CPU-only hosts."""
-    if torch.cuda.is_available():
+def _cuda_is_identity(force: bool = False):
+    """dynamic_pillar_vfe.py:87-89 call .cuda() unconditionally; make that a no-op on CPU-only hosts, and - force - on a
+    GPU box when the reference is to run on the host cores (the CPU baseline of bench.py)."""
+    if torch.cuda.is_available() and not force:
         yield
         return
     orig = torch.Tensor.cuda
@@ -179,11 +180,11 @@ class Cfg(dict):
 
 def build_reference_front_end(num_raw_point_features, voxel_size, point_cloud_range, grid_size,
                               num_filters=(64, 64), use_norm=True, with_distance=False, use_absolute_xyz=True):
-    """Constructs the reference's DynamicPillarVFE + PointPillarScatter in eval mode on CPU."""
+    """Constructs the reference's DynamicPillarVFE + PointPillarScatter in eval mode on the CPU (also on a GPU box)."""
     ns = load_reference_modules()
     vfe_cfg = Cfg(NUM_RAW_POINT_FEATURES=num_raw_point_features, USE_NORM=use_norm, WITH_DISTANCE=with_distance,
                   USE_ABSLOTE_XYZ=use_absolute_xyz, NUM_FILTERS=list(num_filters))
-    with ns.cuda_is_identity():
+    with ns.cuda_is_identity(force=True):
         vfe = ns.DynamicPillarVFE(model_cfg=vfe_cfg, num_point_features=num_raw_point_features,
                                   voxel_size=voxel_size, grid_size=grid_size,
                                   point_cloud_range=point_cloud_range)

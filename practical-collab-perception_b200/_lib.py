@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libpcp_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 PCP_COUNTS_LEN = 8
+VOXELIZE_METHODS = {"auto": 0, "histogram": 1, "radix": 2, "radix_or_auto": 2}   # radix_or_auto: see FrontEnd.voxelize
 COUNT_PILLARS, COUNT_KEPT, COUNT_FRAMES, COUNT_BAD_FRAME, COUNT_MAX_PER_PILLAR, COUNT_VOXELS = 0, 1, 2, 3, 4, 5
 
 
@@ -35,6 +36,8 @@ _SIGNATURES = {
     "pcp_pack_pfn_params": (C.c_int, [C.POINTER(PcpPfnDesc)] + [_P] * 12 + [C.c_float, _P, _P]),
     "pcp_voxelize": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(PcpGrid), _P, C.c_size_t,
                                _P, _P, _P, C.c_int64, _P, _P]),
+    "pcp_voxelize_method": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(PcpGrid), _P, C.c_size_t,
+                                      _P, _P, _P, C.c_int64, _P, C.c_int32, _P]),
     "pcp_pfn": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(PcpGrid), C.POINTER(PcpPfnDesc), _P,
                           _P, C.c_size_t, _P, _P, C.c_int64, _P]),
     "pcp_pfn_stages": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(PcpGrid), C.POINTER(PcpPfnDesc), _P,

@@ -148,7 +148,7 @@ extern "C" int pcp_max_index_i64(const int64_t* index, int64_t n, int32_t* max_p
   PCP_REQUIRE(max_plus_one_out && n >= 0 && (n == 0 || index), PCP_E_INVALID, "pcp_max_index_i64: bad argument");
   PCP_CUDA(cudaMemsetAsync(max_plus_one_out, 0, sizeof(int32_t), stream));
   if (n > 0) {
-    max_index_kernel<<<148, 256, 0, stream>>>(index, n, max_plus_one_out);
+    max_index_kernel<<<sm_count(), 256, 0, stream>>>(index, n, max_plus_one_out);
     PCP_LAUNCH_CHECK("max_index_kernel");
   }
   return 0;

@@ -106,8 +106,56 @@ __host__ __device__ inline void unpack_entry(unsigned long long e, int& r, int& 
   len = (int)((e >> 58) & 31ull) + 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// radix path of pcp_voxelize (voxelize_radix.cu): key = bin << shift | cell-in-bin
+// ---------------------------------------------------------------------------------------------
+constexpr int kRxMaxBins = 4096;        // bins (high digit); 16-bit counters per (warp, bin) in shared memory
+constexpr int kRxMinShift = 9;          // 512 cells per bin ...
+constexpr int kRxMaxShift = 10;         // ... or 1024: at most 4 M cells (16 frames of 512 x 512, 4 of 1024 x 1024)
+constexpr int kRxMaxChunks = 256;       // chunks of consecutive input rows (one CTA each; B200: one per SM)
+constexpr int kRxChunkWarps = 16;
+constexpr int kRxMaxChunkPts = 65024;   // rows per chunk: a multiple of 512 below 65536, so that prefixes inside a chunk fit 16 bits
+
+struct RadixPlan {
+  int32_t ok;                           // 0: this problem runs on the histogram path
+  int32_t shift, bin_cells, nbins, nbins_pad;
+  int32_t chunks, chunk_pts, wpts;      // K1 / K3: chunks of chunk_pts rows, wpts rows per warp
+  int32_t gw, ngroups;                  // K4: bins (= warps) per CTA, CTAs
+};
+
+// bins of a key space of `cells` cells; false when the radix path does not cover it
+__host__ __device__ inline bool radix_bins(int64_t cells, int32_t& shift, int32_t& nbins) {
+  shift = kRxMinShift;
+  while (((cells + (1ll << shift) - 1) >> shift) > kRxMaxBins && shift <= kRxMaxShift) ++shift;
+  nbins = (int32_t)((cells + (1ll << shift) - 1) >> shift);
+  return shift <= kRxMaxShift && cells > 0;
+}
+
+__host__ inline RadixPlan radix_plan(int64_t n, int64_t cells, int sms) {
+  RadixPlan p{};
+  if (n <= 0 || !radix_bins(cells, p.shift, p.nbins)) return p;
+  p.bin_cells = 1 << p.shift;
+  p.nbins_pad = (p.nbins + 7) & ~7;
+  int64_t chunks = sms < kRxMaxChunks ? sms : kRxMaxChunks;
+  if (chunks < 1) chunks = 1;
+  const int64_t unit = 32 * kRxChunkWarps;                      // 512 rows: 32 per warp
+  if (chunks > (n + unit - 1) / unit) chunks = (n + unit - 1) / unit;
+  int64_t chunk_pts = ((n + chunks - 1) / chunks + unit - 1) / unit * unit;
+  if (chunk_pts > kRxMaxChunkPts) chunk_pts = kRxMaxChunkPts;
+  chunks = (n + chunk_pts - 1) / chunk_pts;
+  if (chunks > kRxMaxChunks) return p;                          // more than 16.6 M rows: histogram path
+  p.chunks = (int32_t)chunks;
+  p.chunk_pts = (int32_t)chunk_pts;
+  p.wpts = (int32_t)(chunk_pts / kRxChunkWarps);
+  p.gw = (p.shift == kRxMinShift && p.nbins >= 2048) ? 8 : 4;
+  p.ngroups = (p.nbins + p.gw - 1) / p.gw;
+  p.ok = 1;
+  return p;
+}
+
 struct WsLayout {
   size_t hdr, tile_info, cell, cell_rank, key, within, seg_off, sorted_idx, lists, mean, long_table, big_list, long_mean, long_acc, total;
+  size_t rtable, rbin_total, rbin_start, rgroup_info, rrec, rsrec, rkey;   // radix path scratch (zero-sized when it does not apply)
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
   int64_t cells, cap, scan_tiles, seg_cap, long_cap;
   ListOffsets lo;
@@ -148,6 +196,20 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   L.big_list = o;    o = align_up(o + 4 * (size_t)L.long_cap, 256);
   L.long_mean = o;   o = align_up(o + 16 * (size_t)L.long_cap, 256);
   L.long_acc = o;    o = align_up(o + sizeof(uint32_t) * 96 * (size_t)L.long_cap, 256);
+  {
+    // radix path: table[chunk][bin] | bin totals | first row of every bin | K4 group records | {x, y, z, row} records in bin
+    // order, the same records in pillar order, keys in bin order.  Capacities depend on (n, cells) only, never on the device.
+    int32_t shift = 0, nbins = 0;
+    const bool rx = radix_bins(L.cells, shift, nbins) && n > 0 && n <= (int64_t)kRxMaxChunks * kRxMaxChunkPts;
+    const size_t nb = rx ? (size_t)nbins : 0, np = rx ? (size_t)n : 0;
+    L.rtable = o;      o = align_up(o + sizeof(int32_t) * kRxMaxChunks * nb, 256);
+    L.rbin_total = o;  o = align_up(o + sizeof(int32_t) * (nb + 1), 256);
+    L.rbin_start = o;  o = align_up(o + sizeof(int32_t) * (nb + 1), 256);
+    L.rgroup_info = o; o = align_up(o + sizeof(int32_t) * 16 * (nb / 4 + 1), 256);
+    L.rrec = o;        o = align_up(o + 16 * (np + 1), 256);
+    L.rsrec = o;       o = align_up(o + 16 * (np + 1), 256);
+    L.rkey = o;        o = align_up(o + sizeof(int32_t) * (np + 1), 256);
+  }
   L.total = o;
   return L;
 }
@@ -167,6 +229,13 @@ struct WsView {
   int32_t* big_list;
   float4* long_mean;
   unsigned* long_acc;
+  int32_t* rtable;
+  int32_t* rbin_total;
+  int32_t* rbin_start;
+  int32_t* rgroup_info;
+  float4* rrec;
+  float4* rsrec;
+  int32_t* rkey;
 };
 
 __host__ inline WsView ws_view(void* base, const WsLayout& L) {
@@ -186,6 +255,13 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.big_list = reinterpret_cast<int32_t*>(p + L.big_list);
   v.long_mean = reinterpret_cast<float4*>(p + L.long_mean);
   v.long_acc = reinterpret_cast<unsigned*>(p + L.long_acc);
+  v.rtable = reinterpret_cast<int32_t*>(p + L.rtable);
+  v.rbin_total = reinterpret_cast<int32_t*>(p + L.rbin_total);
+  v.rbin_start = reinterpret_cast<int32_t*>(p + L.rbin_start);
+  v.rgroup_info = reinterpret_cast<int32_t*>(p + L.rgroup_info);
+  v.rrec = reinterpret_cast<float4*>(p + L.rrec);
+  v.rsrec = reinterpret_cast<float4*>(p + L.rsrec);
+  v.rkey = reinterpret_cast<int32_t*>(p + L.rkey);
   return v;
 }
 
@@ -199,6 +275,18 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
 // NaN / inf fail the range test the way the reference's int compare does on CPU.
 __device__ __forceinline__ float quantise(float v, float vmin, float vsize) {
   return floorf(__fdiv_rn(__fsub_rn(v, vmin), vsize));
+}
+
+// Linear key of a point row, or -1 when it is culled (dynamic_pillar_vfe.py:98-106).  The range test runs on the integral
+// floats (the same predicate as the reference's compare on the int cast, and false for NaN); points[:, 0].int() truncates
+// toward zero (:104); a frame index outside [0, frames) drops the row and is reported through `bad_frame`.
+__device__ __forceinline__ int32_t point_key(float bf, float x, float y, int32_t frames, const pcp_grid& g, bool& bad_frame) {
+  bad_frame = false;
+  const float qx = quantise(x, g.range_min_x, g.voxel_x);
+  const float qy = quantise(y, g.range_min_y, g.voxel_y);
+  if (!((qx >= 0.f) && (qx < (float)g.nx) && (qy >= 0.f) && (qy < (float)g.ny))) return -1;
+  if (!(bf > -1.f) || !(bf < (float)frames)) { bad_frame = true; return -1; }
+  return (int32_t)bf * (g.nx * g.ny) + (int32_t)qx * g.ny + (int32_t)qy;
 }
 
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldg(p); }

@@ -10,6 +10,14 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
                     const pcp_grid& grid, int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
                     int32_t* counts_out, cudaStream_t stream);
 
+// voxelize_radix.cu: the whole of pcp_voxelize() as a stable two-digit radix sort on the key (see the file header)
+int voxelize_radix(const WsLayout& L, const WsView& W, const RadixPlan& rp, const float* points, int64_t stride, int64_t n,
+                   int32_t frames, const pcp_grid& grid, int32_t* point_pillar_out, int32_t* voxel_coords_out,
+                   int32_t* pillar_count_out, int32_t* counts_out, cudaStream_t stream);
+
+// api.cu: multiprocessors of the current device (queried once per device)
+int sm_count();
+
 // pfn.cu: per-cell mean (mode 0) / max (mode 1) of `channels` columns of `values`, rows visited in ascending row order.
 int launch_segment_reduce(const float* values, int64_t value_stride, int32_t channels, int32_t mode, const WsView& W,
                           float* out, cudaStream_t stream);

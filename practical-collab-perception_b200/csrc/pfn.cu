@@ -203,7 +203,7 @@ static int pow2_at_least(int v) {
 
 int launch_segment_reduce(const float* values, int64_t value_stride, int32_t channels, int32_t mode, const WsView& W,
                           float* out, cudaStream_t stream) {
-  const unsigned blocks = 148 * 8;
+  const unsigned blocks = (unsigned)sm_count() * 8;
   const bool vec4 = (channels % 4 == 0) && (value_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(values) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (vec4) {
@@ -306,7 +306,8 @@ extern "C" int pcp_pfn_stages(const float* points, int64_t row_stride, int64_t n
     if (int rc = launch_pfn_tc(t, n_points, stream)) return rc;
   if ((stages & PCP_PFN_STAGE_LONG) && n_points > kSegRows) {
     const int64_t want = (n_points / (kSegRows + 1) + 7) / 8;
-    const unsigned blocks = (unsigned)(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4);
+    const int64_t cap = (int64_t)sm_count() * 4;
+    const unsigned blocks = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
     pfn_finish_long_kernel<<<blocks, 256, 0, stream>>>(W.hdr, W.long_table, W.long_acc, W.long_mean, packed_params, c_in,
                                                        desc->num_layers, pillar_features_out, pillar_mean_out);
     PCP_LAUNCH_CHECK("pfn_finish_long_kernel");

@@ -6,8 +6,6 @@
 // a CTA owns a (8 rows x 128 columns) patch of one frame, looks the pillar rank of its 1024 cells up
 // once, and for every group of 4 channels gathers 16-byte pieces of the pillar rows, transposes them in
 // registers and issues 128-bit streaming stores, 512 contiguous bytes per warp per (channel, row).
-#include <stdlib.h>
-
 #include "internal.cuh"
 
 namespace pcp {
@@ -26,7 +24,7 @@ __device__ __forceinline__ void st_stream_f4(float* p, float a, float b, float c
 template <bool kXMajor, int kUnroll, int kMinBlocks>
 __global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
 canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
-              float* __restrict__ canvas, int force_empty) {
+              float* __restrict__ canvas) {
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int y = blockIdx.y * kTileY + wy;
@@ -47,7 +45,6 @@ canvas_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map
       for (int i = 0; i < 4; ++i) r[i] = (x0 + i < nx) ? __ldg(m + i) : -1;
     }
   }
-  if (force_empty) { r[0] = r[1] = r[2] = r[3] = -1; }
   float* dst = canvas + ((int64_t)b * channels) * nxy + (int64_t)y * nx + x0;
   const bool vec = (x0 + 3 < nx) && ((nx & 3) == 0) && ((reinterpret_cast<uintptr_t>(canvas) & 15) == 0);
   const bool any = (r[0] >= 0) | (r[1] >= 0) | (r[2] >= 0) | (r[3] >= 0);
@@ -134,46 +131,6 @@ canvas_v8_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_
   }
 }
 
-// Persistent form of canvas_v8_kernel for steady-state pipelining: a fixed number of CTAs per SM walk the patches, so the
-// canvas of batch i leaves room on every SM for the voxelize kernels of batch i + 1 (tools/overlap_probe.py).
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
-canvas_v8p_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
-                  float* __restrict__ canvas, int tiles_x, int tiles_y, int frames) {
-  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  const int64_t nxy = (int64_t)nx * ny;
-  const int n_tiles = tiles_x * tiles_y * frames;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-    const int y = by * kTileY + wy;
-    const int x0 = bx * kTileX + lane * 4;
-    if (y >= ny || x0 >= nx) continue;
-    int r[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = __ldg(rank_map + b * nxy + (int64_t)(x0 + i) * ny + y);
-    float* dst = canvas + ((int64_t)b * channels) * nxy + (int64_t)y * nx + x0;
-    const bool any = (r[0] >= 0) | (r[1] >= 0) | (r[2] >= 0) | (r[3] >= 0);
-    if (!__any_sync(0xffffffffu, any)) {
-#pragma unroll 8
-      for (int c = 0; c < channels; ++c) st_stream_f4(dst + (int64_t)c * nxy, 0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
-    for (int c = 0; c < channels; c += 8) {
-      float8 v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (r[i] >= 0) v[i] = ldg_f8(pf + (int64_t)r[i] * channels + c);
-        else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[i].v[q] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) st_stream_f4(dst + (int64_t)(c + q) * nxy, v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]);
-    }
-  }
-}
-
 // generic path: canvas-ordered rank map from arbitrary voxel_coords rows (frame, z, y, x)
 __global__ void __launch_bounds__(256)
 coords_to_map_kernel(const int32_t* __restrict__ coords, int64_t P, int frames, int nx, int ny,
@@ -219,31 +176,14 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
   PCP_REQUIRE(pillar_features, PCP_E_INVALID, "pcp_bev_scatter_ws: null pillar_features");
   const WsView W = ws_view(const_cast<void*>(workspace), L);
   {
-    static const int variant = getenv("PCP_CANVAS_VARIANT") ? atoi(getenv("PCP_CANVAS_VARIANT")) : 0;   // tuning aid
     const dim3 cg = canvas_grid(grid->nx, grid->ny, num_frames);
     const int th = kTileY * 32;
     const bool fast8 = (channels % 8 == 0) && (grid->nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(pillar_features) & 31) == 0) &&
                        ((reinterpret_cast<uintptr_t>(canvas_out) & 15) == 0);
-    static const int persist = getenv("PCP_CANVAS_PERSIST") ? atoi(getenv("PCP_CANVAS_PERSIST")) : 0;   // CTAs per SM, 0 = off
-    if (persist > 0 && fast8) {
-      canvas_v8p_kernel<3><<<148 * persist, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out,
-                                                             (int)cg.x, (int)cg.y, (int)cg.z);
-    } else if ((variant == 0 || variant == 7) && fast8) {
+    if (fast8)
       canvas_v8_kernel<3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
-    } else if (variant == 8 && fast8) {
-      canvas_v8_kernel<4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
-    } else if (variant == 5) {      // diagnostic: pure write stream (every cell treated as empty)
-      PCP_CUDA(cudaMemsetAsync(canvas_out, 0, sizeof(float) * (size_t)num_frames * channels * grid->nx * grid->ny, stream));
-    } else if (variant == 1)
-      canvas_kernel<true, 2, 4><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
-    else if (variant == 2)
-      canvas_kernel<true, 4, 2><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
-    else if (variant == 3)
-      canvas_kernel<true, 4, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
-    else if (variant == 4)
-      canvas_kernel<true, 1, 6><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
     else
-      canvas_kernel<true, 2, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out, variant == 6);
+      canvas_kernel<true, 2, 3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
   }
   PCP_LAUNCH_CHECK("canvas_kernel<ws>");
   return 0;
@@ -252,7 +192,7 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
 namespace pcp {
 int launch_canvas_from_map(const float* rows, const int32_t* rank_map, int32_t channels, int32_t frames, int32_t nx,
                            int32_t ny, float* canvas, cudaStream_t stream) {
-  canvas_kernel<false, 2, 3><<<canvas_grid(nx, ny, frames), kTileY * 32, 0, stream>>>(rows, rank_map, channels, nx, ny, canvas, 0);
+  canvas_kernel<false, 2, 3><<<canvas_grid(nx, ny, frames), kTileY * 32, 0, stream>>>(rows, rank_map, channels, nx, ny, canvas);
   PCP_LAUNCH_CHECK("canvas_kernel<map>");
   return 0;
 }
@@ -275,7 +215,7 @@ extern "C" int pcp_bev_scatter(const float* pillar_features, const int32_t* voxe
     PCP_LAUNCH_CHECK("coords_to_map_kernel");
   }
   canvas_kernel<false, 2, 3><<<canvas_grid(nx, ny, num_frames), kTileY * 32, 0, stream>>>(pillar_features, cell_map_scratch,
-                                                                                     channels, nx, ny, canvas_out, 0);
+                                                                                     channels, nx, ny, canvas_out);
   PCP_LAUNCH_CHECK("canvas_kernel<map>");
   return 0;
 }
@@ -286,7 +226,7 @@ extern "C" int pcp_num_frames(const int32_t* voxel_coords, int64_t num_pillars, 
               "pcp_num_frames: bad argument");
   PCP_CUDA(cudaMemsetAsync(num_frames_out, 0, sizeof(int32_t), stream));
   if (num_pillars > 0) {
-    num_frames_kernel<<<148, 256, 0, stream>>>(voxel_coords, num_pillars, num_frames_out);
+    num_frames_kernel<<<sm_count(), 256, 0, stream>>>(voxel_coords, num_pillars, num_frames_out);
     PCP_LAUNCH_CHECK("num_frames_kernel");
   }
   return 0;

@@ -36,15 +36,31 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// mbarrier.try_wait suspends the thread in hardware until the phase completes or an implementation-defined time limit
+// expires.  PCP_MBAR_HINT > 0 passes an explicit suspend-time hint (ns): ptxas then adds a NANOSLEEP.SYNCS per failed
+// attempt, which wakes on every arrival at the barrier - with 256-arrival barriers that is hundreds of re-polls per slot.
+#ifndef PCP_MBAR_HINT
+#define PCP_MBAR_HINT 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if PCP_MBAR_HINT > 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of spinning
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)PCP_MBAR_HINT)
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -53,10 +69,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// named barrier among `nthreads` threads of the CTA (id 1..15; id 0 is __syncthreads)
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---- proxies / fences -----------------------------------------------------------------------------

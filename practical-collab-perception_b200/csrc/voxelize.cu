@@ -16,8 +16,6 @@
 //                       dense per-class lists (thread / warp / CTA per pillar); long pillars also get
 //                       their segment entries here.
 // No kernel synchronises with the host; the only data-dependent size (P) is read back by the caller.
-#include <stdlib.h>
-
 #include "internal.cuh"
 
 namespace pcp {
@@ -51,19 +49,11 @@ quantise_count_kernel(const float* __restrict__ points, int64_t stride, int64_t 
   int32_t k[kPtsPerThread], w[kPtsPerThread];
 #pragma unroll
   for (int u = 0; u < kPtsPerThread; ++u) {
-    const float qx = quantise(x[u], g.range_min_x, g.voxel_x);
-    const float qy = quantise(y[u], g.range_min_y, g.voxel_y);
-    // reference: (coords >= 0) & (coords < grid) on the int-cast floor (dynamic_pillar_vfe.py:99);
-    // qx, qy are integral floats, the float compare is the same predicate and is false for NaN.
-    const bool keep = (base + u * 256 < n) && (qx >= 0.f) && (qx < (float)g.nx) && (qy >= 0.f) && (qy < (float)g.ny);
     k[u] = -1; w[u] = 0;
-    if (keep) {
-      // points[:, 0].int() truncates toward zero (:104)
-      if (!(bf[u] > -1.f) || !(bf[u] < (float)frames)) {
-        atomicAdd(&hdr[PCP_COUNT_BAD_FRAME], 1);
-      } else {
-        k[u] = (int32_t)bf[u] * (g.nx * g.ny) + (int32_t)qx * g.ny + (int32_t)qy;
-      }
+    if (base + u * 256 < n) {
+      bool bad_frame;
+      k[u] = point_key(bf[u], x[u], y[u], frames, g, bad_frame);
+      if (bad_frame) atomicAdd(&hdr[PCP_COUNT_BAD_FRAME], 1);
     }
   }
 #pragma unroll
@@ -752,19 +742,15 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
   }
   if (n > 0) {
     const int64_t want = (n + kPrepThreads - 1) / kPrepThreads;
-    const unsigned blocks = (unsigned)(want < 148 * 4 ? want : 148 * 4);
+    const int64_t cap = (int64_t)sm_count() * 4;
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
     const bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
-    // PCP_PREP_SPLIT=1 (diagnostic): one launch per phase so that a launch list shows each phase's time
-    static const bool split = getenv("PCP_PREP_SPLIT") != nullptr;
-    for (int ph = 0; ph < (split ? 4 : 1); ++ph) {
-      const int mask = split ? (1 << ph) : 15;
-      if (vec4)
-        pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                     W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, mask);
-      else
-        pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                      W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, mask);
-    }
+    if (vec4)
+      pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                   W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
+    else
+      pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
+                                                                    W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
     PCP_LAUNCH_CHECK("pillar_prep_kernel");
   }
   return 0;
@@ -778,10 +764,10 @@ extern "C" size_t pcp_workspace_bytes(int64_t n_points, int32_t max_frames, int3
   return ws_layout(n_points, max_frames, nx, ny).total;
 }
 
-extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
-                            const pcp_grid* grid, void* workspace, size_t workspace_bytes,
-                            int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
-                            int64_t pillar_capacity, int32_t* counts_out, void* stream_) {
+extern "C" int pcp_voxelize_method(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
+                                   const pcp_grid* grid, void* workspace, size_t workspace_bytes,
+                                   int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
+                                   int64_t pillar_capacity, int32_t* counts_out, int32_t method, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PCP_REQUIRE(grid && workspace && voxel_coords_out && counts_out, PCP_E_INVALID, "pcp_voxelize: null argument");
   PCP_REQUIRE(n_points >= 0 && n_points < (1ll << 29), PCP_E_INVALID, "pcp_voxelize: n_points out of range (< 2^29)");
@@ -791,6 +777,8 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   PCP_REQUIRE(grid->nx <= 65535 && grid->ny <= 65535, PCP_E_UNSUPPORTED, "pcp_voxelize: nx, ny must be <= 65535");
   PCP_REQUIRE((int64_t)max_frames * grid->nx * grid->ny < (1ll << 31), PCP_E_UNSUPPORTED,
               "pcp_voxelize: frames*nx*ny must fit int32 (the reference's merge_coords is int32 too)");
+  PCP_REQUIRE(method == PCP_VOXELIZE_AUTO || method == PCP_VOXELIZE_HISTOGRAM || method == PCP_VOXELIZE_RADIX, PCP_E_INVALID,
+              "pcp_voxelize: unknown method %d", method);
   const WsLayout L = ws_layout(n_points, max_frames, grid->nx, grid->ny);
   PCP_REQUIRE(workspace_bytes >= L.total, PCP_E_WORKSPACE, "pcp_voxelize: workspace %zu < %zu bytes",
               workspace_bytes, L.total);
@@ -799,6 +787,21 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   PCP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PCP_E_INVALID, "pcp_voxelize: workspace not 256-byte aligned");
   PCP_REQUIRE((reinterpret_cast<uintptr_t>(voxel_coords_out) & 15) == 0, PCP_E_INVALID, "pcp_voxelize: voxel_coords_out not 16-byte aligned");
   const WsView W = ws_view(workspace, L);
+
+  // the radix path covers key spaces of at most 4 M cells and batches of at most 16.6 M rows (RadixPlan)
+  // AUTO is the histogram path: measured on the B200 it is the faster of the two at every size (profiles/r02_voxelize_*:
+  // 184 vs 392 us on the bench batch - the radix path's one-warp-per-bin stage is bound by its step-to-step latency chain
+  // and by the few dense bins at the frame centres).  The radix path stays selectable: it is the one whose means are the
+  // sequential row-order sums for pillars of ANY length.
+  if (method == PCP_VOXELIZE_RADIX) {
+    const RadixPlan rp = radix_plan(n_points, L.cells, sm_count());
+    PCP_REQUIRE(rp.ok, PCP_E_UNSUPPORTED,
+                "pcp_voxelize: the radix method covers 1 <= n_points <= %lld rows and at most %d cells",
+                (long long)kRxMaxChunks * kRxMaxChunkPts, kRxMaxBins << kRxMaxShift);
+    if (rp.ok)
+      return voxelize_radix(L, W, rp, points, row_stride, n_points, max_frames, *grid, point_pillar_out, voxel_coords_out,
+                            pillar_count_out, counts_out, stream);
+  }
 
   PCP_CUDA(cudaMemsetAsync(workspace, 0, L.clear_bytes, stream));
   if (n_points > 0) {
@@ -814,4 +817,12 @@ extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_p
   }
   return finish_grouping(L, W, n_points, grid->nx, grid->ny, points, row_stride, *grid, point_pillar_out, voxel_coords_out,
                          pillar_count_out, counts_out, stream);
+}
+
+extern "C" int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
+                            const pcp_grid* grid, void* workspace, size_t workspace_bytes,
+                            int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
+                            int64_t pillar_capacity, int32_t* counts_out, void* stream) {
+  return pcp_voxelize_method(points, row_stride, n_points, max_frames, grid, workspace, workspace_bytes, point_pillar_out,
+                             voxel_coords_out, pillar_count_out, pillar_capacity, counts_out, PCP_VOXELIZE_AUTO, stream);
 }

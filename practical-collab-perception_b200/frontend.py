@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
-import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
@@ -63,6 +62,9 @@ def device_guard(fn):
     return wrapped
 
 
+DEFAULT_VOXELIZE_METHOD = "auto"
+
+
 @dataclass
 class GridSpec:
     """Constants DynamicPillarVFE.__init__ derives (dynamic_pillar_vfe.py:77-89), evaluated with the
@@ -104,9 +106,16 @@ class FrontEnd:
     ``read_counts`` (the single D2H read of P the data-dependent output shape needs)."""
 
     def __init__(self, grid: GridSpec, c_raw: int, use_absolute_xyz: bool = True, with_distance: bool = False,
-                 num_filters: Sequence[int] = (64, 64)):
+                 num_filters: Sequence[int] = (64, 64), voxelize_method: Optional[str] = None):
+        """voxelize_method: "auto" (= "histogram", the faster one on the B200), "histogram", "radix" (stable radix sort;
+        raises outside the sizes it covers) or "radix_or_auto" (radix where it applies) - pcp_voxelize_method, identical
+        results; None = DEFAULT_VOXELIZE_METHOD."""
         self.lib = _lib.load()
         self.grid = grid
+        voxelize_method = voxelize_method or DEFAULT_VOXELIZE_METHOD
+        if voxelize_method not in _lib.VOXELIZE_METHODS:
+            raise ValueError(f"voxelize_method must be one of {sorted(_lib.VOXELIZE_METHODS)}")
+        self.voxelize_method = voxelize_method
         nf = list(num_filters)
         if len(nf) not in (1, 2) or nf[-1] != 64 or (len(nf) == 2 and nf[0] != 64):
             raise NotImplementedError(
@@ -147,6 +156,10 @@ class FrontEnd:
         return self.packed
 
     # ------------------------------------------------------------------ stages
+    def radix_applies(self, n_points: int, max_frames: int) -> bool:
+        """What PCP_VOXELIZE_RADIX covers (include/pcp_b200.h): 1 .. 16.6 M rows, at most 4 M cells."""
+        return 1 <= n_points <= 256 * 65024 and int(max_frames) * self.grid.nx * self.grid.ny <= 4096 * 1024
+
     def capacity(self, n_points: int, max_frames: int) -> int:
         return max(1, min(int(n_points), int(max_frames) * self.grid.nx * self.grid.ny))
 
@@ -174,9 +187,12 @@ class FrontEnd:
         counts = buf("counts", (_lib.PCP_COUNTS_LEN,), torch.int32)
         pp = buf("point_pillar", (max(n, 1),), torch.int32) if want_point_pillar else None
         pc = buf("pillar_count_buf", (cap,), torch.int32) if want_counts_per_pillar else None
-        rc = self.lib.pcp_voxelize(_ptr(points), stride, n, int(max_frames), C.byref(self.grid.c), _ptr(ws), ws.numel(),
-                                   _ptr(pp), _ptr(coords), _ptr(pc), coords.shape[0], _ptr(counts), _stream())
-        _lib.check(rc, "pcp_voxelize")
+        method = _lib.VOXELIZE_METHODS[self.voxelize_method]
+        if self.voxelize_method == "radix_or_auto" and not self.radix_applies(n, max_frames):
+            method = _lib.VOXELIZE_METHODS["auto"]
+        rc = self.lib.pcp_voxelize_method(_ptr(points), stride, n, int(max_frames), C.byref(self.grid.c), _ptr(ws), ws.numel(),
+                                          _ptr(pp), _ptr(coords), _ptr(pc), coords.shape[0], _ptr(counts), method, _stream())
+        _lib.check(rc, "pcp_voxelize_method")
         self.ws.n_points, self.ws.max_frames = n, int(max_frames)
         self.ws.generation += 1
         out["capacity"] = cap
@@ -286,8 +302,7 @@ class PipelinedFrontEnd:
     def _ensure_streams(self, device):
         if self._streams is None or self._streams[0].device != device:
             # lower number = higher priority; CUDA clamps to the device's range
-            pa, pb = (int(v) for v in os.environ.get("PCP_PIPE_PRIO", "-5,0").split(","))     # tuning aid
-            self._streams = (torch.cuda.Stream(device=device, priority=pa), torch.cuda.Stream(device=device, priority=pb))
+            self._streams = (torch.cuda.Stream(device=device, priority=-5), torch.cuda.Stream(device=device, priority=0))
         return self._streams
 
     @device_guard

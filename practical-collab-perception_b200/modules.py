@@ -102,10 +102,12 @@ class DynamicPillarVFE(VFETemplate):
         return self.num_filters[-1]
 
     # -- kernel-side state -------------------------------------------------------------------------
+    voxelize_method = None        # None (frontend.DEFAULT_VOXELIZE_METHOD) | "auto" | "radix" | "histogram": FrontEnd
+
     def _front_end(self) -> FrontEnd:
         if self._fe is None:
             self._fe = FrontEnd(self._grid, self.num_raw_point_features, self.use_absolute_xyz,
-                                self.with_distance, list(self.num_filters))
+                                self.with_distance, list(self.num_filters), voxelize_method=self.voxelize_method)
         return self._fe
 
     def _sync_params(self, device) -> None:

@@ -14,6 +14,21 @@ from tests.helpers import (assert_features_close, golden_cases, golden_cfg, laye
                            model_cfgs)
 
 pytestmark = pytest.mark.gpu
+
+
+class _RadixWhereItApplies(str):
+    """Marker value of the fixture below: FrontEnd falls back to "auto" for shapes the radix method does not cover."""
+
+
+@pytest.fixture(autouse=True, params=["auto", "radix"])
+def voxelize_method(request):
+    """Every test of this file runs on both compaction algorithms of pcp_voxelize_method: the dense-histogram path ("auto")
+    and the stable radix sort (wherever it applies).  Results must be identical."""
+    from pcp_b200 import frontend
+    old = frontend.DEFAULT_VOXELIZE_METHOD
+    frontend.DEFAULT_VOXELIZE_METHOD = "radix_or_auto" if request.param == "radix" else "auto"
+    yield request.param
+    frontend.DEFAULT_VOXELIZE_METHOD = old
 DEV = "cuda:0"
 
 
@@ -430,3 +445,54 @@ def test_stress_config_against_oracle(n_points, uniform):
     vfe, scat = build_modules(5, vox, rng, grid, sd)
     bd = run_modules(vfe, scat, pts, 1)
     check_against(bd, oracle_want(pts, cfg, layers_from_state_dict(sd)), pts.shape[0])
+
+
+@pytest.mark.parametrize("n_frames,n_points,voxel,ego", [(8, 300000, None, False), (1, 32768, None, True), (1, 4000000, [0.1, 0.1, 8.0], False),
+                                                         (3, 777, None, False), (16, 1000, None, False)])
+def test_radix_and_histogram_compaction_agree_bit_for_bit(n_frames, n_points, voxel, ego):
+    """pcp_voxelize_method: the stable radix sort and the dense-histogram path give the same pillars, point->pillar map,
+    counts, per-pillar means (sequential sums in row order on both), PFN features, canvas and segment reductions."""
+    from pcp_b200.frontend import FrontEnd, GridSpec
+    c_raw = 11 if ego else 5
+    syn, rng, vox, grid, sd, cfg = v2x_setup(c_raw, voxel=voxel)
+    pts = syn.batch_of_frames(n_frames, n_points, 17, ego_columns=ego).to(DEV)
+    vals = torch.randn(pts.shape[0], 8, generator=torch.Generator().manual_seed(5)).to(DEV)
+    bn = lambda i: [sd[f"pfn_layers.{i}.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")]
+    res = {}
+    for method in ("radix", "histogram"):
+        fe = FrontEnd(GridSpec(vox, rng, grid), c_raw, voxelize_method=method)
+        fe.pack_params(sd["pfn_layers.0.linear.weight"].to(DEV), bn(0), sd["pfn_layers.1.linear.weight"].to(DEV), bn(1))
+        out = fe.voxelize(pts, n_frames, want_point_pillar=True, want_counts_per_pillar=True)
+        fe.pfn(pts, out, want_mean=True)
+        canvas = fe.scatter_ws(out["pillar_features_buf"], n_frames)
+        smax, smean = fe.segment_reduce(vals, "max"), fe.segment_reduce(vals, "mean")
+        torch.cuda.synchronize()
+        counts = fe.read_counts(out)
+        p = int(counts[0])
+        res[method] = dict(counts=counts.copy(), vc=out["voxel_coords_buf"][:p].clone(), pp=out["point_pillar"][:pts.shape[0]].clone(),
+                           pc=out["pillar_count_buf"][:p].clone(), pf=out["pillar_features_buf"][:p].clone(),
+                           mean=out["pillar_mean_buf"][:p].clone(), canvas=canvas, smax=smax[:p].clone(), smean=smean[:p].clone())
+    a, b = res["radix"], res["histogram"]
+    assert np.array_equal(a["counts"], b["counts"]), (a["counts"], b["counts"])
+    assert a["counts"][0] > 0
+    giant = int(a["counts"][4]) > 4096                 # the histogram path sums pillars above 4096 rows in arrival order
+    for k in ("vc", "pp", "pc", "mean", "pf", "canvas", "smax", "smean"):
+        if giant and k in ("mean", "pf", "canvas", "smean"):
+            assert_features_close(a[k].cpu().numpy(), b[k].cpu().numpy(), k)
+        else:
+            assert torch.equal(a[k], b[k]), k
+
+
+def test_radix_method_reports_what_it_does_not_cover():
+    from pcp_b200.frontend import FrontEnd, GridSpec
+    syn, rng, vox, grid, sd, cfg = v2x_setup(5)
+    pts = syn.batch_of_frames(1, 1000, 3).to(DEV)
+    fe = FrontEnd(GridSpec(vox, rng, grid), 5, voxelize_method="radix")
+    with pytest.raises(RuntimeError, match="radix method covers"):
+        fe.voxelize(pts, 40)                           # 40 x 512 x 512 cells > 4 M: histogram path only
+    auto = FrontEnd(GridSpec(vox, rng, grid), 5, voxelize_method="auto")
+    out = auto.voxelize(pts, 40)
+    torch.cuda.synchronize()
+    assert int(auto.read_counts(out)[0]) > 0
+    with pytest.raises(ValueError):
+        FrontEnd(GridSpec(vox, rng, grid), 5, voxelize_method="sort")

@@ -12,6 +12,23 @@ from oracle import pillar_oracle as po
 from tests.helpers import assert_features_close, layers_from_state_dict, model_cfgs
 
 pytestmark = pytest.mark.gpu
+
+
+class _RadixWhereItApplies(str):
+    """Marker value of the fixture below: FrontEnd falls back to "auto" for shapes the radix method does not cover."""
+
+
+@pytest.fixture(autouse=True, params=["auto", "radix"])
+def voxelize_method(request):
+    """Every test of this file runs on both compaction algorithms of pcp_voxelize_method: the dense-histogram path ("auto")
+    and the stable radix sort (wherever it applies).  Results must be identical."""
+    from pcp_b200 import frontend
+    old = frontend.DEFAULT_VOXELIZE_METHOD
+    frontend.DEFAULT_VOXELIZE_METHOD = "radix_or_auto" if request.param == "radix" else "auto"
+    yield request.param
+    frontend.DEFAULT_VOXELIZE_METHOD = old
+
+
 DEV = "cuda:0"
 SETTINGS = dict(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
 
@@ -38,6 +55,12 @@ _modules = {}
 
 
 def modules():
+    from pcp_b200 import frontend
+    return _modules_for(frontend.DEFAULT_VOXELIZE_METHOD)
+
+
+def _modules_for(method, _cache={}):
+    _modules = _cache.setdefault(method, {})        # the module's FrontEnd binds the method when it is first used
     if not _modules:
         import pcp_b200
         from pcp_b200 import synthetic as syn
@@ -110,7 +133,7 @@ def test_dynamic_mean_vfe_matches_oracle(seed, n, frames, c, snap):
     assert torch.equal(bd["voxel_features"].cpu(), want["voxel_features"])
 
 
-# ---- late-fusion NMS: random clustered boxes vs the float64 oracle ------------------------------------
+# ---- late-fusion NMS: random clustered boxes vs the oracle ------------------------------------
 def _boxes(seed, n_obj, per_obj, degenerate):
     g = torch.Generator().manual_seed(seed)
     rows = []
@@ -140,12 +163,15 @@ def test_nms_random_scenes_against_the_oracle(seed, n_obj, per_obj, thresh, dege
     from oracle import nms_oracle as nmo
     b = _boxes(seed, max(n_obj, 6 if degenerate else 1), per_obj, degenerate)
     bn = b.numpy().astype(np.float64)
-    iou = nmo.boxes_iou_bev(bn[:, :7], bn[:, :7])
+    # the product follows the reference kernel's procedure (corner test with a 1e-2 m margin): the oracle's float32
+    # restatement of that procedure matches it to rounding, the exact float64 area to the kernel's own error
+    iou = nmo.ref_iou_f32(b.numpy()[:, :7], b.numpy()[:, :7])
     got_iou = pcp_b200.boxes_iou_bev(b[:, :7].contiguous().to(DEV), b[:, :7].contiguous().to(DEV)).cpu().numpy()
     assert np.abs(got_iou - iou).max() < 1e-5
+    assert np.abs(got_iou - nmo.boxes_iou_bev(bn[:, :7], bn[:, :7])).max() < 5e-3
     off = iou[~np.eye(len(iou), dtype=bool)]
     if off.size and np.any(np.abs(off - thresh) < 1e-4):
-        return                                                    # a pair sits on the threshold: fp32 vs fp64 may differ
+        return                                                    # a pair sits on the threshold: the last bits decide
     cfg = pcp_b200.CfgDict(NMS_TYPE="nms_gpu", NMS_THRESH=thresh, NMS_PRE_MAXSIZE=pre, NMS_POST_MAXSIZE=post)
     bd = b.to(DEV)
     sel, sc = pcp_b200.class_agnostic_nms(bd[:, 7], bd[:, :7], cfg, score_thresh=score_thresh)
