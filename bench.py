@@ -409,7 +409,10 @@ def run_ours(args):
         stage_roofline[name] = {"ms": stage_ms[j], "ms_alone": serial_stage_ms[j], "algorithmic_bytes": alg[name], "achieved": ach,
                                 "frac": ach / peak, "frac_alone": alg[name] / (serial_stage_ms[j] * 1e-3) / 1e9 / peak,
                                 "traffic": ncu_traffic(name)}
-    dom = max(range(3), key=lambda j: stage_ms[j])
+    # The contract's single `roofline` object is for ONE kernel: the longest-running kernel on the step's critical path.  The
+    # critical path is the graph's main branch - the five voxelize launches (the longest of them, pillar_prep, is 58 us alone)
+    # and the PFN kernel; the canvas kernel runs on the side branch, hidden beside the next batch's voxelize launches.
+    dom = 1
     dom_name = stage_names[dom]
     achieved = stage_roofline[dom_name]["achieved"]
     chain_achieved = chain_bytes / (ms_per_step * 1e-3) / 1e9
@@ -472,48 +475,76 @@ def run_ours(args):
     dev_in = [torch.empty_like(host_batches[0], device=dev) for _ in range(n_in)]     # input ring: no allocation per step
     in_free = [None] * n_in                                                           # "the step that read buffer k is done"
 
-    def prefetch(i):
-        k = i % n_in
-        with torch.cuda.stream(copy_stream):
-            if in_free[k] is not None:
-                copy_stream.wait_event(in_free[k])
-            dev_in[k].copy_(host_batches[i & 1], non_blocking=True)      # H2D from pinned memory
-            e = torch.cuda.Event()
-            e.record(copy_stream)
-        return dev_in[k], e
+    # What crosses PCIe: the columns the pillar encoder reads (x, y, z, intensity, time: NUM_RAW_POINT_FEATURES = 5), frames
+    # back to back, + one row offset per frame - what pcp_b200.collate_points builds in place of collate_batch's np.pad +
+    # np.concatenate (dataset.py:224-229) in the data-loader workers, outside the model step like collate_batch itself.
+    # pcp_b200.load_points_to_gpu (the replacement of load_data_to_gpu, models/__init__.py:23-34) copies it and rebuilds
+    # the (N, 1 + C) rows on the device.  `e2e_full_rows` ships collate_batch's own (N, 8) fp32 rows instead.
+    from pcp_b200.loader import collate_points
+    packed = []
+    for h in host_batches:
+        hn = h.numpy()
+        frames = [hn[b * POINTS_PER_FRAME:(b + 1) * POINTS_PER_FRAME, 1:] for b in range(B)]
+        packed.append(collate_points(frames, columns=tuple(range(C_RAW))))
 
-    def e2e_loop(n):
-        nxt = prefetch(0)
+    from pcp_b200.loader import PointsPrefetcher
+    pre = PointsPrefetcher(dev, depth=n_in)
+
+    def e2e_loop(n, use_packed):
+        def start(i):
+            if use_packed:
+                pre.submit(packed[i & 1])                               # H2D of the shipped columns on the copy stream
+                return None
+            k = i % n_in
+            with torch.cuda.stream(copy_stream):
+                if in_free[k] is not None:
+                    copy_stream.wait_event(in_free[k])
+                dev_in[k].copy_(host_batches[i & 1], non_blocking=True)   # H2D of collate_batch's full rows
+                e = torch.cuda.Event()
+                e.record(copy_stream)
+            return dev_in[k], e
+
+        nxt = start(0)
         for i in range(n):
-            pts, ready = nxt
+            cur_in = nxt
             if i + 1 < n:
-                nxt = prefetch(i + 1)
+                nxt = start(i + 1)
             cur = torch.cuda.current_stream()
-            cur.wait_event(ready)
+            if use_packed:
+                pts = pre.get()                                          # waits for the copy, rebuilds the rows on this stream
+            else:
+                pts, ready = cur_in
+                cur.wait_event(ready)
             with torch.no_grad():
                 bd = scat(vfe({"points": pts, "batch_size": B}))         # vfe reads the 32-byte counts block back
             done = torch.cuda.Event()
             done.record(cur)
             in_free[i % n_in] = done
-            assert bd["spatial_features"].shape[0] == B and bd["voxel_coords"].shape[0] > 0
+            assert bd["spatial_features"].shape[0] == B and bd["voxel_coords"].shape[0] == n_pillars_expect[i & 1]
         for k in range(n_in):
             in_free[k] = None
 
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_loop(2)
-    barrier()
-    t0 = time.perf_counter()
-    s0, s1 = ev(), ev()
-    s0.record()
-    e2e_loop(e2e_steps)
-    s1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(s0.elapsed_time(s1), (time.perf_counter() - t0) * 1e3)
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+
+    def e2e_measure(use_packed):
+        e2e_loop(2, use_packed)
+        barrier()
+        t0 = time.perf_counter()
+        s0, s1 = ev(), ev()
+        s0.record()
+        e2e_loop(e2e_steps, use_packed)
+        s1.record()
+        torch.cuda.synchronize()
+        ms = max(s0.elapsed_time(s1), (time.perf_counter() - t0) * 1e3)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return world * B * e2e_steps / (ms * 1e-3)
+
+    e2e_full_value = e2e_measure(False)
+    e2e_value = e2e_measure(True)
+    e2e_h2d = int(packed[0].data.numel() * 4 + packed[0].frame_offsets.numel() * 4)
 
     line = None
     if rank == 0:
@@ -542,17 +573,24 @@ def run_ours(args):
             "eager_pipelined_ms_per_step": eager_ms_per_step,
             "serial": {"ms_per_step": serial_ms_per_step, "stage_ms": dict(zip(stage_names, serial_stage_ms)), "steps": serial_steps,
                        "note": "one batch at a time on one stream (no overlap between batches)"},
-            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom_name,
+                         "rule": "longest single kernel on the critical path (main graph branch: voxelize launches + PFN); "
+                                 "every stage is in roofline_stages, the whole chain in roofline_chain",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
                          "algorithmic_bytes": alg[dom_name]},
             "roofline_chain": {"bound": "hbm", "achieved": chain_achieved, "peak": peak, "unit": "GB/s",
                                "frac": chain_achieved / peak, "algorithmic_bytes": chain_bytes,
                                "note": "SURVEY 8d bytes of the whole voxelize+PFN+scatter chain / step time"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_batches[0].numel() * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": 4 * _lib.PCP_COUNTS_LEN, "steps": e2e_steps,
-                    "api": "DynamicPillarVFE.forward + PointPillarScatter.forward on pinned host points; the next step's "
-                           "H2D copy is prefetched on a copy stream"},
+                    "api": "PointsPrefetcher(collate_points(frames, columns = the 5 raw point features)) -> "
+                           "DynamicPillarVFE.forward -> PointPillarScatter.forward; pinned host input, the next step's H2D copy "
+                           "runs on a copy stream under this step's kernels, the (N, 1 + C) rows are rebuilt on the device"},
+            "e2e_full_rows": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": int(host_batches[0].numel() * 4),
+                              "d2h_bytes_per_step": 4 * _lib.PCP_COUNTS_LEN, "steps": e2e_steps,
+                              "api": "collate_batch's (N, 8) fp32 rows copied whole, then the same two modules"},
             # quantise, tile sums, cell scan, place, pillar prep, pfn, long-pillar finish, canvas (+1 memset) per step
             "gpu_launches": 8 * args.steps,
             **gather,

@@ -211,6 +211,21 @@ int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreg
               int32_t with_batch_col, float batch_idx, float* rows_out, int64_t out_stride,
               int32_t* box_idx_out, void* stream);
 
+/*
+ * pcp_modar() over per-agent record arrays, with nothing gathered on the host side: box_ptrs / fg_ptrs are DEVICE arrays of
+ * num_agents device pointers (agent a's (M_a, 9) boxes and (F_a, 13) foreground records; fg_ptrs may be NULL = no
+ * propagation, an agent without records has F_a = 0), box_offsets / fg_offsets their prefix sums as above (rows_out and
+ * box_idx_out are indexed through them), and max_sweep_idx is read from device memory (pcp_column_max of the ego cloud's
+ * sweep column, v2x_sim_dataset_ego.py:174) - no device->host synchronisation anywhere on the exchange path.
+ */
+int pcp_modar_agents(const float* const* box_ptrs, const int32_t* box_offsets, const float* const* fg_ptrs,
+                     const int32_t* fg_offsets, const double* se3, int32_t num_agents, int32_t max_boxes_per_agent,
+                     int32_t max_fg_per_agent, float scale, const float* max_sweep_idx_dev, int32_t with_batch_col,
+                     float batch_idx, float* rows_out, int64_t out_stride, int32_t* box_idx_out, void* stream);
+
+/* max over the rows of one column of a row-major fp32 matrix into *max_out (device); 0 for an empty matrix. */
+int pcp_column_max(const float* rows, int64_t row_stride, int64_t n_rows, int32_t column, float* max_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * the callers and data formats either side of the pillar path.
  * ------------------------------------------------------------------------------------------------------------ */
@@ -288,6 +303,21 @@ int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols
                           const int32_t* agent_offsets, const double* se3, int32_t num_agents,
                           const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
                           float* rows_out, int64_t out_stride, int32_t* count_out, void* stream);
+
+/*
+ * Device half of the points loader.  Replaces, for batch_dict['points'], the frame-index padding + concatenation of
+ * collate_batch (pcdet/datasets/dataset.py:224-229) and the .float().cuda() of load_data_to_gpu (pcdet/models/__init__.py:
+ * 23-34): the host ships only the per-point columns a consumer reads (x, y, z, intensity, time = 20 of the 28 bytes of an
+ * early-fusion row; the frame index travels as one row offset per frame), this entry rebuilds the (N, 1 + C) rows.
+ *   packed          (n_points, n_packed_cols) fp32 device: the shipped columns, frames back to back
+ *   col_index_host  HOST int32[n_packed_cols]: which per-point column (0-based, frame-index column not counted) each is
+ *   frame_offsets   device int32[num_frames + 1]: first row of every frame, [num_frames] = n_points
+ *   rows_out        (n_points, out_stride >= 1 + n_point_cols): column 0 = frame index, shipped columns in place, others 0
+ */
+#define PCP_UNPACK_MAX_COLS 16
+int pcp_unpack_points(const float* packed, int32_t n_packed_cols, const int32_t* col_index_host, int64_t n_points,
+                      const int32_t* frame_offsets, int32_t num_frames, int32_t n_point_cols, float* rows_out,
+                      int64_t out_stride, void* stream);
 
 /*
  * Pairwise BEV IoU of rotated boxes [x, y, z, dx, dy, dz, heading]: iou3d_nms_utils.boxes_iou_bev,

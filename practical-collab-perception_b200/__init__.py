@@ -30,6 +30,9 @@ def __getattr__(name):
     if name in ("fuse_agent_points",):
         from . import early_fusion
         return getattr(early_fusion, name)
+    if name in ("collate_points", "load_points_to_gpu", "PackedPoints", "PointsPrefetcher"):
+        from . import loader
+        return getattr(loader, name)
     if name in ("FrontEnd",):
         from . import frontend
         return getattr(frontend, name)

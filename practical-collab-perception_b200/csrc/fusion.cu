@@ -133,6 +133,78 @@ fuse_write_kernel(const FuseArgs A, int64_t n, const int32_t* __restrict__ block
 
 }  // namespace pcp
 
+namespace pcp {
+
+// ------------------------------------------------------------------------------------------------
+// device half of the points loader (pcdet/models/__init__.py:23-34 load_data_to_gpu for batch_dict['points'], after the
+// collate step of pcdet/datasets/dataset.py:224-229): the host ships only the per-point columns a consumer reads, frames
+// back to back, plus one row offset per frame; this kernel rebuilds the (N, 1 + C) rows collate_batch would have produced -
+// frame index in column 0, the shipped columns at their original places, zeros elsewhere.
+// ------------------------------------------------------------------------------------------------
+struct UnpackCols { int32_t k; int32_t col[PCP_UNPACK_MAX_COLS]; };
+
+__global__ void __launch_bounds__(256)
+unpack_points_kernel(const float* __restrict__ packed, int64_t n, const int32_t* __restrict__ frame_off, int32_t frames,
+                     const UnpackCols cols, int32_t n_out_cols, float* __restrict__ out, int64_t out_stride) {
+  extern __shared__ int32_t s_off[];                    // [frames + 1]
+  for (int i = threadIdx.x; i <= frames; i += blockDim.x) s_off[i] = __ldg(frame_off + i);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = frames;                              // frame f: s_off[f] <= i < s_off[f + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (i >= s_off[mid]) lo = mid; else hi = mid;
+  }
+  float v[PCP_UNPACK_MAX_COLS];
+#pragma unroll
+  for (int j = 0; j < PCP_UNPACK_MAX_COLS; ++j)
+    if (j < cols.k) v[j] = __ldg(packed + i * cols.k + j);
+  float* row = out + i * out_stride;
+  if (n_out_cols == 8 && (out_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    float r[8] = {(float)lo, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < PCP_UNPACK_MAX_COLS; ++j)
+      if (j < cols.k) {
+#pragma unroll
+        for (int c = 1; c < 8; ++c)
+          if (cols.col[j] + 1 == c) r[c] = v[j];
+      }
+    reinterpret_cast<float4*>(row)[0] = make_float4(r[0], r[1], r[2], r[3]);
+    reinterpret_cast<float4*>(row)[1] = make_float4(r[4], r[5], r[6], r[7]);
+  } else {
+    row[0] = (float)lo;
+    for (int c = 1; c < n_out_cols; ++c) row[c] = 0.f;
+    for (int j = 0; j < cols.k; ++j) row[1 + cols.col[j]] = v[j];
+  }
+}
+
+}  // namespace pcp
+
+extern "C" int pcp_unpack_points(const float* packed, int32_t n_packed_cols, const int32_t* col_index_host, int64_t n_points,
+                                 const int32_t* frame_offsets, int32_t num_frames, int32_t n_point_cols, float* rows_out,
+                                 int64_t out_stride, void* stream_) {
+  using namespace pcp;       // (defined ahead of the file-wide using-directive below)
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(n_points >= 0 && num_frames > 0 && num_frames <= 8192, PCP_E_INVALID, "pcp_unpack_points: bad n_points / num_frames");
+  PCP_REQUIRE(n_packed_cols > 0 && n_packed_cols <= PCP_UNPACK_MAX_COLS && n_point_cols >= n_packed_cols, PCP_E_INVALID,
+              "pcp_unpack_points: 1 <= shipped columns <= %d <= point columns", PCP_UNPACK_MAX_COLS);
+  PCP_REQUIRE(out_stride >= 1 + n_point_cols, PCP_E_INVALID, "pcp_unpack_points: out_stride < 1 + n_point_cols");
+  if (n_points == 0) return 0;
+  PCP_REQUIRE(packed && col_index_host && frame_offsets && rows_out, PCP_E_INVALID, "pcp_unpack_points: null argument");
+  UnpackCols cols{};
+  cols.k = n_packed_cols;
+  for (int j = 0; j < n_packed_cols; ++j) {
+    PCP_REQUIRE(col_index_host[j] >= 0 && col_index_host[j] < n_point_cols, PCP_E_INVALID, "pcp_unpack_points: column index out of range");
+    cols.col[j] = col_index_host[j];
+  }
+  const unsigned blocks = (unsigned)((n_points + 255) / 256);
+  unpack_points_kernel<<<blocks, 256, sizeof(int32_t) * (size_t)(num_frames + 1), stream>>>(
+      packed, n_points, frame_offsets, num_frames, cols, 1 + n_point_cols, rows_out, out_stride);
+  PCP_LAUNCH_CHECK("unpack_points_kernel");
+  return 0;
+}
+
 using namespace pcp;
 
 extern "C" size_t pcp_fuse_scratch_bytes(int64_t n_points) {

@@ -30,8 +30,9 @@ __device__ __forceinline__ bool point_in_box(float x, float y, float z, const Bo
 
 // 1 + 2. membership of every foreground point: grid (point chunks, agents); the agent's boxes sit in shared memory
 __global__ void __launch_bounds__(256)
-modar_membership_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_off,
-                        const float* __restrict__ fg, const int32_t* __restrict__ fg_off,
+modar_membership_kernel(const float* __restrict__ boxes_cat, const float* const* __restrict__ box_ptrs,
+                        const int32_t* __restrict__ box_off, const float* __restrict__ fg_cat,
+                        const float* const* __restrict__ fg_ptrs, const int32_t* __restrict__ fg_off,
                         int32_t* __restrict__ box_idx_out) {
   __shared__ BoxS s_box[kMaxBoxes];
   const int a = blockIdx.y;
@@ -40,9 +41,12 @@ modar_membership_kernel(const float* __restrict__ boxes, const int32_t* __restri
   const int tid = threadIdx.x;
   if ((int64_t)blockIdx.x * blockDim.x >= F) return;
   const int i = blockIdx.x * blockDim.x + tid;
+  // records either concatenated (one array + offsets) or per agent (a table of device pointers: nothing is copied together)
+  const float* boxes = box_ptrs ? box_ptrs[a] : boxes_cat + (int64_t)b0 * 9;
+  const float* fg = fg_ptrs ? fg_ptrs[a] : fg_cat + (int64_t)f0 * 13;
   float x = 0.f, y = 0.f, z = 0.f;
   if (i < F) {
-    const float* p = fg + (int64_t)(f0 + i) * 13;
+    const float* p = fg + (int64_t)i * 13;
     x = p[0]; y = p[1]; z = p[2];
   }
   int hit = -1;
@@ -50,7 +54,7 @@ modar_membership_kernel(const float* __restrict__ boxes, const int32_t* __restri
     const int mc = min(kMaxBoxes, M - mb);
     __syncthreads();
     for (int k = tid; k < mc; k += blockDim.x) {
-      const float* bx = boxes + (int64_t)(b0 + mb + k) * 9;
+      const float* bx = boxes + (int64_t)(mb + k) * 9;
       BoxS s;
       s.cx = bx[0]; s.cy = bx[1]; s.cz = bx[2]; s.hx = bx[3]; s.hy = bx[4]; s.hz = bx[5];
       const float rz = bx[6];
@@ -73,17 +77,22 @@ modar_membership_kernel(const float* __restrict__ boxes, const int32_t* __restri
 constexpr int kIdxPanel = 8192;
 
 __global__ void __launch_bounds__(256)
-modar_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_off,
-                  const float* __restrict__ fg, const int32_t* __restrict__ fg_off, const double* __restrict__ se3,
-                  float scale, float max_sweep_idx, int with_batch_col, float batch_idx,
+modar_rows_kernel(const float* __restrict__ boxes_cat, const float* const* __restrict__ box_ptrs,
+                  const int32_t* __restrict__ box_off, const float* __restrict__ fg_cat,
+                  const float* const* __restrict__ fg_ptrs, const int32_t* __restrict__ fg_off, int has_fg,
+                  const double* __restrict__ se3, float scale, float max_sweep_idx_arg,
+                  const float* __restrict__ max_sweep_idx_dev, int with_batch_col, float batch_idx,
                   float* __restrict__ rows_out, int64_t out_stride, const int32_t* __restrict__ box_idx) {
   __shared__ int32_t s_idx[kIdxPanel];
   const int a = blockIdx.y;
   const int b0 = box_off[a], M = box_off[a + 1] - b0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   if (blockIdx.x * nwarp >= M) return;
-  const bool propagate = (fg != nullptr) && (scale != 0.f);
+  const bool propagate = has_fg && (scale != 0.f);
   const int f0 = propagate ? fg_off[a] : 0, F = propagate ? fg_off[a + 1] - f0 : 0;
+  const float* boxes = box_ptrs ? box_ptrs[a] : boxes_cat + (int64_t)b0 * 9;
+  const float* fg = !propagate ? nullptr : (fg_ptrs ? fg_ptrs[a] : fg_cat + (int64_t)f0 * 13);
+  const float max_sweep_idx = max_sweep_idx_dev ? __ldg(max_sweep_idx_dev) : max_sweep_idx_arg;
   const double* T = se3 + 12 * a;
   const double yaw_T = atan2(T[4], T[0]);  // rotation_matrix_to_yaw: arctan2(R10, R00), nuscenes_temporal_utils.py:28-29
   const int k = blockIdx.x * nwarp + warp;
@@ -102,7 +111,7 @@ modar_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ b
         if (m == 0) continue;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (mine) {
-          const float* p = fg + (int64_t)(f0 + p0 + i) * 13;
+          const float* p = fg + (int64_t)(p0 + i) * 13;
           fx = p[10]; fy = p[11]; fz = p[12];     // flow3 = last three columns (v2x_sim_dataset_ego.py:213)
         }
         cnt += __popc(m);
@@ -117,7 +126,7 @@ modar_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ b
     }
   }
   if (k >= M) return;
-  const float* bx = boxes + (int64_t)(b0 + k) * 9;
+  const float* bx = boxes + (int64_t)k * 9;
   float ox = 0.f, oy = 0.f, oz = 0.f;
   if (cnt > 0) {
     const float c = (float)cnt;
@@ -146,33 +155,82 @@ modar_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ b
   }
 }
 
+// max of one column of a row-major fp32 matrix (ego_points[:, sweep column].max(), v2x_sim_dataset_ego.py:174), one CTA;
+// an empty matrix gives 0 (the host wrapper's convention)
+__global__ void __launch_bounds__(1024)
+column_max_kernel(const float* __restrict__ rows, int64_t stride, int64_t n, int32_t col, float* __restrict__ out) {
+  __shared__ float s_red[32];
+  float m = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, __ldg(rows + i * stride + col));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : -INFINITY;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (threadIdx.x == 0) *out = (n > 0) ? m : 0.f;
+  }
+}
+
 }  // namespace pcp
 
 using namespace pcp;
+
+static int modar_launch(const float* boxes, const float* const* box_ptrs, const int32_t* box_offsets, const float* foreground,
+                        const float* const* fg_ptrs, const int32_t* fg_offsets, const double* se3, int32_t num_agents,
+                        int32_t max_boxes_per_agent, int32_t max_fg_per_agent, float scale, float max_sweep_idx,
+                        const float* max_sweep_idx_dev, int32_t with_batch_col, float batch_idx, float* rows_out,
+                        int64_t out_stride, int32_t* box_idx_out, cudaStream_t stream) {
+  PCP_REQUIRE(num_agents >= 0, PCP_E_INVALID, "pcp_modar: num_agents < 0");
+  if (num_agents == 0) return 0;
+  PCP_REQUIRE((boxes || box_ptrs) && box_offsets && se3 && rows_out, PCP_E_INVALID, "pcp_modar: null argument");
+  PCP_REQUIRE(out_stride >= 13 + (with_batch_col ? 1 : 0), PCP_E_INVALID, "pcp_modar: out_stride too small");
+  const bool has_fg = foreground != nullptr || fg_ptrs != nullptr;
+  PCP_REQUIRE(!has_fg || (fg_offsets && box_idx_out), PCP_E_INVALID,
+              "pcp_modar: foreground given without fg_offsets / box_idx_out");
+  PCP_REQUIRE(max_boxes_per_agent >= 0 && max_fg_per_agent >= 0 && num_agents <= 65535, PCP_E_INVALID, "pcp_modar: bad sizes");
+  if (max_boxes_per_agent == 0) return 0;
+  const bool propagate = has_fg && scale != 0.f && max_fg_per_agent > 0;
+  if (propagate) {
+    const dim3 grid((unsigned)((max_fg_per_agent + 255) / 256), (unsigned)num_agents);
+    modar_membership_kernel<<<grid, 256, 0, stream>>>(boxes, box_ptrs, box_offsets, foreground, fg_ptrs, fg_offsets, box_idx_out);
+    PCP_LAUNCH_CHECK("modar_membership_kernel");
+  }
+  const dim3 grid((unsigned)((max_boxes_per_agent + 7) / 8), (unsigned)num_agents);
+  modar_rows_kernel<<<grid, 256, 0, stream>>>(boxes, box_ptrs, box_offsets, foreground, fg_ptrs, fg_offsets, propagate ? 1 : 0, se3,
+                                              scale, max_sweep_idx, max_sweep_idx_dev, with_batch_col, batch_idx, rows_out,
+                                              out_stride, box_idx_out);
+  PCP_LAUNCH_CHECK("modar_rows_kernel");
+  return 0;
+}
 
 extern "C" int pcp_modar(const float* boxes, const int32_t* box_offsets, const float* foreground,
                          const int32_t* fg_offsets, const double* se3, int32_t num_agents, int32_t max_boxes_per_agent,
                          int32_t max_fg_per_agent, float scale,
                          float max_sweep_idx, int32_t with_batch_col, float batch_idx, float* rows_out,
                          int64_t out_stride, int32_t* box_idx_out, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PCP_REQUIRE(num_agents >= 0, PCP_E_INVALID, "pcp_modar: num_agents < 0");
-  if (num_agents == 0) return 0;
-  PCP_REQUIRE(boxes && box_offsets && se3 && rows_out, PCP_E_INVALID, "pcp_modar: null argument");
-  PCP_REQUIRE(out_stride >= 13 + (with_batch_col ? 1 : 0), PCP_E_INVALID, "pcp_modar: out_stride too small");
-  PCP_REQUIRE(!foreground || (fg_offsets && box_idx_out), PCP_E_INVALID,
-              "pcp_modar: foreground given without fg_offsets / box_idx_out");
-  PCP_REQUIRE(max_boxes_per_agent >= 0 && max_fg_per_agent >= 0 && num_agents <= 65535, PCP_E_INVALID, "pcp_modar: bad sizes");
-  if (max_boxes_per_agent == 0) return 0;
-  const bool propagate = foreground != nullptr && scale != 0.f && max_fg_per_agent > 0;
-  if (propagate) {
-    const dim3 grid((unsigned)((max_fg_per_agent + 255) / 256), (unsigned)num_agents);
-    modar_membership_kernel<<<grid, 256, 0, stream>>>(boxes, box_offsets, foreground, fg_offsets, box_idx_out);
-    PCP_LAUNCH_CHECK("modar_membership_kernel");
-  }
-  const dim3 grid((unsigned)((max_boxes_per_agent + 7) / 8), (unsigned)num_agents);
-  modar_rows_kernel<<<grid, 256, 0, stream>>>(boxes, box_offsets, propagate ? foreground : nullptr, fg_offsets, se3, scale,
-                                              max_sweep_idx, with_batch_col, batch_idx, rows_out, out_stride, box_idx_out);
-  PCP_LAUNCH_CHECK("modar_rows_kernel");
+  return modar_launch(boxes, nullptr, box_offsets, foreground, nullptr, fg_offsets, se3, num_agents, max_boxes_per_agent,
+                      max_fg_per_agent, scale, max_sweep_idx, nullptr, with_batch_col, batch_idx, rows_out, out_stride,
+                      box_idx_out, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int pcp_modar_agents(const float* const* box_ptrs, const int32_t* box_offsets, const float* const* fg_ptrs,
+                                const int32_t* fg_offsets, const double* se3, int32_t num_agents, int32_t max_boxes_per_agent,
+                                int32_t max_fg_per_agent, float scale, const float* max_sweep_idx_dev, int32_t with_batch_col,
+                                float batch_idx, float* rows_out, int64_t out_stride, int32_t* box_idx_out, void* stream_) {
+  PCP_REQUIRE(num_agents <= 0 || (box_ptrs && max_sweep_idx_dev), PCP_E_INVALID, "pcp_modar_agents: null argument");
+  return modar_launch(nullptr, box_ptrs, box_offsets, nullptr, fg_ptrs, fg_offsets, se3, num_agents, max_boxes_per_agent,
+                      max_fg_per_agent, scale, 0.f, max_sweep_idx_dev, with_batch_col, batch_idx, rows_out, out_stride,
+                      box_idx_out, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int pcp_column_max(const float* rows, int64_t row_stride, int64_t n_rows, int32_t column, float* max_out,
+                              void* stream_) {
+  PCP_REQUIRE(max_out && n_rows >= 0 && column >= 0 && column < row_stride && (n_rows == 0 || rows), PCP_E_INVALID,
+              "pcp_column_max: bad argument");
+  column_max_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream_)>>>(rows, row_stride, n_rows, column, max_out);
+  PCP_LAUNCH_CHECK("column_max_kernel");
   return 0;
 }

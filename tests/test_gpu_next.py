@@ -222,3 +222,65 @@ def test_early_fusion_feeds_the_pillar_path():
     assert torch.equal(bd["voxel_coords"].cpu(), want["voxel_coords"])
     assert_features_close(bd["pillar_features"].cpu().numpy(), want["pillar_features"].numpy(), "pillar_features")
     assert torch.equal((bd["spatial_features"].cpu() != 0).any(1), (want["spatial_features"] != 0).any(1))
+
+
+def test_load_points_to_gpu_rebuilds_collate_batch_rows():
+    """SURVEY 8f rank 3, host->device half: collate_points + load_points_to_gpu against the reference's collate_batch
+    (dataset.py:224-229) + load_data_to_gpu (models/__init__.py:23-34) restated with numpy / torch."""
+    import pcp_b200
+    g = np.random.default_rng(3)
+    frames = [g.normal(size=(n, 7)) * 20 for n in (4000, 1, 0, 2500)]
+    want = torch.from_numpy(np.concatenate([np.pad(f, ((0, 0), (1, 0)), mode="constant", constant_values=i)
+                                            for i, f in enumerate(frames)])).float()
+    full = pcp_b200.load_points_to_gpu(pcp_b200.collate_points(frames), DEV)
+    torch.cuda.synchronize()
+    assert torch.equal(full.cpu(), want)
+    packed = pcp_b200.collate_points(frames, columns=(0, 1, 2, 3, 4))
+    staging = {}
+    out = torch.full((7000, 8), 7.0, device=DEV)
+    got = pcp_b200.load_points_to_gpu(packed, DEV, out=out, staging=staging)
+    torch.cuda.synchronize()
+    assert got.shape == (6501, 8) and got.data_ptr() == out.data_ptr()
+    assert torch.equal(got[:, :6].cpu(), want[:, :6]) and float(got[:, 6:].abs().max()) == 0.0
+    assert float(out[6501:].min()) == 7.0                                  # rows past N untouched
+    # the array collate_batch built (float64) through the plain path
+    plain = pcp_b200.load_points_to_gpu(want.double().numpy(), DEV)
+    assert torch.equal(plain.cpu(), want)
+    # the pillar path gives the same result on the shipped-columns rows as on the full rows
+    from pcp_b200 import synthetic as syn
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    grid = syn.grid_size_of(rng, syn.V2X_VOXEL)
+    vfe_cfg, _ = syn.model_cfgs(5)
+    vfe = pcp_b200.DynamicPillarVFE(model_cfg=vfe_cfg, num_point_features=5, voxel_size=syn.V2X_VOXEL, grid_size=grid,
+                                    point_cloud_range=rng)
+    vfe.load_state_dict(syn.pfn_state_dict(11))
+    vfe = vfe.to(DEV).eval()
+    a = vfe({"points": full, "batch_size": 4})
+    b = vfe({"points": got, "batch_size": 4})
+    assert torch.equal(a["voxel_coords"], b["voxel_coords"]) and torch.equal(a["pillar_features"], b["pillar_features"])
+
+
+def test_points_prefetcher_streams_batches_in_order():
+    import pcp_b200
+    g = np.random.default_rng(9)
+    batches = []
+    for j in range(7):
+        frames = [g.normal(size=(int(g.integers(0, 3000)), 7)) * 30 for _ in range(3)]
+        batches.append((pcp_b200.collate_points(frames, columns=(0, 1, 2, 4)), frames))
+    pre = pcp_b200.PointsPrefetcher(DEV, depth=2)
+    got = []
+    pre.submit(batches[0][0])
+    for j in range(7):
+        if j + 1 < 7:
+            pre.submit(batches[j + 1][0])
+        got.append(pre.get().clone())
+    torch.cuda.synchronize()
+    for (packed, frames), rows in zip(batches, got):
+        want = torch.from_numpy(np.concatenate([np.pad(f, ((0, 0), (1, 0)), mode="constant", constant_values=i)
+                                                for i, f in enumerate(frames)])).float()
+        assert rows.shape == want.shape
+        for c in (0, 1, 2, 3, 5):
+            assert torch.equal(rows[:, c].cpu(), want[:, c])
+        assert float(rows[:, [4, 6, 7]].abs().max()) == 0.0 if rows.shape[0] else True
+    with pytest.raises(RuntimeError):
+        pre.get()

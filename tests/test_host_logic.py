@@ -165,3 +165,26 @@ def test_synthetic_generators_are_seeded_and_shaped():
     ego, agents = syn.modar_scene(2, 0, n_agents=2, n_ego_points=64)
     assert ego.shape == (64, 14) and all(ag["modar"].shape[1] == 9 and ag["foreground"].shape[1] == 13 for ag in agents)
     assert list(syn.grid_size_of(syn.V2X_RANGE, syn.STRESS_VOXEL)) == [1024, 1024, 1]
+
+
+def test_collate_points_replaces_the_points_branch_of_collate_batch():
+    """pcp_b200.collate_points: the frame-index padding + concatenation of collate_batch (dataset.py:224-229) and the
+    .float() of load_data_to_gpu, into one (pinned) buffer, optionally a subset of the columns."""
+    import numpy as np
+    from pcp_b200.loader import collate_points
+    g = np.random.default_rng(0)
+    frames = [g.normal(size=(n, 7)) for n in (5, 0, 11)]                 # float64, as the dataset returns them
+    p = collate_points(frames)
+    want = np.concatenate([np.pad(f, ((0, 0), (1, 0)), mode="constant", constant_values=i) for i, f in enumerate(frames)])
+    assert p.columns == tuple(range(7)) and p.n_point_cols == 7 and p.batch_size == 3 and p.n_points == 16
+    assert p.frame_offsets.tolist() == [0, 5, 5, 16]
+    assert np.array_equal(p.data.numpy(), want[:, 1:].astype(np.float32))
+    sub = collate_points(frames, columns=(0, 1, 2, 3, 4))
+    assert np.array_equal(sub.data.numpy(), want[:, 1:6].astype(np.float32))
+    again = collate_points([f[:3] for f in frames if len(f)], columns=(0, 1, 2, 3, 4), out=sub)      # refill in place
+    assert again.data.data_ptr() == sub.data.data_ptr() and again.frame_offsets.tolist() == [0, 3, 6]
+    import pytest
+    with pytest.raises(ValueError):
+        collate_points(frames, columns=(0, 0))
+    with pytest.raises(ValueError):
+        collate_points(frames, columns=(7,))
