@@ -243,6 +243,9 @@ def run_ours(args):
     from pcp_b200.frontend import FrontEnd, GridSpec, PipelinedFrontEnd
     from tests.helpers import model_cfgs
 
+    if args.voxelize_method:
+        from pcp_b200 import frontend as _fe_mod
+        _fe_mod.DEFAULT_VOXELIZE_METHOD = args.voxelize_method
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -632,6 +635,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--voxelize-method", default=None, help="diagnostic: pcp_voxelize_method (auto | histogram | radix | binned)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

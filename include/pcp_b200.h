@@ -124,6 +124,7 @@ int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int3
 #define PCP_VOXELIZE_AUTO      0
 #define PCP_VOXELIZE_HISTOGRAM 1
 #define PCP_VOXELIZE_RADIX     2
+#define PCP_VOXELIZE_BINNED    3
 int pcp_voxelize_method(const float* points, int64_t row_stride, int64_t n_points, int32_t max_frames,
                         const pcp_grid* grid, void* workspace, size_t workspace_bytes,
                         int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,

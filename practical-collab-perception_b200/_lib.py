@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libpcp_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 PCP_COUNTS_LEN = 8
-VOXELIZE_METHODS = {"auto": 0, "histogram": 1, "radix": 2, "radix_or_auto": 2}   # radix_or_auto: see FrontEnd.voxelize
+# radix_or_auto / binned_or_auto: the named method where it applies, else "auto" (see FrontEnd.voxelize)
+VOXELIZE_METHODS = {"auto": 0, "histogram": 1, "radix": 2, "radix_or_auto": 2, "binned": 3, "binned_or_auto": 3}
 COUNT_PILLARS, COUNT_KEPT, COUNT_FRAMES, COUNT_BAD_FRAME, COUNT_MAX_PER_PILLAR, COUNT_VOXELS = 0, 1, 2, 3, 4, 5
 
 

@@ -153,7 +153,19 @@ __host__ inline RadixPlan radix_plan(int64_t n, int64_t cells, int sms) {
   return p;
 }
 
+// ---------------------------------------------------------------------------------------------
+// binned path of pcp_voxelize (voxelize_binned.cu): bin = one scan tile of kScanTileCells consecutive cells
+// ---------------------------------------------------------------------------------------------
+constexpr int kBnMaxBins = 2048;        // every tile of the finish kernel sums the records of all tiles before it: keep that small
+constexpr int kBnCtrlInts = 64;         // [1] tile ticket of the finish kernel
+
+// the binned method covers 1 .. 2^29 - 1 rows and key spaces of at most kBnMaxBins * kScanTileCells = 4 M cells
+__host__ __device__ inline bool binned_applies(int64_t n, int64_t cells) {
+  return n > 0 && cells > 0 && (cells + kScanTileCells - 1) / kScanTileCells <= kBnMaxBins;
+}
+
 struct WsLayout {
+  size_t bz_ctrl, bz_count, bz_cursor, bz_frames, bz_rec, bz_start, bz_clear_bytes;   // binned path
   size_t hdr, tile_info, cell, cell_rank, key, within, seg_off, sorted_idx, lists, mean, long_table, big_list, long_mean, long_acc, total;
   size_t rtable, rbin_total, rbin_start, rgroup_info, rrec, rsrec, rkey;   // radix path scratch (zero-sized when it does not apply)
   size_t clear_bytes;  // bytes from hdr that the prologue memset clears
@@ -172,6 +184,19 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
   L.long_cap = n / (kSegRows + 1) + 1;
   size_t o = 0;
   L.hdr = o;         o = align_up(o + sizeof(int32_t) * kHdrInts, 256);
+  {
+    // binned path: control words, per-bin row counts / fill cursors, per-tile frame count + 1 and per-tile records (16
+    // ints, every field stored + 1: zero = not published yet) - cleared together with hdr by one small memset
+    const size_t nb = binned_applies(n, L.cells) ? (size_t)L.scan_tiles : 0;
+    L.bz_ctrl = o;   o += sizeof(int32_t) * kBnCtrlInts;
+    L.bz_count = o;  o += sizeof(int32_t) * nb;
+    L.bz_cursor = o; o += sizeof(int32_t) * nb;
+    L.bz_frames = o; o += sizeof(int32_t) * nb;
+    o = align_up(o, 64);
+    L.bz_rec = o;    o = align_up(o + sizeof(int32_t) * 16 * nb, 256);
+    L.bz_clear_bytes = o;
+    L.bz_start = o;  o = align_up(o + sizeof(int32_t) * (nb + 1), 256);
+  }
   L.tile_info = o;   o = align_up(o + sizeof(int32_t) * 17 * (size_t)(L.scan_tiles + 1), 256);   // records + per-tile frame count
   L.cell = o;        o = align_up(o + sizeof(int32_t) * (size_t)L.cells, 256);
   L.clear_bytes = o;
@@ -201,7 +226,7 @@ __host__ inline WsLayout ws_layout(int64_t n, int32_t frames, int32_t nx, int32_
     // order, the same records in pillar order, keys in bin order.  Capacities depend on (n, cells) only, never on the device.
     int32_t shift = 0, nbins = 0;
     const bool rx = radix_bins(L.cells, shift, nbins) && n > 0 && n <= (int64_t)kRxMaxChunks * kRxMaxChunkPts;
-    const size_t nb = rx ? (size_t)nbins : 0, np = rx ? (size_t)n : 0;
+    const size_t nb = rx ? (size_t)nbins : 0, np = (rx || binned_applies(n, L.cells)) ? (size_t)n : 0;
     L.rtable = o;      o = align_up(o + sizeof(int32_t) * kRxMaxChunks * nb, 256);
     L.rbin_total = o;  o = align_up(o + sizeof(int32_t) * (nb + 1), 256);
     L.rbin_start = o;  o = align_up(o + sizeof(int32_t) * (nb + 1), 256);
@@ -229,6 +254,12 @@ struct WsView {
   int32_t* big_list;
   float4* long_mean;
   unsigned* long_acc;
+  int32_t* bz_ctrl;
+  int32_t* bz_count;
+  int32_t* bz_cursor;
+  int32_t* bz_frames;
+  int32_t* bz_rec;
+  int32_t* bz_start;
   int32_t* rtable;
   int32_t* rbin_total;
   int32_t* rbin_start;
@@ -255,6 +286,12 @@ __host__ inline WsView ws_view(void* base, const WsLayout& L) {
   v.big_list = reinterpret_cast<int32_t*>(p + L.big_list);
   v.long_mean = reinterpret_cast<float4*>(p + L.long_mean);
   v.long_acc = reinterpret_cast<unsigned*>(p + L.long_acc);
+  v.bz_ctrl = reinterpret_cast<int32_t*>(p + L.bz_ctrl);
+  v.bz_count = reinterpret_cast<int32_t*>(p + L.bz_count);
+  v.bz_cursor = reinterpret_cast<int32_t*>(p + L.bz_cursor);
+  v.bz_frames = reinterpret_cast<int32_t*>(p + L.bz_frames);
+  v.bz_rec = reinterpret_cast<int32_t*>(p + L.bz_rec);
+  v.bz_start = reinterpret_cast<int32_t*>(p + L.bz_start);
   v.rtable = reinterpret_cast<int32_t*>(p + L.rtable);
   v.rbin_total = reinterpret_cast<int32_t*>(p + L.rbin_total);
   v.rbin_start = reinterpret_cast<int32_t*>(p + L.rbin_start);

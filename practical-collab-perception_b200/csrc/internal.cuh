@@ -15,6 +15,14 @@ int voxelize_radix(const WsLayout& L, const WsView& W, const RadixPlan& rp, cons
                    int32_t frames, const pcp_grid& grid, int32_t* point_pillar_out, int32_t* voxel_coords_out,
                    int32_t* pillar_count_out, int32_t* counts_out, cudaStream_t stream);
 
+// voxelize_binned.cu: the whole of pcp_voxelize() as one coarse partition pass + a per-tile finish (see the file header)
+int voxelize_binned(const WsLayout& L, const WsView& W, const float* points, int64_t stride, int64_t n, int32_t frames,
+                    const pcp_grid& grid, int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
+                    int32_t* counts_out, cudaStream_t stream);
+// voxelize.cu: pillar_prep_kernel for the pillars above 8 rows, reading the binned path's placed records
+int launch_pillar_prep_rec(const WsLayout& L, const WsView& W, const float* points, int64_t stride, int64_t n,
+                            const pcp_grid& grid, cudaStream_t stream);
+
 // api.cu: multiprocessors of the current device (queried once per device)
 int sm_count();
 

@@ -420,8 +420,10 @@ __device__ __forceinline__ void prep_short_one(const float* __restrict__ points,
 // W lanes per pillar (two length classes of at most W rows, walked back to back), items [w_begin, w_end) of the
 // concatenated lists: rank by counting against the warp's shared-memory copy, lanes 0, 1, 2 of the group run the
 // sequential sums of x, y, z.  warp_smem: 4 x 32 words of this warp.
-template <int W, bool kVec4>
-__device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64_t stride, const pcp_grid& g,
+// kRec: the pillar's rows are {x, y, z, row number} records at srec[off ..] (binned path) instead of row numbers in sorted_idx
+template <int W, bool kVec4, bool kRec>
+__device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64_t stride, const float4* __restrict__ srec,
+                                         const pcp_grid& g,
                                          const unsigned long long* __restrict__ list_a, int count_a,
                                          const unsigned long long* __restrict__ list_b, int count_b, int w_begin, int w_end,
                                          int32_t* __restrict__ sorted_idx, float4* __restrict__ mean, int32_t* warp_smem) {
@@ -434,7 +436,9 @@ __device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64
     const int w = w0 + sub;
     int r = 0, off = 0, n = 0;
     if (w < total) unpack_entry(__ldg(w < count_a ? list_a + w : list_b + (w - count_a)), r, off, n);
-    const int32_t v = (ln < n) ? sorted_idx[off + ln] : 0x7fffffff;
+    float4 rc = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+    if (kRec && ln < n) rc = __ldcg(srec + off + ln);
+    const int32_t v = kRec ? __float_as_int(rc.w) : ((ln < n) ? sorted_idx[off + ln] : 0x7fffffff);
     sv[ln] = v;
     __syncwarp();
     int rank = 0;
@@ -446,7 +450,8 @@ __device__ __forceinline__ void prep_mid(const float* __restrict__ points, int64
     float x = 0.f, y = 0.f, z = 0.f;
     if (ln < n) {
       sorted_idx[off + rank] = v;
-      load_xyz<kVec4>(points, stride, v, x, y, z);
+      if (kRec) { x = rc.x; y = rc.y; z = rc.z; }
+      else load_xyz<kVec4>(points, stride, v, x, y, z);
       sx[rank] = x; sx[32 + rank] = y; sx[64 + rank] = z;
     }
     __syncwarp();
@@ -477,9 +482,9 @@ struct PrepSmem {
   };
 };
 
-template <bool kVec4>
+template <bool kVec4, bool kRec>
 __global__ void __launch_bounds__(kPrepThreads, 4)
-pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __restrict__ hdr,
+pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float4* __restrict__ srec, int32_t* __restrict__ hdr,
                    unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
                    const int32_t* __restrict__ big_list, int32_t* __restrict__ sorted_idx, float4* __restrict__ mean,
                    float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, const pcp_grid g, int phase_mask) {
@@ -512,7 +517,8 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       if (n <= kCountSortMax) {
         int32_t* s2 = sm.cta.scratch;
         const int n4 = (n + 3) & ~3;
-        for (int i = tid; i < n4; i += kPrepThreads) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+        for (int i = tid; i < n4; i += kPrepThreads)
+          s[i] = (i < n) ? (kRec ? __float_as_int(__ldcg(srec + off + i).w) : sorted_idx[off + i]) : 0x7fffffff;
         __syncthreads();
         for (int i = tid; i < n; i += kPrepThreads) {
           const int32_t v = s[i];
@@ -529,7 +535,8 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       } else {
         int m = 2048;
         while (m < n) m <<= 1;
-        for (int i = tid; i < m; i += kPrepThreads) s[i] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+        for (int i = tid; i < m; i += kPrepThreads)
+          s[i] = (i < n) ? (kRec ? __float_as_int(__ldcg(srec + off + i).w) : sorted_idx[off + i]) : 0x7fffffff;
         __syncthreads();
         for (int k = 2; k <= m; k <<= 1) {
           for (int j = k >> 1; j > 0; j >>= 1) {
@@ -576,7 +583,13 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
       for (int i = tid; i < n; i += kPrepThreads) {
         float x, y, z;
-        load_xyz<kVec4>(points, stride, sorted_idx[off + i], x, y, z);
+        if (kRec) {
+          const float4 rc = __ldcg(srec + off + i);
+          x = rc.x; y = rc.y; z = rc.z;
+          sorted_idx[off + i] = __float_as_int(rc.w);
+        } else {
+          load_xyz<kVec4>(points, stride, sorted_idx[off + i], x, y, z);
+        }
         a0 += x; a1 += y; a2 += z;
       }
 #pragma unroll
@@ -594,7 +607,8 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
       if (tid == 0) {
         float x, y, z;
-        load_xyz<kVec4>(points, stride, sorted_idx[off], x, y, z);
+        if (kRec) { const float4 rc = __ldcg(srec + off); x = rc.x; y = rc.y; }
+        else load_xyz<kVec4>(points, stride, sorted_idx[off], x, y, z);
         s_red[0][1] = pack_cell(x, y, g);
       }
     }
@@ -621,10 +635,17 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
     int32_t* s1 = sm.warp_words[warp][1];
     const int n4 = (n + 3) & ~3;
     int32_t v[kWarpLongMax / 32];
+    float x[kWarpLongMax / 32], y[kWarpLongMax / 32], z[kWarpLongMax / 32];
 #pragma unroll
     for (int k = 0; k < kWarpLongMax / 32; ++k) {
       const int i = k * 32 + lane;
-      v[k] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+      if (kRec) {
+        float4 rc = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+        if (i < n) rc = __ldcg(srec + off + i);
+        v[k] = __float_as_int(rc.w); x[k] = rc.x; y[k] = rc.y; z[k] = rc.z;
+      } else {
+        v[k] = (i < n) ? sorted_idx[off + i] : 0x7fffffff;
+      }
       if (i < n4) s0[i] = v[k];
     }
     __syncwarp();
@@ -637,30 +658,41 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       for (int k = 0; k < kWarpLongMax / 32; ++k)
         rank[k] += (t.x < v[k]) + (t.y < v[k]) + (t.z < v[k]) + (t.w < v[k]);
     }
-#pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k)
-      if (k * 32 + lane < n) s1[rank[k]] = v[k];
-    __syncwarp();
     float* fx = reinterpret_cast<float*>(sm.warp_words[warp][0]);
     float* fy = reinterpret_cast<float*>(sm.warp_words[warp][2]);
-    float x[kWarpLongMax / 32], y[kWarpLongMax / 32], z[kWarpLongMax / 32];
-#pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k) {
-      const int i = k * 32 + lane;
-      if (i < n) {
-        const int32_t idx = s1[i];
-        sorted_idx[off + i] = idx;
-        load_xyz<kVec4>(points, stride, idx, x[k], y[k], z[k]);
-      }
-    }
-    __syncwarp();                       // every lane has read its sorted row numbers: s1 can be reused for z
     float* fz = reinterpret_cast<float*>(sm.warp_words[warp][1]);
+    if (kRec) {
+      // every lane holds its own rows' coordinates: they go straight to their ranks
+      __syncwarp();                     // every lane has finished reading s0 (= fx)
 #pragma unroll
-    for (int k = 0; k < kWarpLongMax / 32; ++k) {
-      const int i = k * 32 + lane;
-      if (i < n) { fx[i] = x[k]; fy[i] = y[k]; fz[i] = z[k]; }
+      for (int k = 0; k < kWarpLongMax / 32; ++k)
+        if (k * 32 + lane < n) {
+          sorted_idx[off + rank[k]] = v[k];
+          fx[rank[k]] = x[k]; fy[rank[k]] = y[k]; fz[rank[k]] = z[k];
+        }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int k = 0; k < kWarpLongMax / 32; ++k)
+        if (k * 32 + lane < n) s1[rank[k]] = v[k];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < kWarpLongMax / 32; ++k) {
+        const int i = k * 32 + lane;
+        if (i < n) {
+          const int32_t idx = s1[i];
+          sorted_idx[off + i] = idx;
+          load_xyz<kVec4>(points, stride, idx, x[k], y[k], z[k]);
+        }
+      }
+      __syncwarp();                     // every lane has read its sorted row numbers: s1 can be reused for z
+#pragma unroll
+      for (int k = 0; k < kWarpLongMax / 32; ++k) {
+        const int i = k * 32 + lane;
+        if (i < n) { fx[i] = x[k]; fy[i] = y[k]; fz[i] = z[k]; }
+      }
+      __syncwarp();
     }
-    __syncwarp();
     float acc = 0.f;
     if (lane < 3) {
       const float* src = lane == 0 ? fx : (lane == 1 ? fy : fz);
@@ -669,7 +701,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
     }
     const float my = __shfl_sync(0xffffffffu, acc, 1), mz = __shfl_sync(0xffffffffu, acc, 2);
     if (lane == 0) {
-      const float cw = pack_cell(x[0], y[0], g);
+      const float cw = pack_cell(fx[0], fy[0], g);
       long_mean[li] = make_float4(acc, my, mz, cw);
       mean[r] = make_float4(acc, my, mz, cw);
     }
@@ -683,14 +715,14 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, int32_t* __
       const int ca = hdr[kHdrListCount + 6], cb = hdr[kHdrListCount + 7];
       constexpr int kChunk = kPrepWarps * 2 * 4;          // 4 rounds of the CTA
       for (int w0 = grab(1, kChunk); w0 < ca + cb; w0 = grab(1, kChunk))
-        prep_mid<16, kVec4>(points, stride, g, lists + lo.off[6], ca, lists + lo.off[7], cb, w0, w0 + kChunk, sorted_idx, mean,
+        prep_mid<16, kVec4, kRec>(points, stride, srec, g, lists + lo.off[6], ca, lists + lo.off[7], cb, w0, w0 + kChunk, sorted_idx, mean,
                             &sm.warp_words[warp][0][0]);
     }
     {
       const int ca = hdr[kHdrListCount + 8], cb = hdr[kHdrListCount + 9];
       constexpr int kChunk = kPrepWarps * 4;
       for (int w0 = grab(2, kChunk); w0 < ca + cb; w0 = grab(2, kChunk))
-        prep_mid<32, kVec4>(points, stride, g, lists + lo.off[8], ca, lists + lo.off[9], cb, w0, w0 + kChunk, sorted_idx, mean,
+        prep_mid<32, kVec4, kRec>(points, stride, srec, g, lists + lo.off[8], ca, lists + lo.off[9], cb, w0, w0 + kChunk, sorted_idx, mean,
                             &sm.warp_words[warp][0][0]);
     }
   }
@@ -746,13 +778,33 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     const bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
     if (vec4)
-      pillar_prep_kernel<true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                   W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
+      pillar_prep_kernel<true, false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, nullptr, W.hdr, W.lists, L.lo, W.long_table,
+                                                                          W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
     else
-      pillar_prep_kernel<false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.hdr, W.lists, L.lo, W.long_table, W.big_list,
-                                                                    W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
+      pillar_prep_kernel<false, false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, nullptr, W.hdr, W.lists, L.lo, W.long_table,
+                                                                           W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
     PCP_LAUNCH_CHECK("pillar_prep_kernel");
   }
+  return 0;
+}
+
+// Pillars above 8 rows (phases 1 | 2 | 4 of pillar_prep_kernel: long pillars and the 9 .. 32-row classes) from the placed
+// {x, y, z, row} records of the binned path (voxelize_binned.cu, which finishes every shorter pillar inside its per-tile
+// kernel): ascending row order, mean, segment entries, max accumulators.
+int launch_pillar_prep_rec(const WsLayout& L, const WsView& W, const float* points, int64_t stride, int64_t n,
+                           const pcp_grid& grid, cudaStream_t stream) {
+  if (n <= 8) return 0;
+  const int64_t want = n / (9 * kPrepWarps) + 1;                       // at most n / 9 pillars, one (half) warp each
+  const int64_t cap = (int64_t)sm_count() * 4;
+  const unsigned blocks = (unsigned)(want < cap ? want : cap);
+  const bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+  if (vec4)
+    pillar_prep_kernel<true, true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.rsrec, W.hdr, W.lists, L.lo, W.long_table,
+                                                                       W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 7);
+  else
+    pillar_prep_kernel<false, true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.rsrec, W.hdr, W.lists, L.lo, W.long_table,
+                                                                        W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 7);
+  PCP_LAUNCH_CHECK("pillar_prep_kernel(records)");
   return 0;
 }
 }  // namespace pcp
@@ -777,7 +829,8 @@ extern "C" int pcp_voxelize_method(const float* points, int64_t row_stride, int6
   PCP_REQUIRE(grid->nx <= 65535 && grid->ny <= 65535, PCP_E_UNSUPPORTED, "pcp_voxelize: nx, ny must be <= 65535");
   PCP_REQUIRE((int64_t)max_frames * grid->nx * grid->ny < (1ll << 31), PCP_E_UNSUPPORTED,
               "pcp_voxelize: frames*nx*ny must fit int32 (the reference's merge_coords is int32 too)");
-  PCP_REQUIRE(method == PCP_VOXELIZE_AUTO || method == PCP_VOXELIZE_HISTOGRAM || method == PCP_VOXELIZE_RADIX, PCP_E_INVALID,
+  PCP_REQUIRE(method == PCP_VOXELIZE_AUTO || method == PCP_VOXELIZE_HISTOGRAM || method == PCP_VOXELIZE_RADIX ||
+                  method == PCP_VOXELIZE_BINNED, PCP_E_INVALID,
               "pcp_voxelize: unknown method %d", method);
   const WsLayout L = ws_layout(n_points, max_frames, grid->nx, grid->ny);
   PCP_REQUIRE(workspace_bytes >= L.total, PCP_E_WORKSPACE, "pcp_voxelize: workspace %zu < %zu bytes",
@@ -801,6 +854,14 @@ extern "C" int pcp_voxelize_method(const float* points, int64_t row_stride, int6
     if (rp.ok)
       return voxelize_radix(L, W, rp, points, row_stride, n_points, max_frames, *grid, point_pillar_out, voxel_coords_out,
                             pillar_count_out, counts_out, stream);
+  }
+
+  if (method == PCP_VOXELIZE_BINNED) {
+    PCP_REQUIRE(binned_applies(n_points, L.cells), PCP_E_UNSUPPORTED,
+                "pcp_voxelize: the binned method covers n_points >= 1 and at most %lld cells",
+                (long long)kBnMaxBins * kScanTileCells);
+    return voxelize_binned(L, W, points, row_stride, n_points, max_frames, *grid, point_pillar_out, voxel_coords_out,
+                           pillar_count_out, counts_out, stream);
   }
 
   PCP_CUDA(cudaMemsetAsync(workspace, 0, L.clear_bytes, stream));

@@ -160,6 +160,10 @@ class FrontEnd:
         """What PCP_VOXELIZE_RADIX covers (include/pcp_b200.h): 1 .. 16.6 M rows, at most 4 M cells."""
         return 1 <= n_points <= 256 * 65024 and int(max_frames) * self.grid.nx * self.grid.ny <= 4096 * 1024
 
+    def binned_applies(self, n_points: int, max_frames: int) -> bool:
+        """What PCP_VOXELIZE_BINNED covers (include/pcp_b200.h): at least one row, at most 2048 x 2048 = 4.2 M cells."""
+        return n_points >= 1 and int(max_frames) * self.grid.nx * self.grid.ny <= 2048 * 2048
+
     def capacity(self, n_points: int, max_frames: int) -> int:
         return max(1, min(int(n_points), int(max_frames) * self.grid.nx * self.grid.ny))
 
@@ -189,6 +193,8 @@ class FrontEnd:
         pc = buf("pillar_count_buf", (cap,), torch.int32) if want_counts_per_pillar else None
         method = _lib.VOXELIZE_METHODS[self.voxelize_method]
         if self.voxelize_method == "radix_or_auto" and not self.radix_applies(n, max_frames):
+            method = _lib.VOXELIZE_METHODS["auto"]
+        if self.voxelize_method == "binned_or_auto" and not self.binned_applies(n, max_frames):
             method = _lib.VOXELIZE_METHODS["auto"]
         rc = self.lib.pcp_voxelize_method(_ptr(points), stride, n, int(max_frames), C.byref(self.grid.c), _ptr(ws), ws.numel(),
                                           _ptr(pp), _ptr(coords), _ptr(pc), coords.shape[0], _ptr(counts), method, _stream())

@@ -20,13 +20,13 @@ class _RadixWhereItApplies(str):
     """Marker value of the fixture below: FrontEnd falls back to "auto" for shapes the radix method does not cover."""
 
 
-@pytest.fixture(autouse=True, params=["auto", "radix"])
+@pytest.fixture(autouse=True, params=["auto", "radix", "binned"])
 def voxelize_method(request):
     """Every test of this file runs on both compaction algorithms of pcp_voxelize_method: the dense-histogram path ("auto")
     and the stable radix sort (wherever it applies).  Results must be identical."""
     from pcp_b200 import frontend
     old = frontend.DEFAULT_VOXELIZE_METHOD
-    frontend.DEFAULT_VOXELIZE_METHOD = "radix_or_auto" if request.param == "radix" else "auto"
+    frontend.DEFAULT_VOXELIZE_METHOD = {"radix": "radix_or_auto", "binned": "binned_or_auto"}.get(request.param, "auto")
     yield request.param
     frontend.DEFAULT_VOXELIZE_METHOD = old
 DEV = "cuda:0"
@@ -449,7 +449,7 @@ def test_stress_config_against_oracle(n_points, uniform):
 
 @pytest.mark.parametrize("n_frames,n_points,voxel,ego", [(8, 300000, None, False), (1, 32768, None, True), (1, 4000000, [0.1, 0.1, 8.0], False),
                                                          (3, 777, None, False), (16, 1000, None, False)])
-def test_radix_and_histogram_compaction_agree_bit_for_bit(n_frames, n_points, voxel, ego):
+def test_compaction_methods_agree_bit_for_bit(n_frames, n_points, voxel, ego):
     """pcp_voxelize_method: the stable radix sort and the dense-histogram path give the same pillars, point->pillar map,
     counts, per-pillar means (sequential sums in row order on both), PFN features, canvas and segment reductions."""
     from pcp_b200.frontend import FrontEnd, GridSpec
@@ -459,7 +459,7 @@ def test_radix_and_histogram_compaction_agree_bit_for_bit(n_frames, n_points, vo
     vals = torch.randn(pts.shape[0], 8, generator=torch.Generator().manual_seed(5)).to(DEV)
     bn = lambda i: [sd[f"pfn_layers.{i}.norm.{k}"].to(DEV) for k in ("weight", "bias", "running_mean", "running_var")]
     res = {}
-    for method in ("radix", "histogram"):
+    for method in ("radix", "histogram", "binned"):
         fe = FrontEnd(GridSpec(vox, rng, grid), c_raw, voxelize_method=method)
         fe.pack_params(sd["pfn_layers.0.linear.weight"].to(DEV), bn(0), sd["pfn_layers.1.linear.weight"].to(DEV), bn(1))
         out = fe.voxelize(pts, n_frames, want_point_pillar=True, want_counts_per_pillar=True)
@@ -472,15 +472,17 @@ def test_radix_and_histogram_compaction_agree_bit_for_bit(n_frames, n_points, vo
         res[method] = dict(counts=counts.copy(), vc=out["voxel_coords_buf"][:p].clone(), pp=out["point_pillar"][:pts.shape[0]].clone(),
                            pc=out["pillar_count_buf"][:p].clone(), pf=out["pillar_features_buf"][:p].clone(),
                            mean=out["pillar_mean_buf"][:p].clone(), canvas=canvas, smax=smax[:p].clone(), smean=smean[:p].clone())
-    a, b = res["radix"], res["histogram"]
-    assert np.array_equal(a["counts"], b["counts"]), (a["counts"], b["counts"])
-    assert a["counts"][0] > 0
-    giant = int(a["counts"][4]) > 4096                 # the histogram path sums pillars above 4096 rows in arrival order
-    for k in ("vc", "pp", "pc", "mean", "pf", "canvas", "smax", "smean"):
-        if giant and k in ("mean", "pf", "canvas", "smean"):
-            assert_features_close(a[k].cpu().numpy(), b[k].cpu().numpy(), k)
-        else:
-            assert torch.equal(a[k], b[k]), k
+    b = res["histogram"]
+    for other in ("radix", "binned"):
+        a = res[other]
+        assert np.array_equal(a["counts"], b["counts"]), (other, a["counts"], b["counts"])
+        assert a["counts"][0] > 0
+        giant = int(a["counts"][4]) > 4096             # the histogram path sums pillars above 4096 rows in arrival order
+        for k in ("vc", "pp", "pc", "mean", "pf", "canvas", "smax", "smean"):
+            if giant and k in ("mean", "pf", "canvas", "smean"):
+                assert_features_close(a[k].cpu().numpy(), b[k].cpu().numpy(), k)
+            else:
+                assert torch.equal(a[k], b[k]), (other, k)
 
 
 def test_radix_method_reports_what_it_does_not_cover():

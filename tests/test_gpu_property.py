@@ -18,13 +18,13 @@ class _RadixWhereItApplies(str):
     """Marker value of the fixture below: FrontEnd falls back to "auto" for shapes the radix method does not cover."""
 
 
-@pytest.fixture(autouse=True, params=["auto", "radix"])
+@pytest.fixture(autouse=True, params=["auto", "radix", "binned"])
 def voxelize_method(request):
     """Every test of this file runs on both compaction algorithms of pcp_voxelize_method: the dense-histogram path ("auto")
     and the stable radix sort (wherever it applies).  Results must be identical."""
     from pcp_b200 import frontend
     old = frontend.DEFAULT_VOXELIZE_METHOD
-    frontend.DEFAULT_VOXELIZE_METHOD = "radix_or_auto" if request.param == "radix" else "auto"
+    frontend.DEFAULT_VOXELIZE_METHOD = {"radix": "radix_or_auto", "binned": "binned_or_auto"}.get(request.param, "auto")
     yield request.param
     frontend.DEFAULT_VOXELIZE_METHOD = old
 

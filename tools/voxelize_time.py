@@ -1,4 +1,5 @@
-"""Device time of pcp_voxelize_method alone, radix sort vs dense histogram (CUDA events, medians): the bench batch
+"""Device time of pcp_voxelize_method alone, per compaction method (CUDA events, medians; `graph`: the same call captured
+in a CUDA graph and replayed, i.e. without the host's launch gaps): the bench batch
 (8 early-fusion frames), one early-fusion frame, one 32 k frame, the 1 M / 4 M stress clouds.
     python tools/voxelize_time.py [--json out.json]"""
 import argparse
@@ -19,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--methods", default="binned,histogram,radix")
     ap.add_argument("--case", type=int, default=-1, help="run only this case (for an ncu launch list)")
     args = ap.parse_args()
     dev = "cuda:0"
@@ -33,9 +35,11 @@ def main():
         gs = GridSpec(vox, rng, syn.grid_size_of(rng, vox))
         batches = [syn.batch_of_frames(frames, npts, 3, first_frame=1000 * a).to(dev) for a in range(2)]
         row = {}
-        for method in ("radix", "histogram"):
+        for method in args.methods.split(","):
             fe = FrontEnd(gs, 5, voxelize_method=method)
             out = {}
+            if not getattr(fe, method + "_applies", lambda *a: True)(npts * frames, frames):
+                continue
             for cold in (False, True):
                 ts = []
                 for i in range(args.iters + 3):
@@ -49,10 +53,29 @@ def main():
                     if i >= 3:
                         ts.append(e0.elapsed_time(e1) * 1e3)
                 row[method + ("_cold" if cold else "")] = statistics.median(ts)
-            row["pillars"] = int(fe.read_counts(out)[0])
+            # the same call as one CUDA graph launch
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fe.voxelize(batches[0], frames, out, want_point_pillar=False)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    fe.voxelize(batches[0], frames, out, want_point_pillar=False)
+            torch.cuda.synchronize()
+            ts = []
+            for i in range(args.iters + 3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+            row[method + "_graph"] = statistics.median(ts)
+            row["pillars_" + method] = int(fe.read_counts(out)[0])
+            del g
         res[name] = row
-        print(f"{name:16s} pillars {row['pillars']:8d}  radix {row['radix']:7.1f} us (L2 flushed {row['radix_cold']:7.1f})   "
-              f"histogram {row['histogram']:7.1f} us (L2 flushed {row['histogram_cold']:7.1f})", flush=True)
+        print(f"{name:16s} " + "  ".join(f"{k} {v:.1f}" if isinstance(v, float) else f"{k} {v}" for k, v in row.items()), flush=True)
     if args.json:
         json.dump(res, open(args.json, "w"), indent=1)
 
