@@ -131,6 +131,65 @@ canvas_v8_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_
   }
 }
 
+// TMA variant of canvas_v8_kernel (additionally nx % 128 == 0, ny % 8 == 0: every CTA owns a full 8 x 128 patch).  Per step
+// of 8 channels the patch's (8 channels x 8 rows x 128 columns) block is assembled in shared memory - every lane stores the
+// same transposed 16-byte pieces it would have sent to global memory - and leaves as 64 bulk copies (cp.async.bulk, the
+// TMA unit) of 512 contiguous bytes, issued by two warps, while all warps already gather the next 8 channels.  Two staging
+// buffers: a buffer is rewritten once the bulk copies issued from it two steps ago have finished READING shared memory.
+constexpr int kTmaStageFloats = 8 * kTileY * kTileX;          // one buffer: 32 KB
+
+__device__ __forceinline__ void bulk_store_g(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
+canvas_tma_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
+                  float* __restrict__ canvas) {
+  extern __shared__ __align__(128) float s_stage[];            // [2][8 channels][8 rows][128 columns]
+  const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * kTileY, xt = blockIdx.x * kTileX;
+  const int y = y0 + wy, x0 = xt + lane * 4;
+  const int64_t nxy = (int64_t)nx * ny;
+  int r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = __ldg(rank_map + b * nxy + (int64_t)(x0 + i) * ny + y);
+  // issuing threads (two warps): thread t sends channel t >> 3, row t & 7 of the step
+  const int iq = tid >> 3, irow = tid & 7;
+  float* const gdst = canvas + ((int64_t)b * channels + iq) * nxy + (int64_t)(y0 + irow) * nx + xt;
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_stage);
+  int step = 0;
+  for (int c = 0; c < channels; c += 8, ++step) {
+    float8 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (r[i] >= 0) v[i] = ldg_f8(pf + (int64_t)r[i] * channels + c);
+      else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[i].v[q] = 0.f;
+      }
+    }
+    const int buf = step & 1;
+    if (step >= 2) {
+      if (tid < 64) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+    float* sb = s_stage + buf * kTmaStageFloats + wy * kTileX + lane * 4;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(sb + q * (kTileY * kTileX)) = make_float4(v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid < 64) {
+      bulk_store_g(gdst + (int64_t)c * nxy, s_base + 4u * (uint32_t)(buf * kTmaStageFloats + iq * (kTileY * kTileX) + irow * kTileX),
+                   kTileX * 4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid < 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // generic path: canvas-ordered rank map from arbitrary voxel_coords rows (frame, z, y, x)
 __global__ void __launch_bounds__(256)
 coords_to_map_kernel(const int32_t* __restrict__ coords, int64_t P, int frames, int nx, int ny,
@@ -180,6 +239,13 @@ extern "C" int pcp_bev_scatter_ws(const float* pillar_features, int32_t channels
     const int th = kTileY * 32;
     const bool fast8 = (channels % 8 == 0) && (grid->nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(pillar_features) & 31) == 0) &&
                        ((reinterpret_cast<uintptr_t>(canvas_out) & 15) == 0);
+#ifdef PCP_CANVAS_TMA
+    if (fast8 && grid->nx % kTileX == 0 && grid->ny % kTileY == 0) {
+      const int smem = 2 * kTmaStageFloats * (int)sizeof(float);
+      PCP_CUDA(cudaFuncSetAttribute(canvas_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      canvas_tma_kernel<3><<<cg, th, smem, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
+    } else
+#endif
     if (fast8)
       canvas_v8_kernel<3><<<cg, th, 0, stream>>>(pillar_features, W.cell_rank, channels, grid->nx, grid->ny, canvas_out);
     else

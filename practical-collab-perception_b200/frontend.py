@@ -116,6 +116,7 @@ class FrontEnd:
         if voxelize_method not in _lib.VOXELIZE_METHODS:
             raise ValueError(f"voxelize_method must be one of {sorted(_lib.VOXELIZE_METHODS)}")
         self.voxelize_method = voxelize_method
+        self._counts_pinned = None
         nf = list(num_filters)
         if len(nf) not in (1, 2) or nf[-1] != 64 or (len(nf) == 2 and nf[0] != 64):
             raise NotImplementedError(
@@ -169,7 +170,11 @@ class FrontEnd:
 
     @device_guard
     def voxelize(self, points: torch.Tensor, max_frames: int, out: Optional[Dict[str, torch.Tensor]] = None,
-                 want_point_pillar: bool = True, want_counts_per_pillar: bool = False) -> Dict[str, torch.Tensor]:
+                 want_point_pillar: bool = True, want_counts_per_pillar: bool = False,
+                 host_counts: bool = False) -> Dict[str, torch.Tensor]:
+        """host_counts: also start the 32-byte copy of the counts block to pinned host memory right behind the voxelize
+        kernels and record an event, so that ``read_counts`` waits for voxelize only - not for whatever the caller
+        enqueues next (the module enqueues the PFN before it reads P)."""
         _require_cuda(points, "points")
         if points.dtype != torch.float32 or points.dim() != 2 or points.stride(1) != 1:
             raise RuntimeError("points must be a 2-D fp32 tensor with unit column stride")
@@ -202,6 +207,14 @@ class FrontEnd:
         self.ws.n_points, self.ws.max_frames = n, int(max_frames)
         self.ws.generation += 1
         out["capacity"] = cap
+        out.pop("counts_host", None)
+        if host_counts:
+            if self._counts_pinned is None:
+                self._counts_pinned = torch.empty(_lib.PCP_COUNTS_LEN, dtype=torch.int32).pin_memory()
+            self._counts_pinned.copy_(counts, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            out["counts_host"] = (self._counts_pinned, ev)
         return out
 
     @device_guard
@@ -275,6 +288,11 @@ class FrontEnd:
     @staticmethod
     def read_counts(out: Dict[str, torch.Tensor]) -> np.ndarray:
         """The one D2H read of the path: 32 bytes (P, N', frames, bad-frame count, max points per pillar)."""
+        early = out.get("counts_host")
+        if early is not None:
+            pinned, ev = early
+            ev.synchronize()
+            return pinned.numpy().copy()
         return out["counts"].cpu().numpy()
 
 

@@ -164,9 +164,11 @@ class DynamicPillarVFE(VFETemplate):
             max_frames = int(points[:, 0].max().item()) + 1 if points.shape[0] else 1
         max_frames = max(int(max_frames), 1)
 
-        out = fe.voxelize(points, max_frames, self._bufs, want_point_pillar=True)
+        out = fe.voxelize(points, max_frames, self._bufs, want_point_pillar=True, host_counts=True)
         fe.pfn(points, out)
-        counts = fe.read_counts(out)                      # the one host sync of the module (32 bytes)
+        # the one host sync of the module (32 bytes): it waits for the voxelize kernels only, the PFN keeps running while
+        # the caller (PointPillarScatter, ...) enqueues what comes next
+        counts = fe.read_counts(out)
         if counts[_lib.COUNT_BAD_FRAME] > 0:
             raise RuntimeError(f"{int(counts[_lib.COUNT_BAD_FRAME])} points carry a frame index outside "
                                f"[0, {max_frames}) (batch_dict['batch_size'] too small?)")
