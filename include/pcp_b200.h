@@ -306,6 +306,23 @@ int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols
                           float* rows_out, int64_t out_stride, int32_t* count_out, void* stream);
 
 /*
+ * Producer side of the exchange: the foreground records one agent broadcasts.  Replaces, in the test-time branch of
+ * pcdet/models/bev_layers/hunter_jr.py:377-397, torch.sigmoid(points_cls_logit), the mask prob[:, 0] < 0.3, the torch.cat of
+ * [points[mask, 1:], prob[mask], points_flow3d[mask]] and the per-sample boolean split: one stable partition on the GPU.
+ *   points       (n_points, point_stride) fp32: column 0 = sample index, columns 1 .. n_point_cols are sent (7 in the reference)
+ *   cls_logit    (n_points, logit_stride >= 3), flow3d (n_points, flow_stride >= 3)
+ *   rows_out     (>= n_points, out_stride >= n_point_cols + 6): [point columns | prob3 | flow3], grouped by sample, input order
+ *   frame_offsets_out  device int32[num_frames + 1]: first row of every sample, [num_frames] = rows sent
+ *   scratch      pcp_select_scratch_bytes(n_points, num_frames) bytes
+ * Rows whose sample index is outside [0, num_frames) are not sent (the reference's loop over metadata never reaches them).
+ */
+size_t pcp_select_scratch_bytes(int64_t n_points, int32_t num_frames);
+int pcp_select_foreground(const float* points, int64_t point_stride, int32_t n_point_cols, const float* cls_logit,
+                          int64_t logit_stride, const float* flow3d, int64_t flow_stride, int64_t n_points,
+                          int32_t num_frames, float threshold, int32_t* scratch, float* rows_out, int64_t out_stride,
+                          int32_t* frame_offsets_out, void* stream);
+
+/*
  * Device half of the points loader.  Replaces, for batch_dict['points'], the frame-index padding + concatenation of
  * collate_batch (pcdet/datasets/dataset.py:224-229) and the .float().cuda() of load_data_to_gpu (pcdet/models/__init__.py:
  * 23-34): the host ships only the per-point columns a consumer reads (x, y, z, intensity, time = 20 of the 28 bytes of an

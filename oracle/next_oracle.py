@@ -151,3 +151,16 @@ def fuse_agent_points(ego_points: np.ndarray, agent_points: Sequence[np.ndarray]
             & (pts[:, 2] >= r[2]) & (pts[:, 2] < r[5])
         pts = pts[m]
     return pts
+
+
+def select_foreground(points, points_cls_logit, points_flow3d, batch_size, threshold=0.3):
+    """pcdet/models/bev_layers/hunter_jr.py:377-397, the test-time exchange block, line by line on CPU tensors:
+    sigmoid (:379), mask_send = P(background) < 0.3 (:380), cat of points[mask, 1:] | prob[mask] | flow[mask] (:382-385),
+    per-sample boolean split (:387-391).  Returns one (F_b, C + 6) tensor per sample (empty when the sample sends nothing;
+    the reference skips those at :392)."""
+    import torch
+    points_cls_prob = torch.sigmoid(points_cls_logit)
+    mask_send = points_cls_prob[:, 0] < threshold
+    points_to_send = torch.cat([points[mask_send, 1:], points_cls_prob[mask_send], points_flow3d[mask_send]], dim=1)
+    points_to_send_batch_idx = points[mask_send, 0].long()
+    return [points_to_send[points_to_send_batch_idx == b_idx] for b_idx in range(batch_size)]

@@ -24,7 +24,8 @@ def __getattr__(name):
     if name in ("class_agnostic_nms", "multi_classes_nms", "nms_gpu", "nms_normal_gpu", "boxes_iou_bev"):
         from . import nms
         return getattr(nms, name)
-    if name in ("pack_exchange", "unpack_exchange", "read_exchange", "write_exchange", "ExchangeMessage"):
+    if name in ("pack_exchange", "unpack_exchange", "read_exchange", "write_exchange", "ExchangeMessage", "select_foreground",
+                "exchange_payloads"):
         from . import exchange
         return getattr(exchange, name)
     if name in ("fuse_agent_points",):

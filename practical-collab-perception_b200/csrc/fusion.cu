@@ -205,7 +205,151 @@ extern "C" int pcp_unpack_points(const float* packed, int32_t n_packed_cols, con
   return 0;
 }
 
+namespace pcp {
+
+// ------------------------------------------------------------------------------------------------
+// producer side of the exchange: foreground selection (reference: pcdet/models/bev_layers/hunter_jr.py:377-397)
+//   prob = sigmoid(cls_logit);  send = prob[:, 0] < threshold;  row = [point columns 1.. | prob (3) | flow (3)];
+//   per sample b: the rows with int(points[:, 0]) == b, in input order.
+// Stable partition by sample: per-CTA kept counts per sample (sample-major table), one-block exclusive scan, write.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 256;
+constexpr int kSelItems = 4;
+constexpr int kSelBlock = kSelThreads * kSelItems;
+
+struct SelArgs {
+  const float* points; int64_t p_stride; int32_t n_pt_cols;      // columns 1 .. n_pt_cols are sent (column 0 = sample index)
+  const float* logit; int64_t l_stride;
+  const float* flow; int64_t f_stride;
+  int32_t frames; float threshold;
+};
+
+__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// sample index of row i if it is sent, else -1
+__device__ __forceinline__ int sel_frame(const SelArgs& A, int64_t i) {
+  const float p0 = sigmoid_rn(__ldg(A.logit + i * A.l_stride));
+  if (!(p0 < A.threshold)) return -1;
+  const float bf = __ldg(A.points + i * A.p_stride);
+  if (!(bf > -1.f) || !(bf < (float)A.frames)) return -1;
+  return (int)bf;                                              // .long(): truncation toward zero
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+sel_count_kernel(const SelArgs A, int64_t n, int32_t nblk, int32_t* __restrict__ table) {
+  extern __shared__ int32_t s_cnt[];                           // [frames]
+  for (int f = threadIdx.x; f < A.frames; f += kSelThreads) s_cnt[f] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kSelItems; ++u) {
+    const int64_t i = (int64_t)blockIdx.x * kSelBlock + (int64_t)threadIdx.x * kSelItems + u;
+    if (i < n) {
+      const int f = sel_frame(A, i);
+      if (f >= 0) atomicAdd(&s_cnt[f], 1);
+    }
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < A.frames; f += kSelThreads) table[(int64_t)f * nblk + blockIdx.x] = s_cnt[f];
+}
+
+// frame_offsets[f] = first output row of sample f (the scanned table entry of its first CTA); [frames] = total
+__global__ void sel_offsets_kernel(const int32_t* __restrict__ table, const int32_t* __restrict__ total, int32_t nblk,
+                                   int32_t frames, int32_t* __restrict__ frame_offsets) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < frames) frame_offsets[f] = table[(int64_t)f * nblk];
+  if (f == frames) frame_offsets[frames] = *total;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+sel_write_kernel(const SelArgs A, int64_t n, int32_t nblk, const int32_t* __restrict__ table, float* __restrict__ out,
+                 int64_t out_stride) {
+  __shared__ int s_warp[kSelThreads / 32];
+  __shared__ int s_lo, s_hi;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_lo = 0x7fffffff; s_hi = -1; }
+  __syncthreads();
+  int fr[kSelItems];
+  int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+  for (int u = 0; u < kSelItems; ++u) {
+    const int64_t i = (int64_t)blockIdx.x * kSelBlock + (int64_t)tid * kSelItems + u;
+    fr[u] = (i < n) ? sel_frame(A, i) : -1;
+    if (fr[u] >= 0) { lo = min(lo, fr[u]); hi = max(hi, fr[u]); }
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane == 0 && hi >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+  __syncthreads();
+  const int f_lo = s_lo, f_hi = s_hi;
+  // one pass per sample present in this CTA (rows arrive grouped by sample: one pass, two at a sample boundary)
+  for (int f = f_lo; f <= f_hi; ++f) {
+    int c = 0;
+#pragma unroll
+    for (int u = 0; u < kSelItems; ++u) c += (fr[u] == f) ? 1 : 0;
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    __syncthreads();                       // s_warp of the previous pass has been read
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int pos = table[(int64_t)f * nblk + blockIdx.x] + incl - c;
+    for (int w = 0; w < warp; ++w) pos += s_warp[w];
+#pragma unroll
+    for (int u = 0; u < kSelItems; ++u) {
+      if (fr[u] != f) continue;
+      const int64_t i = (int64_t)blockIdx.x * kSelBlock + (int64_t)tid * kSelItems + u;
+      float* dst = out + (int64_t)pos * out_stride;
+      const float* prow = A.points + i * A.p_stride + 1;
+      for (int k = 0; k < A.n_pt_cols; ++k) dst[k] = __ldg(prow + k);
+      dst += A.n_pt_cols;
+      const float* lrow = A.logit + i * A.l_stride;
+      dst[0] = sigmoid_rn(__ldg(lrow)); dst[1] = sigmoid_rn(__ldg(lrow + 1)); dst[2] = sigmoid_rn(__ldg(lrow + 2));
+      const float* frow = A.flow + i * A.f_stride;
+      dst[3] = __ldg(frow); dst[4] = __ldg(frow + 1); dst[5] = __ldg(frow + 2);
+      ++pos;
+    }
+  }
+}
+
+}  // namespace pcp
+
 using namespace pcp;
+
+extern "C" size_t pcp_select_scratch_bytes(int64_t n_points, int32_t num_frames) {
+  if (n_points < 0 || num_frames <= 0) return 0;
+  return sizeof(int32_t) * ((size_t)((n_points + kSelBlock - 1) / kSelBlock) * (size_t)num_frames + 2);
+}
+
+extern "C" int pcp_select_foreground(const float* points, int64_t point_stride, int32_t n_point_cols, const float* cls_logit,
+                                     int64_t logit_stride, const float* flow3d, int64_t flow_stride, int64_t n_points,
+                                     int32_t num_frames, float threshold, int32_t* scratch, float* rows_out,
+                                     int64_t out_stride, int32_t* frame_offsets_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PCP_REQUIRE(scratch && frame_offsets_out, PCP_E_INVALID, "pcp_select_foreground: null argument");
+  PCP_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - kSelBlock, PCP_E_INVALID, "pcp_select_foreground: n_points out of range");
+  PCP_REQUIRE(num_frames >= 1 && num_frames <= 4096, PCP_E_INVALID, "pcp_select_foreground: 1 <= num_frames <= 4096");
+  PCP_REQUIRE(n_points == 0 || (points && cls_logit && flow3d && rows_out), PCP_E_INVALID, "pcp_select_foreground: null input");
+  PCP_REQUIRE(n_point_cols >= 1 && point_stride >= 1 + n_point_cols && logit_stride >= 3 && flow_stride >= 3 &&
+                  out_stride >= n_point_cols + 6, PCP_E_INVALID, "pcp_select_foreground: bad column counts / strides");
+  const int nblk = (int)((n_points + kSelBlock - 1) / kSelBlock);
+  if (nblk == 0) {
+    PCP_CUDA(cudaMemsetAsync(frame_offsets_out, 0, sizeof(int32_t) * (size_t)(num_frames + 1), stream));
+    return 0;
+  }
+  SelArgs A{points, point_stride, n_point_cols, cls_logit, logit_stride, flow3d, flow_stride, num_frames, threshold};
+  int32_t* total = scratch + (size_t)nblk * num_frames;
+  sel_count_kernel<<<nblk, kSelThreads, sizeof(int32_t) * (size_t)num_frames, stream>>>(A, n_points, nblk, scratch);
+  PCP_LAUNCH_CHECK("sel_count_kernel");
+  fuse_scan_kernel<<<1, 1024, 0, stream>>>(scratch, nblk * num_frames, total);
+  PCP_LAUNCH_CHECK("fuse_scan_kernel");
+  sel_offsets_kernel<<<(num_frames + 256) / 256, 256, 0, stream>>>(scratch, total, nblk, num_frames, frame_offsets_out);
+  PCP_LAUNCH_CHECK("sel_offsets_kernel");
+  sel_write_kernel<<<nblk, kSelThreads, 0, stream>>>(A, n_points, nblk, scratch, rows_out, out_stride);
+  PCP_LAUNCH_CHECK("sel_write_kernel");
+  return 0;
+}
 
 extern "C" size_t pcp_fuse_scratch_bytes(int64_t n_points) {
   if (n_points < 0) return 0;

@@ -92,6 +92,57 @@ def pack_exchange(detections: Union[Dict[str, torch.Tensor], torch.Tensor], fore
     return buf
 
 
+def select_foreground(points: torch.Tensor, points_cls_logit: torch.Tensor, points_flow3d: torch.Tensor, batch_size: int,
+                      threshold: float = 0.3):
+    """The foreground records every sample of a batch sends away - drop-in for the test-time block of HunterJr.forward
+    (pcdet/models/bev_layers/hunter_jr.py:377-397): ``sigmoid`` of the 3-class logits, ``P(background) < threshold``, the
+    ``torch.cat`` of ``[points[mask, 1:], prob[mask], flow[mask]]`` and the per-sample split, as ONE stable partition on the
+    GPU (csrc/fusion.cu: pcp_select_foreground) followed by one (batch_size + 1)-int read-back.
+
+    points (N, 1 + C) with the sample index in column 0 (C = 7: point5 | sweep_idx | inst_idx), points_cls_logit (N, 3),
+    points_flow3d (N, 3), all on the same GPU.  Returns a list of ``batch_size`` (F_b, C + 6) fp32 tensors (views of one
+    buffer; a sample that sends nothing gets an empty one - the reference skips those)."""
+    import ctypes as C
+    from . import _lib
+    from .frontend import _ptr, _stream
+    if not points.is_cuda:
+        raise RuntimeError("select_foreground: tensors must be on the GPU (pcp_b200 has no CPU path)")
+    dev = points.device
+    if points_cls_logit.device != dev or points_flow3d.device != dev:
+        raise RuntimeError("select_foreground: points, points_cls_logit and points_flow3d must be on the same device")
+    n = int(points.shape[0])
+    if points_cls_logit.shape != (n, 3) or points_flow3d.shape != (n, 3) or points.dim() != 2 or points.shape[1] < 2:
+        raise ValueError("select_foreground: expected points (N, 1 + C), points_cls_logit (N, 3), points_flow3d (N, 3)")
+    batch_size = int(batch_size)
+    f32 = lambda t: t.detach() if (t.dtype == torch.float32 and t.stride(1) == 1) else t.detach().float().contiguous()
+    pts, lg, fl = f32(points), f32(points_cls_logit), f32(points_flow3d)
+    c = int(pts.shape[1]) - 1
+    with torch.cuda.device(dev):
+        lib = _lib.load()
+        rows = torch.empty((max(n, 1), c + 6), dtype=torch.float32, device=dev)
+        offs = torch.empty((batch_size + 1,), dtype=torch.int32, device=dev)
+        scratch = torch.empty(int(lib.pcp_select_scratch_bytes(n, batch_size)) // 4 + 1, dtype=torch.int32, device=dev)
+        rc = lib.pcp_select_foreground(_ptr(pts), pts.stride(0), c, _ptr(lg), lg.stride(0), _ptr(fl), fl.stride(0), n, batch_size,
+                                       C.c_float(threshold), _ptr(scratch), _ptr(rows), rows.stride(0), _ptr(offs), _stream())
+        _lib.check(rc, "pcp_select_foreground")
+        o = offs.cpu().tolist()                              # the one host read (the reference syncs on torch.any(mask_send))
+    return [rows[o[b]:o[b + 1]] for b in range(batch_size)]
+
+
+def exchange_payloads(pred_dicts, foreground_per_sample, agent_ids, timestamps):
+    """One ExchangeMessage buffer per sample of a batch: the (M, 9) ``mo_pts`` records CenterHead assembles
+    (center_head.py:409-427: cat of pred_boxes | pred_scores | pred_labels) and the sample's foreground records
+    (``select_foreground``), packed on the device - what the reference torch.save()s as ``*_modar.pth`` /
+    ``*_foreground.pth``.  Samples without boxes send nothing (None), as in the reference."""
+    out = []
+    for pred, fg, aid, ts in zip(pred_dicts, foreground_per_sample, agent_ids, timestamps):
+        if pred["pred_boxes"].shape[0] == 0:
+            out.append(None)
+            continue
+        out.append(pack_exchange(pred, fg if (fg is not None and fg.shape[0]) else None, agent_id=int(aid), timestamp=float(ts)))
+    return out
+
+
 def parse_header(header: bytes):
     """-> (agent_id, timestamp, M, F); raises ValueError on a foreign or newer message."""
     if len(header) < HEADER_BYTES:

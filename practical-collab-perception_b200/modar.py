@@ -10,6 +10,7 @@ after the ego rows.  All agents of a frame are processed by ONE kernel launch (c
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Dict, Optional, Sequence, Union
 
 import numpy as np
@@ -53,18 +54,22 @@ def _as_boxes9(det: Union[Dict[str, torch.Tensor], torch.Tensor], device) -> tor
     return t
 
 
-_staging = {}   # device -> [pinned uint8 buffer, event of the last H2D that read it]
+_staging = {}   # (device, stream, thread) -> [pinned uint8 buffer, event of the last H2D that read it]
+_staging_lock = threading.Lock()
 
 
 def _upload(dev, arrays):
-    """One asynchronous H2D copy for all the small host-side arrays of a call (poses, offsets): they are packed into a
-    pinned staging buffer (8-byte aligned pieces) and come back as typed views of one device buffer."""
+    """One asynchronous H2D copy for all the small host-side arrays of a call (poses, offsets, pointers): they are packed
+    into a pinned staging buffer (8-byte aligned pieces) and come back as typed views of one device buffer.  One staging
+    buffer per (device, stream, host thread): concurrent callers never share one."""
     sizes = [(a.nbytes + 7) // 8 * 8 for a in arrays]
     total = max(sum(sizes), 8)
-    st = _staging.get(dev)
-    if st is None or st[0].numel() < total:
-        st = [torch.empty(max(total, 4096), dtype=torch.uint8).pin_memory(), None]
-        _staging[dev] = st
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, threading.get_ident())
+    with _staging_lock:
+        st = _staging.get(key)
+        if st is None or st[0].numel() < total:
+            st = [torch.empty(max(total, 4096), dtype=torch.uint8).pin_memory(), None]
+            _staging[key] = st
     if st[1] is not None:
         st[1].synchronize()                      # the previous call's copy has left the staging buffer
     host = st[0].numpy()
@@ -124,8 +129,6 @@ def _modar_exchange(detections, foreground, target_se3_agent, t_detect, t_query,
         raise ValueError(f"ego_points must have 13 or 14 columns, got {ncol}")
     with_b = ncol == 14
     ego = ego_points if (ego_points.dtype == torch.float32 and ego_points.is_contiguous()) else ego_points.float().contiguous()
-    if max_sweep_idx is None:
-        max_sweep_idx = float(ego[:, -2].max().item()) if ego.shape[0] else 0.0     # :174
     scale = flow_scale(t_detect, t_query, sample_interval)
 
     boxes = [_as_boxes9(d, dev) for d in detections]
@@ -150,22 +153,29 @@ def _modar_exchange(detections, foreground, target_se3_agent, t_detect, t_query,
     fg_off = np.zeros(n_agents + 1, dtype=np.int32)
     box_off[1:] = np.cumsum([b.shape[0] for b in boxes])
     fg_off[1:] = np.cumsum([f.shape[0] for f in fgs])
-    se3 = np.stack([np.asarray(t, dtype=np.float64)[:3, :4].reshape(12) for t in target_se3_agent])
     for t in target_se3_agent:
         if np.asarray(t).shape != (4, 4):
             raise ValueError("target_se3_agent must be (4, 4)")
-    boxes_all = torch.cat(boxes, dim=0).contiguous()
-    fg_all = torch.cat(fgs, dim=0).contiguous()
-    se3_d, meta = _upload(dev, [se3, np.concatenate([box_off, fg_off])])          # one small asynchronous H2D
-    box_idx = torch.empty((max(fg_all.shape[0], 1),), dtype=torch.int32, device=dev)
-    have_fg = fg_all.shape[0] > 0
+    se3 = np.stack([np.asarray(t, dtype=np.float64)[:3, :4].reshape(12) for t in target_se3_agent])
+    # Nothing is gathered and nothing is read back: the kernel takes one device pointer per agent (records stay where the
+    # exchange format left them) and the sweep index from device memory (reduced there when the caller did not give it).
+    box_ptrs = np.asarray([b.data_ptr() if b.shape[0] else 0 for b in boxes], dtype=np.uint64)
+    fg_ptrs = np.asarray([f.data_ptr() if f.shape[0] else 0 for f in fgs], dtype=np.uint64)
+    msi_host = np.asarray([0.0 if max_sweep_idx is None else float(max_sweep_idx)], dtype=np.float32)
+    se3_d, meta, bp_d, fp_d, msi_d = _upload(dev, [se3, np.concatenate([box_off, fg_off]), box_ptrs, fg_ptrs, msi_host])
+    if max_sweep_idx is None:                                                       # points_[:, -2].max() (:174)
+        rc = lib.pcp_column_max(_ptr(ego), ego.stride(0), n_ego, ncol - 2, _ptr(msi_d), _stream())
+        _lib.check(rc, "pcp_column_max")
+    n_fg = int(fg_off[-1])
+    have_fg = n_fg > 0
+    box_idx = torch.empty((max(n_fg, 1),), dtype=torch.int32, device=dev)
     rows = out[n_ego:]
-    rc = lib.pcp_modar(_ptr(boxes_all), C.c_void_p(meta.data_ptr()), _ptr(fg_all) if have_fg else None,
-                       C.c_void_p(meta.data_ptr() + 4 * (n_agents + 1)), _ptr(se3_d), n_agents,
-                       int(max(b.shape[0] for b in boxes)), int(max(f.shape[0] for f in fgs)),
-                       C.c_float(scale), C.c_float(max_sweep_idx), int(with_b), C.c_float(batch_idx),
-                       _ptr(rows), ncol, _ptr(box_idx), _stream())
-    _lib.check(rc, "pcp_modar")
+    rc = lib.pcp_modar_agents(_ptr(bp_d), C.c_void_p(meta.data_ptr()), _ptr(fp_d) if have_fg else None,
+                              C.c_void_p(meta.data_ptr() + 4 * (n_agents + 1)), _ptr(se3_d), n_agents,
+                              int(max(b.shape[0] for b in boxes)), int(max(f.shape[0] for f in fgs)),
+                              C.c_float(scale), _ptr(msi_d), int(with_b), C.c_float(batch_idx),
+                              _ptr(rows), ncol, _ptr(box_idx), _stream())
+    _lib.check(rc, "pcp_modar_agents")
     if return_box_idx:
-        return out, (box_idx[:fg_all.shape[0]] if have_fg else None)
+        return out, (box_idx[:n_fg] if have_fg else None)
     return out

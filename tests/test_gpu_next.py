@@ -284,3 +284,50 @@ def test_points_prefetcher_streams_batches_in_order():
         assert float(rows[:, [4, 6, 7]].abs().max()) == 0.0 if rows.shape[0] else True
     with pytest.raises(RuntimeError):
         pre.get()
+
+
+@pytest.mark.parametrize("n,frames,sorted_by_frame", [(50000, 4, True), (3001, 3, False), (0, 2, True), (7, 5, True)])
+def test_select_foreground_matches_the_reference_block(n, frames, sorted_by_frame):
+    """pcp_b200.select_foreground vs the restated hunter_jr.py:377-397 block: the same rows, in the same order, per sample;
+    probabilities to 1e-6 (expf of the GPU vs the CPU's vectorised exp), everything else bit for bit.  Rows within 2e-6 of
+    the 0.3 threshold are steered away from it (a last-bit difference of sigmoid may flip them)."""
+    import pcp_b200
+    from oracle import next_oracle as no
+    g = torch.Generator().manual_seed(n + frames)
+    pts = torch.randn(n, 8, generator=g)
+    b = torch.randint(0, frames, (n,), generator=g).float()
+    pts[:, 0] = torch.sort(b).values if sorted_by_frame else b
+    if n > 5:
+        pts[3, 0] = float(frames)                      # a row of a sample the batch does not have: never sent
+    logit = torch.randn(n, 3, generator=g) * 2
+    p0 = torch.sigmoid(logit[:, 0])
+    logit[(p0 - 0.3).abs() < 2e-6, 0] += 0.01
+    flow = torch.randn(n, 3, generator=g)
+    want = no.select_foreground(pts, logit, flow, frames)
+    got = pcp_b200.select_foreground(pts.to(DEV), logit.to(DEV), flow.to(DEV), frames)
+    assert len(got) == frames
+    for w, gt in zip(want, got):
+        gt = gt.cpu()
+        assert gt.shape == w.shape
+        assert torch.equal(gt[:, :7], w[:, :7]) and torch.equal(gt[:, 10:], w[:, 10:])
+        assert torch.allclose(gt[:, 7:10], w[:, 7:10], rtol=0, atol=1e-6)
+
+
+def test_exchange_payloads_round_trip_through_the_wire_format():
+    """select_foreground + exchange_payloads -> unpack_exchange -> modar_exchange consumes the records unchanged."""
+    import pcp_b200
+    from pcp_b200 import exchange
+    g = torch.Generator().manual_seed(3)
+    n = 4000
+    pts = torch.randn(n, 8, generator=g)
+    pts[:, 0] = torch.sort(torch.randint(0, 2, (n,), generator=g).float()).values
+    logit, flow = torch.randn(n, 3, generator=g) * 2, torch.randn(n, 3, generator=g)
+    fg = pcp_b200.select_foreground(pts.to(DEV), logit.to(DEV), flow.to(DEV), 2)
+    preds = [{"pred_boxes": torch.randn(5, 7, generator=g).to(DEV), "pred_scores": torch.rand(5, generator=g).to(DEV),
+              "pred_labels": torch.ones(5).to(DEV)},
+             {"pred_boxes": torch.zeros(0, 7).to(DEV), "pred_scores": torch.zeros(0).to(DEV), "pred_labels": torch.zeros(0).to(DEV)}]
+    msgs = exchange.exchange_payloads(preds, fg, agent_ids=[1, 2], timestamps=[0.2, 0.2])
+    assert msgs[1] is None                              # no boxes: nothing is sent (center_head.py:413)
+    m = exchange.unpack_exchange(msgs[0])
+    assert m.agent_id == 1 and m.boxes.shape == (5, 9) and torch.equal(m.foreground, fg[0])
+    assert torch.equal(m.boxes[:, :7], preds[0]["pred_boxes"])
