@@ -14,7 +14,10 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
+        "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
