@@ -120,6 +120,13 @@ int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int3
  *                           mean is the sequential sum in row order for pillars of ANY length (the histogram path falls back
  *                           to arrival order above 4096 points).  Covers key spaces of at most 4 M cells (16 frames of
  *                           512 x 512) and 1 .. 16.6 M rows; PCP_E_UNSUPPORTED outside.
+ *   PCP_VOXELIZE_BINNED     one coarse partition pass into bins of 2048 consecutive cells ({x, y, z, row} records, unordered
+ *                           inside a bin), then one CTA per bin: rows per cell, scan, placement, pillars of up to 8 rows put in
+ *                           row order and averaged from the contiguous records, global ranks from a look-back over 64-byte
+ *                           tile records; longer pillars go through the work lists (csrc/voxelize_binned.cu).  One returning
+ *                           global atomic per (CTA, bin) instead of one per point, 20 KB cleared instead of 8 MB, 4 launches
+ *                           instead of 5 - and still slower than HISTOGRAM (169 vs 152 us on the bench batch, DESIGN.md
+ *                           section 3).  Covers n_points >= 1 and at most 4 M cells; PCP_E_UNSUPPORTED outside.
  */
 #define PCP_VOXELIZE_AUTO      0
 #define PCP_VOXELIZE_HISTOGRAM 1
