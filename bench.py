@@ -595,6 +595,43 @@ def run_ours(args):
     e2e_value = max(e2e_runs)
     e2e_h2d = int(packed[0].data.numel() * 4 + packed[0].frame_offsets.numel() * 4)
 
+    # ---------------- the reference's own modules on THIS GPU (rank 0, outside the timed region) ----------------
+    # The same unmodified files as the CPU arm, moved to the device: torch ops on CUDA tensors (torch.unique, index_add_,
+    # scatter-reduce through the pure-torch torch_scatter restatement, nn.Linear / BatchNorm1d, index assignment per frame).
+    ref_gpu = None
+    if rank == 0:
+        try:
+            from oracle import ref_loader as rl
+            if rl.reference_available():
+                torch.cuda.empty_cache()
+                r_vfe, r_scat = rl.build_reference_front_end(C_RAW, syn.V2X_VOXEL, rng, grid)
+                r_vfe.load_state_dict(sd)
+                r_vfe, r_scat = r_vfe.to(dev), r_scat.to(dev)
+                for name in ("grid_size", "voxel_size", "point_cloud_range"):     # plain tensor attributes (.cuda() in the ctor, :87-89)
+                    t = getattr(r_vfe, name, None)
+                    if torch.is_tensor(t):
+                        setattr(r_vfe, name, t.to(dev))
+                ts = []
+                with torch.no_grad():
+                    for i in range(5):
+                        a0, a1 = ev(), ev()
+                        a0.record()
+                        bd_r = r_scat(r_vfe({"points": dev_batches[i & 1], "batch_size": B}))
+                        a1.record()
+                        torch.cuda.synchronize()
+                        if i >= 2:
+                            ts.append(a0.elapsed_time(a1))
+                ms_r = statistics.median(ts)
+                ref_gpu = {"value": B / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r,
+                           "pillars": int(bd_r["voxel_coords"].shape[0]),
+                           "note": "the reference's own DynamicPillarVFE.forward + PointPillarScatter.forward (unmodified files, "
+                                   "torch_scatter = its pure-torch restatement) on the same GPU and the same device-resident "
+                                   "8-frame batch, CUDA events, median of 3"}
+                del r_vfe, r_scat, bd_r
+                torch.cuda.empty_cache()
+        except Exception as exc:
+            ref_gpu = {"error": repr(exc)[:200]}
+
     line = None
     if rank == 0:
         cpu = None
@@ -632,6 +669,7 @@ def run_ours(args):
                                "frac": chain_achieved / peak, "algorithmic_bytes": chain_bytes,
                                "note": "SURVEY 8d bytes of the whole voxelize+PFN+scatter chain / step time"},
             "cpu_baseline": cpu,
+            "reference_on_gpu": ref_gpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": 4 * _lib.PCP_COUNTS_LEN, "steps": e2e_steps, "runs": e2e_runs,
                     "api": "PointsPrefetcher(collate_points(frames, columns = the 5 raw point features)) -> "

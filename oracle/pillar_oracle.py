@@ -36,10 +36,10 @@ def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim_size: Optional[int]
     """torch_scatter.scatter_mean(src, index, dim=0); call site dynamic_pillar_vfe.py:110."""
     if dim_size is None:
         dim_size = int(index.max()) + 1 if index.numel() else 0
-    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype)
-    out.index_add_(0, index, src)                       # sequential, in row order, on CPU
-    cnt = torch.zeros(dim_size, dtype=src.dtype)
-    cnt.index_add_(0, index, torch.ones(index.shape[0], dtype=src.dtype))
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    out.index_add_(0, index, src)                       # sequential, in row order, on CPU (atomics on a CUDA tensor)
+    cnt = torch.zeros(dim_size, dtype=src.dtype, device=src.device)
+    cnt.index_add_(0, index, torch.ones(index.shape[0], dtype=src.dtype, device=src.device))
     cnt.clamp_(min=1)
     return out / cnt.view(-1, *([1] * (src.dim() - 1)))
 
@@ -48,7 +48,7 @@ def scatter_max(src: torch.Tensor, index: torch.Tensor, dim_size: Optional[int] 
     """torch_scatter.scatter_max(src, index, dim=0)[0]; call site dynamic_pillar_vfe.py:40."""
     if dim_size is None:
         dim_size = int(index.max()) + 1 if index.numel() else 0
-    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype)
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     if index.numel() == 0:
         return out
     idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)

@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--l2-persist", type=float, default=0.0,
                     help="fraction of the input rows pinned in L2 (access policy window on the voxelize / PFN streams); 0 = off")
+    ap.add_argument("--l2-persist-ws", type=float, default=0.0,
+                    help="MB at the start of each voxelize workspace (histogram, rank map, keys, slots, sorted rows) marked "
+                         "persisting in L2 on the voxelize / PFN stream, so that the canvas stream cannot evict them; 0 = off")
     args = ap.parse_args()
     from pcp_b200 import synthetic as syn
     from pcp_b200.frontend import FrontEnd, GridSpec
@@ -72,17 +75,29 @@ def main():
         _fields_ = [("win", _Win), ("pad", ctypes.c_char * 64)]
 
     rt = None
-    if args.l2_persist > 0:
+    if args.l2_persist > 0 or args.l2_persist_ws > 0:
         rt = ctypes.CDLL("libcudart.so.12")
         mx, mw = ctypes.c_int(), ctypes.c_int()
         rt.cudaDeviceGetAttribute(ctypes.byref(mx), 108, 0)      # cudaDevAttrMaxPersistingL2CacheSize
         rt.cudaDeviceGetAttribute(ctypes.byref(mw), 109, 0)      # cudaDevAttrMaxAccessPolicyWindowSize
-        rc = rt.cudaDeviceSetLimit(6, ctypes.c_size_t(mx.value))  # cudaLimitPersistingL2CacheSize
+        want = mx.value if args.l2_persist > 0 else min(mx.value, int(args.l2_persist_ws * 2**20))
+        rc = rt.cudaDeviceSetLimit(6, ctypes.c_size_t(want))      # cudaLimitPersistingL2CacheSize
+        mx = ctypes.c_int(want)
         print(json.dumps({"max_persisting_l2": mx.value, "max_window": mw.value, "set_limit_rc": rc}), flush=True)
         max_persist, max_window = mx.value, mw.value
 
-    def set_window(stream, t):
+    def set_window(stream, t, k=0):
         if rt is None:
+            return
+        if args.l2_persist_ws > 0:
+            ws = fes[k].ws.buf
+            if ws is None:                      # first use of this buffer set: the workspace is allocated by the call itself
+                return
+            a = _Attr()
+            nbytes = min(int(args.l2_persist_ws * 2**20), ws.numel(), max_window)
+            a.win = _Win(ws.data_ptr(), nbytes, min(1.0, max_persist / nbytes), 2, 1)      # persisting hits / streaming misses
+            rc = rt.cudaStreamSetAttribute(ctypes.c_void_p(stream.cuda_stream), 1, ctypes.byref(a))
+            assert rc == 0, rc
             return
         a = _Attr()
         nbytes = min(t.numel() * 4, max_window)
@@ -123,9 +138,9 @@ def main():
                 pts = batches[i & 1]
                 if done_c[k] is not None:
                     sv.wait_event(done_c[k])            # buffer set k is free again
-                set_window(sv, pts)
+                set_window(sv, pts, k)
                 if sp is not sv:
-                    set_window(sp, pts)
+                    set_window(sp, pts, k)
                 with torch.cuda.stream(sv):
                     fes[k].voxelize(pts, B, outs[k], want_point_pillar=False)
                     e_v = torch.cuda.Event()
@@ -169,7 +184,7 @@ def main():
         plans += [("vp_c", least, least, least, nb), ("vp_c", greatest, greatest, least, nb), ("vp_c", least, least, greatest, nb)]
     plans += [("v_p_c", least, least, least, 3), ("v_p_c", greatest, least, least, 3), ("v_p_c", greatest, greatest, least, 3),
               ("v_p_c", least, greatest, least, 3), ("v_p_c", greatest, least, greatest, 3)]
-    if args.l2_persist > 0:
+    if args.l2_persist > 0 or args.l2_persist_ws > 0:
         plans = [("serial", 0, 0, 0, 1), ("vp_c", greatest, greatest, least, 2), ("vp_c", greatest, greatest, least, 3)]
     for mode, pv, pp, pc, nb in plans:
         us, ok = run(mode, pv, pp, pc, nb, args.steps)
