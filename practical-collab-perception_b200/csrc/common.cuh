@@ -87,6 +87,8 @@ __host__ __device__ inline int class_of(int n) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kHdrInts = 64;
 constexpr int kHdrPrepTicket = 16;   // [16, 20): work tickets of pillar_prep_kernel (long, mid-16, mid-32, short)
+constexpr int kHdrScanTicket = 20;   // tile ticket of the single-launch cell scan
+constexpr int kScanFusedMaxTiles = 2048;   // above this the scan runs as two launches (every tile sums ALL records before it)
 constexpr int kHdrListCount = 32;    // [32, 32 + kNumLists): entries in each list
 constexpr int kHdrLongCount = 48;    // long pillars
 constexpr int kHdrBigCount = 49;     // long pillars above kWarpLongMax rows (handled by a whole CTA in pillar_prep_kernel)

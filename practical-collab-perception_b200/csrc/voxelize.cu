@@ -317,6 +317,239 @@ scan_cells_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, i
   }
 }
 
+// Single-launch form of the two kernels above for key spaces of at most kScanFusedMaxTiles tiles (4 M cells): every tile
+// computes its own record, PUBLISHES it - every field stored + 1 into memory the prologue memset zeroed, as four 16-byte
+// stores, so a quarter counts as published when none of its four words is zero: no flag, no fence - and then sums the
+// records of all tiles before it.  A tile publishes before it waits and tiles are numbered by a ticket in start order
+// (every lower-numbered tile is already running), so the wait cannot deadlock.  Saves one launch and the second read of
+// the cell array's counts.
+__device__ __forceinline__ int4 ld_volatile_int4(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_volatile_int(const int32_t* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kScanThreads, 4)
+scan_cells_fused_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_rank, int64_t cells, int32_t nx, int32_t ny,
+                        int32_t* __restrict__ tile_info, int32_t* __restrict__ tile_frames, int32_t* __restrict__ hdr,
+                        int32_t* __restrict__ seg_off, int32_t* __restrict__ voxel_coords,
+                        int32_t* __restrict__ pillar_count, unsigned long long* __restrict__ lists, const ListOffsets lo,
+                        int4* __restrict__ long_table, int32_t* __restrict__ big_list, int32_t scan_tiles) {
+  __shared__ int s_cls[kTiInts];                 // running in-tile counters (classes, long, segs, big)
+  __shared__ int s_rec[kTiInts];                 // this tile's record
+  __shared__ int s_before[kTiInts];              // sums over the tiles before this one (kTiMax: max)
+  __shared__ int s_part[kScanThreads / 32][kTiInts];
+  __shared__ unsigned long long s_warp[kScanThreads / 32];
+  __shared__ long long s_lo[kNumClasses];
+  __shared__ int s_frw[kScanThreads / 32];
+  __shared__ int s_tile, s_fr;
+  __shared__ int32_t s_pcnt[kScanTileCells];     // rows of the pillar
+  __shared__ int32_t s_poff[kScanTileCells];     // its first sorted position (local to the tile until the prefix is known)
+  __shared__ uint16_t s_pidx[kScanTileCells];    // its cell inside the tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_tile = atomicAdd(&hdr[kHdrScanTicket], 1); s_fr = 0; }
+  if (tid < kTiInts) { s_cls[tid] = 0; s_rec[tid] = 0; }
+  if (tid < kNumClasses) s_lo[tid] = lo.off[tid];
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t base = (int64_t)tile * kScanTileCells + (int64_t)tid * kScanItems;
+  int32_t c[kScanItems];
+  load_tile_counts(cell, base, cells, c);
+  // ---- this tile's record (as tile_sums_kernel) ----
+  unsigned long long mine = 0;
+  {
+    int pts = 0, pil = 0, cmax = 0, last_nonempty = -1, nlong = 0, nseg = 0, nbig = 0;
+    unsigned long long cls = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (c[j] > 0) {
+        pts += c[j]; ++pil; cmax = max(cmax, c[j]); last_nonempty = j;
+        if (c[j] <= kSegRows) cls += 1ull << (6 * class_of(c[j]));
+        else { ++nlong; nseg += (c[j] + kSegRows - 1) / kSegRows; nbig += (c[j] > kWarpLongMax) ? 1 : 0; }
+      }
+    }
+    mine = ((unsigned long long)(uint32_t)pts << 32) | (unsigned long long)(uint32_t)pil;
+    const int wpts = __reduce_add_sync(0xffffffffu, pts), wpil = __reduce_add_sync(0xffffffffu, pil);
+    const int wmax = __reduce_max_sync(0xffffffffu, cmax);
+    if (wpil) {
+      if (lane == 0) { atomicAdd(&s_rec[kTiPoints], wpts); atomicAdd(&s_rec[kTiPillars], wpil); atomicMax(&s_rec[kTiMax], wmax); }
+#pragma unroll
+      for (int k = 0; k < kNumClasses; ++k) {
+        const int v = __reduce_add_sync(0xffffffffu, (int)((cls >> (6 * k)) & 63ull));
+        if (lane == 0 && v) atomicAdd(&s_rec[kTiClass + k], v);
+      }
+    }
+    if (__any_sync(0xffffffffu, nlong > 0)) {
+      const int a = __reduce_add_sync(0xffffffffu, nlong), b = __reduce_add_sync(0xffffffffu, nseg);
+      const int d = __reduce_add_sync(0xffffffffu, nbig);
+      if (lane == 0) { atomicAdd(&s_rec[kTiLong], a); atomicAdd(&s_rec[kTiSegs], b); atomicAdd(&s_rec[kTiBig], d); }
+    }
+    int fr = 0;
+    if (last_nonempty >= 0) fr = (int)(((uint32_t)base + (uint32_t)last_nonempty) / ((uint32_t)nx * (uint32_t)ny)) + 1;
+    fr = __reduce_max_sync(0xffffffffu, fr);
+    if (lane == 0 && fr) atomicMax(&s_fr, fr);
+  }
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  // ---- publish ----
+  if (tid < 4) {
+    const int4 v = make_int4(s_rec[4 * tid] + 1, s_rec[4 * tid + 1] + 1, s_rec[4 * tid + 2] + 1, s_rec[4 * tid + 3] + 1);
+    *reinterpret_cast<int4*>(tile_info + (int64_t)tile * kTiInts + 4 * tid) = v;
+  }
+  if (tid == 4) tile_frames[tile] = s_fr + 1;
+  unsigned long long warp_excl = 0, tile_total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    if (w < warp) warp_excl += s_warp[w];
+    tile_total += s_warp[w];
+  }
+  // ---- local ranks / positions; non-empty cells -> compact per-pillar arrays ----
+  const unsigned long long excl0 = warp_excl + (incl - mine);
+  const int rl0 = (int)(excl0 & 0xffffffffull), ol0 = (int)(excl0 >> 32);     // local rank / position of this thread's first pillar
+  {
+    int rl = rl0, ol = ol0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (c[j] > 0) {
+        s_pcnt[rl] = c[j]; s_poff[rl] = ol; s_pidx[rl] = (uint16_t)(tid * kScanItems + j);
+        ++rl; ol += c[j];
+      }
+    }
+  }
+  // ---- sum of the records of all tiles before this one ----
+  {
+    int acc[kTiInts];
+#pragma unroll
+    for (int i = 0; i < kTiInts; ++i) acc[i] = 0;
+    for (int t0 = tid; t0 < tile; t0 += kScanThreads * 2) {
+      int4 v[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t0 + u * kScanThreads;
+        if (t < tile) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[u][q] = ld_volatile_int4(tile_info + (int64_t)t * kTiInts + 4 * q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t0 + u * kScanThreads;
+        if (t < tile) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            while (v[u][q].x == 0 || v[u][q].y == 0 || v[u][q].z == 0 || v[u][q].w == 0) {
+              __nanosleep(40);
+              v[u][q] = ld_volatile_int4(tile_info + (int64_t)t * kTiInts + 4 * q);
+            }
+            acc[4 * q + 0] += v[u][q].x - 1; acc[4 * q + 1] += v[u][q].y - 1; acc[4 * q + 2] += v[u][q].z - 1;
+            if (q < 3) acc[4 * q + 3] += v[u][q].w - 1; else acc[kTiMax] = max(acc[kTiMax], v[u][q].w - 1);
+          }
+        }
+      }
+    }
+    int frames = 0;
+    if (tile == scan_tiles - 1) {
+      for (int t = tid; t < tile; t += kScanThreads) {
+        int f = ld_volatile_int(tile_frames + t);
+        while (f == 0) { __nanosleep(40); f = ld_volatile_int(tile_frames + t); }
+        frames = max(frames, f - 1);
+      }
+      frames = __reduce_max_sync(0xffffffffu, frames);
+    }
+#pragma unroll
+    for (int i = 0; i < kTiInts; ++i)
+      acc[i] = (i == kTiMax) ? __reduce_max_sync(0xffffffffu, acc[i]) : __reduce_add_sync(0xffffffffu, acc[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kTiInts; ++i) s_part[warp][i] = acc[i];
+      s_frw[warp] = frames;
+    }
+  }
+  __syncthreads();
+  if (tid < kTiInts) {
+    int v = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) v = (tid == kTiMax) ? max(v, s_part[w][tid]) : v + s_part[w][tid];
+    s_before[tid] = v;
+  }
+  __syncthreads();
+  const int32_t r_tile = s_before[kTiPillars], off_tile = s_before[kTiPoints];
+  if (tile == scan_tiles - 1) {
+    if (tid == 0) {
+      const int32_t P = r_tile + s_rec[kTiPillars];
+      const int32_t Nk = off_tile + s_rec[kTiPoints];
+      hdr[PCP_COUNT_PILLARS] = P;
+      hdr[PCP_COUNT_KEPT] = Nk;
+      hdr[PCP_COUNT_MAX_PER_PILLAR] = max(s_before[kTiMax], s_rec[kTiMax]);
+      seg_off[P] = Nk;
+      hdr[kHdrLongCount] = s_before[kTiLong] + s_rec[kTiLong];
+      hdr[kHdrListCount + kSegList] = s_before[kTiSegs] + s_rec[kTiSegs];
+      hdr[kHdrBigCount] = s_before[kTiBig] + s_rec[kTiBig];
+      int frames = s_fr;
+#pragma unroll
+      for (int w = 0; w < kScanThreads / 32; ++w) frames = max(frames, s_frw[w]);
+      hdr[PCP_COUNT_FRAMES] = frames;
+    }
+    if (tid < kNumClasses) hdr[kHdrListCount + tid] = s_before[kTiClass + tid] + s_rec[kTiClass + tid];
+  }
+  // ---- per cell: first sorted position / rank (or -1) as vector stores ----
+  {
+    int32_t vo[kScanItems], vr[kScanItems];
+    int rl = r_tile + rl0, ol = off_tile + ol0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      vo[j] = -1; vr[j] = -1;
+      if (c[j] > 0) { vo[j] = ol; vr[j] = rl; ++rl; ol += c[j]; }
+    }
+    if (base + kScanItems <= cells) {
+      *reinterpret_cast<int4*>(cell + base) = make_int4(vo[0], vo[1], vo[2], vo[3]);
+      *reinterpret_cast<int4*>(cell + base + 4) = make_int4(vo[4], vo[5], vo[6], vo[7]);
+      *reinterpret_cast<int4*>(cell_rank + base) = make_int4(vr[0], vr[1], vr[2], vr[3]);
+      *reinterpret_cast<int4*>(cell_rank + base + 4) = make_int4(vr[4], vr[5], vr[6], vr[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j)
+        if (base + j < cells) { cell[base + j] = vo[j]; cell_rank[base + j] = vr[j]; }
+    }
+  }
+  // ---- per pillar, consecutive threads = consecutive ranks (as scan_cells_kernel phase B) ----
+  const int npil = (int)(tile_total & 0xffffffffull);
+  const uint32_t nxy = (uint32_t)nx * (uint32_t)ny;
+  const uint32_t tile_cell0 = (uint32_t)tile * (uint32_t)kScanTileCells;
+  for (int q = tid; q < npil; q += kScanThreads) {
+    const int32_t cnt = s_pcnt[q], off = off_tile + s_poff[q];
+    const int32_t r = r_tile + q;
+    const uint32_t idx = tile_cell0 + s_pidx[q];
+    const uint32_t b = idx / nxy, rem = idx - b * nxy;
+    const uint32_t cx = rem / (uint32_t)ny, cy = rem - cx * (uint32_t)ny;
+    seg_off[r] = off;
+    if (voxel_coords) *reinterpret_cast<int4*>(voxel_coords + 4 * (int64_t)r) = make_int4((int)b, 0, (int)cy, (int)cx);
+    if (pillar_count) pillar_count[r] = cnt;
+    if (cnt <= kSegRows) {
+      const int k = class_of(cnt);
+      const int slot = s_before[kTiClass + k] + atomicAdd(&s_cls[kTiClass + k], 1);
+      lists[s_lo[k] + slot] = pack_entry(r, off, cnt);
+    } else {
+      const int nseg = (cnt + kSegRows - 1) / kSegRows;
+      const int li = s_before[kTiLong] + atomicAdd(&s_cls[kTiLong], 1);
+      const int sb = s_before[kTiSegs] + atomicAdd(&s_cls[kTiSegs], nseg);
+      long_table[li] = make_int4(r, off, cnt, sb);
+      if (cnt > kWarpLongMax) big_list[s_before[kTiBig] + atomicAdd(&s_cls[kTiBig], 1)] = li;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 3. counting-sort scatter + point -> pillar map
 // ------------------------------------------------------------------------------------------------
@@ -759,13 +992,21 @@ namespace pcp {
 int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, int32_t ny, const float* points, int64_t stride,
                     const pcp_grid& grid, int32_t* point_pillar_out, int32_t* voxel_coords_out, int32_t* pillar_count_out,
                     int32_t* counts_out, cudaStream_t stream) {
-  tile_sums_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(W.cell, L.cells, nx, ny, W.tile_info,
-                                                                      W.tile_info + 16 * (L.scan_tiles + 1));
-  PCP_LAUNCH_CHECK("tile_sums_kernel");
-  scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
-      W.cell, W.cell_rank, L.cells, nx, ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
-      W.lists, L.lo, W.long_table, W.big_list, L.scan_tiles);
-  PCP_LAUNCH_CHECK("scan_cells_kernel");
+  if (L.scan_tiles <= kScanFusedMaxTiles) {
+    // one launch: tile records are published and summed inside the kernel (tile_info / hdr were zeroed by the prologue memset)
+    scan_cells_fused_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
+        W.cell, W.cell_rank, L.cells, nx, ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off, voxel_coords_out,
+        pillar_count_out, W.lists, L.lo, W.long_table, W.big_list, (int32_t)L.scan_tiles);
+    PCP_LAUNCH_CHECK("scan_cells_fused_kernel");
+  } else {
+    tile_sums_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(W.cell, L.cells, nx, ny, W.tile_info,
+                                                                        W.tile_info + 16 * (L.scan_tiles + 1));
+    PCP_LAUNCH_CHECK("tile_sums_kernel");
+    scan_cells_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
+        W.cell, W.cell_rank, L.cells, nx, ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off, voxel_coords_out, pillar_count_out,
+        W.lists, L.lo, W.long_table, W.big_list, L.scan_tiles);
+    PCP_LAUNCH_CHECK("scan_cells_kernel");
+  }
   {
     const unsigned blocks = (unsigned)((n + 256 * kPtsPerThread - 1) / (256 * kPtsPerThread));
     place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.cell_rank, n, W.sorted_idx,
