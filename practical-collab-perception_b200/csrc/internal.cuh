@@ -4,6 +4,41 @@
 
 namespace pcp {
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The kernels of the voxelize -> PFN chain run back to back on one stream; launched
+// with launch_pdl() each of them may be scheduled while its predecessor is still draining: it says so itself by calling
+// pdl_launch_dependents() first thing, and it calls pdl_wait() before it touches anything its predecessor wrote (the wait
+// returns when the prerequisite grid has completed and its writes are visible).  The hand-over of the SMs from one kernel of
+// the chain to the next then never passes through an idle scheduler.  Without the launch attribute both calls are no-ops.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+// Which edges of the chain are programmatic (make variant NAME=pdl15 SRC="voxelize pfn_tc" DEFS=-DPCP_PDL_MASK=15).
+// MEASURED (profiles/r02_pdl_matrix.jsonl): with every edge programmatic the chain alone gains 2 % (serial step 457 -> 449 us,
+// voxelize 152 -> 149 us) and voxelize beside the canvas stream drops from 254 to 176 us - but only by starving the canvas
+// (its CTAs never find a free slot between two kernels of the chain any more: 228 -> 417 us), and the PFN, queued early,
+// shuts it out completely: the pipelined step goes from 386 to 499 us (434 us with the PFN edge alone).  The steady state is
+// what the library is built for, so the shipped default is 0: no programmatic edges.
+#ifndef PCP_PDL_MASK
+#define PCP_PDL_MASK 0
+#endif
+constexpr int kPdlScan = 1, kPdlPlace = 2, kPdlPrep = 4, kPdlPfn = 8;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int edge, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (PCP_PDL_MASK & edge) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // voxelize.cu: everything after the keying kernel (cell scan, placement, ascending row order inside every cell;
 // the xyz mean only when `points` is given).
 int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, int32_t ny, const float* points, int64_t stride,

@@ -192,9 +192,12 @@ pfn_slot_kernel(const TcArgs A) {
 
   // ---- one-time setup: parameters -> smem, barriers, TMEM, work prefix ----
   {
+    // the packed parameters do not depend on the voxelize kernels: this copy runs while pillar_prep is still draining
+    // (programmatic dependent launch, internal.cuh); everything below reads what voxelize wrote
     const float4* src = reinterpret_cast<const float4*>(A.params);
     float4* dst = reinterpret_cast<float4*>(smem);
     for (int i = tid; i < SP.panels_end / 4; i += kPfnThreads) dst[i] = __ldg(src + i);   // same order in both layouts
+    pdl_wait();
     const ParamLayout PL = param_layout(A.c_in, kLayers);
     for (int i = tid; i < N0; i += kPfnThreads) {
       smem[SP.prm_a0 + i] = A.params[PL.a0 + i];
@@ -993,8 +996,7 @@ static int launch_cfg(const TcArgs& a, int64_t n_points, cudaStream_t stream) {
   const int64_t groups = n_points / kGroup + kNumLists;
   const int64_t sms = sm_count();            // persistent: one CTA per SM
   const unsigned blocks = (unsigned)(groups < sms ? groups : sms);
-  pfn_slot_kernel<kLayers, kCfg><<<blocks, kPfnThreads, SP.total_bytes, stream>>>(a);
-  PCP_LAUNCH_CHECK("pfn_slot_kernel");
+  PCP_CUDA(launch_pdl(kPdlPfn, pfn_slot_kernel<kLayers, kCfg>, dim3(blocks), dim3(kPfnThreads), (size_t)SP.total_bytes, stream, a));
   return 0;
 }
 

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256)
 quantise_count_kernel(const float* __restrict__ points, int64_t stride, int64_t n, int32_t frames,
                       pcp_grid g, int32_t* __restrict__ cell, int32_t* __restrict__ key,
                       int32_t* __restrict__ within, int32_t* __restrict__ hdr) {
+  pdl_launch_dependents();
   const int64_t base = (int64_t)blockIdx.x * (256 * kPtsPerThread) + threadIdx.x;
   float bf[kPtsPerThread], x[kPtsPerThread], y[kPtsPerThread];
 #pragma unroll
@@ -56,6 +57,7 @@ quantise_count_kernel(const float* __restrict__ points, int64_t stride, int64_t 
       if (bad_frame) atomicAdd(&hdr[PCP_COUNT_BAD_FRAME], 1);
     }
   }
+  pdl_wait();                  // everything above read the caller's rows only
 #pragma unroll
   for (int u = 0; u < kPtsPerThread; ++u)
     if (k[u] >= 0) w[u] = atomicAdd(&cell[k[u]], 1);
@@ -352,6 +354,8 @@ scan_cells_fused_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_r
   __shared__ int32_t s_poff[kScanTileCells];     // its first sorted position (local to the tile until the prefix is known)
   __shared__ uint16_t s_pidx[kScanTileCells];    // its cell inside the tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   if (tid == 0) { s_tile = atomicAdd(&hdr[kHdrScanTicket], 1); s_fr = 0; }
   if (tid < kTiInts) { s_cls[tid] = 0; s_rec[tid] = 0; }
   if (tid < kNumClasses) s_lo[tid] = lo.off[tid];
@@ -558,6 +562,8 @@ place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within
              const int32_t* __restrict__ cell, const int32_t* __restrict__ cell_rank, int64_t n,
              int32_t* __restrict__ sorted_idx, int32_t* __restrict__ point_pillar,
              const int32_t* __restrict__ hdr, int32_t* __restrict__ counts_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t base = (int64_t)blockIdx.x * (256 * kPtsPerThread) + threadIdx.x;
   if (base == 0 && counts_out) {
 #pragma unroll
@@ -725,6 +731,8 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
   __shared__ float s_red[3][8];
   __shared__ int s_chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const int nlong = hdr[kHdrLongCount];
   // Work is handed out in CTA-sized chunks through tickets: CTAs that spent time on a big pillar take fewer chunks.
   auto grab = [&](int which, int chunk) {
@@ -994,10 +1002,9 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
                     int32_t* counts_out, cudaStream_t stream) {
   if (L.scan_tiles <= kScanFusedMaxTiles) {
     // one launch: tile records are published and summed inside the kernel (tile_info / hdr were zeroed by the prologue memset)
-    scan_cells_fused_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(
-        W.cell, W.cell_rank, L.cells, nx, ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off, voxel_coords_out,
-        pillar_count_out, W.lists, L.lo, W.long_table, W.big_list, (int32_t)L.scan_tiles);
-    PCP_LAUNCH_CHECK("scan_cells_fused_kernel");
+    PCP_CUDA(launch_pdl(kPdlScan, scan_cells_fused_kernel, dim3((unsigned)L.scan_tiles), dim3(kScanThreads), 0, stream,
+                        W.cell, W.cell_rank, L.cells, nx, ny, W.tile_info, W.tile_info + 16 * (L.scan_tiles + 1), W.hdr, W.seg_off,
+                        voxel_coords_out, pillar_count_out, W.lists, L.lo, W.long_table, W.big_list, (int32_t)L.scan_tiles));
   } else {
     tile_sums_kernel<<<(unsigned)L.scan_tiles, kScanThreads, 0, stream>>>(W.cell, L.cells, nx, ny, W.tile_info,
                                                                         W.tile_info + 16 * (L.scan_tiles + 1));
@@ -1009,22 +1016,21 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
   }
   {
     const unsigned blocks = (unsigned)((n + 256 * kPtsPerThread - 1) / (256 * kPtsPerThread));
-    place_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(W.key, W.within, W.cell, W.cell_rank, n, W.sorted_idx,
-                                                          point_pillar_out, W.hdr, counts_out);
-    PCP_LAUNCH_CHECK("place_kernel");
+    PCP_CUDA(launch_pdl(kPdlPlace, place_kernel, dim3(blocks ? blocks : 1), dim3(256), 0, stream, W.key, W.within, W.cell, W.cell_rank, n,
+                        W.sorted_idx, point_pillar_out, W.hdr, counts_out));
   }
   if (n > 0) {
     const int64_t want = (n + kPrepThreads - 1) / kPrepThreads;
     const int64_t cap = (int64_t)sm_count() * 4;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     const bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    const float4* no_rec = nullptr;
     if (vec4)
-      pillar_prep_kernel<true, false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, nullptr, W.hdr, W.lists, L.lo, W.long_table,
-                                                                          W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
+      PCP_CUDA(launch_pdl(kPdlPrep, pillar_prep_kernel<true, false>, dim3(blocks), dim3(kPrepThreads), 0, stream, points, stride, no_rec, W.hdr,
+                          W.lists, L.lo, W.long_table, W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15));
     else
-      pillar_prep_kernel<false, false><<<blocks, kPrepThreads, 0, stream>>>(points, stride, nullptr, W.hdr, W.lists, L.lo, W.long_table,
-                                                                           W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15);
-    PCP_LAUNCH_CHECK("pillar_prep_kernel");
+      PCP_CUDA(launch_pdl(kPdlPrep, pillar_prep_kernel<false, false>, dim3(blocks), dim3(kPrepThreads), 0, stream, points, stride, no_rec, W.hdr,
+                          W.lists, L.lo, W.long_table, W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15));
   }
   return 0;
 }

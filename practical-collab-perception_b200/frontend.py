@@ -307,9 +307,12 @@ class PipelinedFrontEnd:
     written AND the consumer has had the chance to read it (``release`` records the consumer's stream).
     """
 
-    def __init__(self, grid: GridSpec, c_raw: int, max_frames: int, depth: int = 2, **kwargs):
+    def __init__(self, grid: GridSpec, c_raw: int, max_frames: int, depth: int = 2, priorities: Tuple[int, int] = (-5, 0),
+                 **kwargs):
+        """priorities: CUDA stream priorities of the (voxelize + PFN, canvas) branches; lower = more urgent."""
         if depth < 1:
             raise ValueError("depth must be >= 1")
+        self.priorities = (int(priorities[0]), int(priorities[1]))
         self.max_frames = int(max_frames)
         self.stages = [FrontEnd(grid, c_raw, **kwargs) for _ in range(depth)]
         self.sets = [{} for _ in range(depth)]
@@ -326,7 +329,8 @@ class PipelinedFrontEnd:
     def _ensure_streams(self, device):
         if self._streams is None or self._streams[0].device != device:
             # lower number = higher priority; CUDA clamps to the device's range
-            self._streams = (torch.cuda.Stream(device=device, priority=-5), torch.cuda.Stream(device=device, priority=0))
+            self._streams = (torch.cuda.Stream(device=device, priority=self.priorities[0]),
+                             torch.cuda.Stream(device=device, priority=self.priorities[1]))
         return self._streams
 
     @device_guard
