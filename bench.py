@@ -227,7 +227,7 @@ def workload_config(n_gpus):
                         f"0.2 m pillars, 512x512 canvas, C_raw {C_RAW}, PFN 11->32,64->64",
             "frames_per_gpu": FRAMES_PER_GPU, "points_per_frame": POINTS_PER_FRAME, "global_frames": FRAMES_PER_GPU * n_gpus,
             "parallelism": f"frames sharded over {n_gpus} GPU(s), no hot-path collective",
-            "voxelize": "pcp_voxelize_method AUTO = dense-histogram compaction (the radix-sort method is selectable and slower)",
+            "voxelize": "pcp_voxelize_method AUTO = dense-histogram compaction (the radix-sort and binned methods are selectable and slower)",
             "pipelining": "steady state: canvas of batch i on a low-priority stream beside voxelize of batch i+1, 2 buffer sets, "
                           "one CUDA graph launch per step",
             "l2": "per-step working set ~0.95 GB >> 126 MB L2 (537 MB canvas streamed every step); 2 input batches alternate"}
@@ -680,7 +680,7 @@ def run_ours(args):
                               "d2h_bytes_per_step": 4 * _lib.PCP_COUNTS_LEN, "steps": e2e_steps,
                               "api": "collate_batch's (N, 8) fp32 rows copied whole, then the same two modules"},
             # quantise, tile sums, cell scan, place, pillar prep, pfn, long-pillar finish, canvas (+1 memset) per step
-            "single_frame": {"note": "one frame, serial chain (memset + 8 kernels) as ONE CUDA graph launch, L2 flushed before "
+            "single_frame": {"note": "one frame, serial chain (memset + 7 kernels) as ONE CUDA graph launch, L2 flushed before "
                                      "every replay, median of 10; frac = SURVEY 8d bytes / time / measured copy bandwidth",
                              **single},
             "gpu_launches": 8 * args.steps,
