@@ -16,6 +16,10 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
         "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_srcunit_tex_op_atom.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_atom.sum.per_second", "lts__t_sectors_srcunit_tex_op_atom_dot_alu.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_atom_dot_alu_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_atom_dot_alu_lookup_miss.sum",
+        "lts__t_requests_srcunit_tex_op_red.sum", "lts__t_requests_srcunit_tex_op_read.sum", "lts__t_requests_srcunit_tex_op_write.sum",
         "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum",
         "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
