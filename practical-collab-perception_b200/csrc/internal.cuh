@@ -39,6 +39,43 @@ inline cudaError_t launch_pdl(int edge, void (*kernel)(KArgs...), dim3 grid, dim
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- optional wall-clock trace of the kernels of a step (debug build only: make dbg; tools/stage_trace.py): every kernel
+//      records the earliest CTA start and the latest CTA end (globaltimer, ns) in a per-translation-unit table ----
+#if defined(PCP_STAGE_TRACE) && defined(__CUDACC__)
+#define STAGE_TABLE(name) static __device__ unsigned long long name[8][2]
+#define STAGE_BEGIN(tab, id)                                                                          \
+  do {                                                                                                \
+    if (threadIdx.x == 0) {                                                                           \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      atomicMin(&tab[id][0], t_);                                                                     \
+    }                                                                                                 \
+  } while (0)
+#define STAGE_END(tab, id)                                                                            \
+  do {                                                                                                \
+    if (threadIdx.x == 0) {                                                                           \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      atomicMax(&tab[id][1], t_);                                                                     \
+    }                                                                                                 \
+  } while (0)
+#define STAGE_EXPORT(fn, tab)                                                                         \
+  extern "C" int fn(unsigned long long* host16, int reset) {                                          \
+    if (reset) {                                                                                      \
+      unsigned long long init[8][2];                                                                  \
+      for (int i = 0; i < 8; ++i) { init[i][0] = ~0ull; init[i][1] = 0ull; }                          \
+      return (int)cudaMemcpyToSymbol(tab, init, sizeof(init));                                        \
+    }                                                                                                 \
+    cudaDeviceSynchronize();                                                                          \
+    return (int)cudaMemcpyFromSymbol(host16, tab, sizeof(unsigned long long) * 16);                   \
+  }
+#else
+#define STAGE_TABLE(name)
+#define STAGE_BEGIN(tab, id)
+#define STAGE_END(tab, id)
+#define STAGE_EXPORT(fn, tab)
+#endif
+
 // voxelize.cu: everything after the keying kernel (cell scan, placement, ascending row order inside every cell;
 // the xyz mean only when `points` is given).
 int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, int32_t ny, const float* points, int64_t stride,

@@ -33,6 +33,7 @@ namespace pcp {
 
 using namespace umma;
 
+STAGE_TABLE(g_stage_pfn);           // 0 pfn_slot_kernel
 constexpr int kTcThreads = 256;     // threads of the self-test kernels
 // ---- roles of the PFN kernel (one persistent CTA per SM, 25 warps) ----
 //   warps  0.. 7  E0: layer-0 epilogue      (pillar p = tid & 127, column half h = (tid >> 7) & 1)
@@ -182,6 +183,7 @@ pfn_slot_kernel(const TcArgs A) {
   const bool with_dist = kCfg ? false : (A.with_distance != 0);
   const SmemPlan SP = smem_plan(k0, kLayers, NREG, RowCfg<kCfg>::depth);
   const int tid = threadIdx.x, warp = tid >> 5;
+  STAGE_BEGIN(g_stage_pfn, 0);
   int* const s_rows = reinterpret_cast<int*>(smem + SP.rows);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + SP.ints);
   uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem + SP.ints + 28);
@@ -806,6 +808,7 @@ pfn_slot_kernel(const TcArgs A) {
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+  STAGE_END(g_stage_pfn, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -974,6 +977,8 @@ extern "C" int pcp_selftest_umma_cycles(int32_t mode, int32_t n, int32_t ksteps,
   PCP_LAUNCH_CHECK("umma_cycles_kernel");
   return 0;
 }
+
+STAGE_EXPORT(pcp_debug_stage_pfn, pcp::g_stage_pfn)
 
 #ifdef PCP_PFN_TIMING
 // debug: copies the event trace of CTA 0 (3 roles x kTraceCap x (id, clock)) and the 3 event counts to host memory

@@ -10,6 +10,7 @@
 
 namespace pcp {
 
+STAGE_TABLE(g_stage_canvas);  // 0 canvas_v8_kernel
 constexpr int kTileX = 128;   // columns per CTA (32 lanes x 4)
 constexpr int kTileY = 8;     // rows per CTA (one warp per row)
 
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kTileY * 32, kMinBlocks)
 canvas_v8_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_map, int channels, int nx, int ny,
                  float* __restrict__ canvas) {
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  STAGE_BEGIN(g_stage_canvas, 0);
   const int b = blockIdx.z;
   const int y = blockIdx.y * kTileY + wy;
   const int x0 = blockIdx.x * kTileX + lane * 4;
@@ -129,6 +131,8 @@ canvas_v8_kernel(const float* __restrict__ pf, const int32_t* __restrict__ rank_
 #pragma unroll
     for (int q = 0; q < 8; ++q) st_stream_f4(dst + (int64_t)(c + q) * nxy, v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]);
   }
+  __syncthreads();            // trace only: warps that streamed zeros left earlier
+  STAGE_END(g_stage_canvas, 0);
 }
 
 // TMA variant of canvas_v8_kernel (additionally nx % 128 == 0, ny % 8 == 0: every CTA owns a full 8 x 128 patch).  Per step
@@ -217,6 +221,8 @@ num_frames_kernel(const int32_t* __restrict__ coords, int64_t P, int32_t* __rest
 }  // namespace pcp
 
 using namespace pcp;
+
+STAGE_EXPORT(pcp_debug_stage_canvas, g_stage_canvas)
 
 static dim3 canvas_grid(int nx, int ny, int frames) {
   return dim3((unsigned)((nx + kTileX - 1) / kTileX), (unsigned)((ny + kTileY - 1) / kTileY), (unsigned)frames);

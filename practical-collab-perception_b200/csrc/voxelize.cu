@@ -20,6 +20,8 @@
 
 namespace pcp {
 
+STAGE_TABLE(g_stage_vox);      // 0 quantise_count, 1 cell scan, 2 place, 3 pillar_prep
+
 // ------------------------------------------------------------------------------------------------
 // 1. quantise + count
 // ------------------------------------------------------------------------------------------------
@@ -30,6 +32,7 @@ __global__ void __launch_bounds__(256)
 quantise_count_kernel(const float* __restrict__ points, int64_t stride, int64_t n, int32_t frames,
                       pcp_grid g, int32_t* __restrict__ cell, int32_t* __restrict__ key,
                       int32_t* __restrict__ within, int32_t* __restrict__ hdr) {
+  STAGE_BEGIN(g_stage_vox, 0);
   pdl_launch_dependents();
   const int64_t base = (int64_t)blockIdx.x * (256 * kPtsPerThread) + threadIdx.x;
   float bf[kPtsPerThread], x[kPtsPerThread], y[kPtsPerThread];
@@ -66,6 +69,7 @@ quantise_count_kernel(const float* __restrict__ points, int64_t stride, int64_t 
     const int64_t i = base + u * 256;
     if (i < n) { key[i] = k[u]; within[i] = w[u]; }
   }
+  STAGE_END(g_stage_vox, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,6 +358,7 @@ scan_cells_fused_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_r
   __shared__ int32_t s_poff[kScanTileCells];     // its first sorted position (local to the tile until the prefix is known)
   __shared__ uint16_t s_pidx[kScanTileCells];    // its cell inside the tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  STAGE_BEGIN(g_stage_vox, 1);
   pdl_launch_dependents();
   pdl_wait();
   if (tid == 0) { s_tile = atomicAdd(&hdr[kHdrScanTicket], 1); s_fr = 0; }
@@ -552,6 +557,7 @@ scan_cells_fused_kernel(int32_t* __restrict__ cell, int32_t* __restrict__ cell_r
       if (cnt > kWarpLongMax) big_list[s_before[kTiBig] + atomicAdd(&s_cls[kTiBig], 1)] = li;
     }
   }
+  STAGE_END(g_stage_vox, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -562,6 +568,7 @@ place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within
              const int32_t* __restrict__ cell, const int32_t* __restrict__ cell_rank, int64_t n,
              int32_t* __restrict__ sorted_idx, int32_t* __restrict__ point_pillar,
              const int32_t* __restrict__ hdr, int32_t* __restrict__ counts_out) {
+  STAGE_BEGIN(g_stage_vox, 2);
   pdl_launch_dependents();
   pdl_wait();
   const int64_t base = (int64_t)blockIdx.x * (256 * kPtsPerThread) + threadIdx.x;
@@ -585,6 +592,7 @@ place_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ within
     if (k[u] >= 0) sorted_idx[o[u] + w[u]] = (int32_t)i;
     if (point_pillar && i < n) point_pillar[i] = (k[u] >= 0) ? __ldg(cell_rank + k[u]) : -1;
   }
+  STAGE_END(g_stage_vox, 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -731,6 +739,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
   __shared__ float s_red[3][8];
   __shared__ int s_chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  STAGE_BEGIN(g_stage_vox, 3);
   pdl_launch_dependents();
   pdl_wait();
   const int nlong = hdr[kHdrLongCount];
@@ -989,6 +998,7 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
       }
     }
   }
+  STAGE_END(g_stage_vox, 3);
 }
 
 }  // namespace pcp
@@ -1057,6 +1067,8 @@ int launch_pillar_prep_rec(const WsLayout& L, const WsView& W, const float* poin
 }  // namespace pcp
 
 using namespace pcp;
+
+STAGE_EXPORT(pcp_debug_stage_voxelize, g_stage_vox)
 
 extern "C" size_t pcp_workspace_bytes(int64_t n_points, int32_t max_frames, int32_t nx, int32_t ny) {
   if (n_points < 0 || max_frames <= 0 || nx <= 0 || ny <= 0) return 0;
