@@ -311,6 +311,12 @@ int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols
                           const int32_t* agent_offsets, const double* se3, int32_t num_agents,
                           const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
                           float* rows_out, int64_t out_stride, int32_t* count_out, void* stream);
+/* pcp_fuse_agent_points() over per-agent clouds left where they are: cloud_ptrs is a DEVICE array of num_agents device pointers
+ * (agent a's (N_a, in_stride) rows; agent_offsets their prefix sums as above) - no concatenation of the inputs. */
+int pcp_fuse_agent_clouds(const float* const* cloud_ptrs, int64_t in_stride, int32_t n_cols, int64_t n_points,
+                          const int32_t* agent_offsets, const double* se3, int32_t num_agents,
+                          const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
+                          float* rows_out, int64_t out_stride, int32_t* count_out, void* stream);
 
 /*
  * Producer side of the exchange: the foreground records one agent broadcasts.  Replaces, in the test-time branch of

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "pcp_fuse_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "pcp_fuse_agent_points": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int32, _P, C.c_int32, C.c_float, _P,
                                         _P, C.c_int64, _P, _P]),
+    "pcp_fuse_agent_clouds": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int32, _P, C.c_int32, C.c_float, _P,
+                                        _P, C.c_int64, _P, _P]),
     "pcp_select_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "pcp_select_foreground": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_float,
                                         _P, _P, C.c_int64, _P, _P]),

@@ -17,6 +17,7 @@ constexpr int kFuseItems = 4;
 constexpr int kFuseBlock = kFuseThreads * kFuseItems;   // rows per CTA
 
 struct FuseArgs {
+  const float* const* ptrs;  // per-agent clouds (device array of device pointers), or NULL: one concatenated block at `points`
   const float* points;
   int64_t in_stride;
   int32_t n_cols;            // columns of an input row (x, y, z, ...), all copied
@@ -34,10 +35,15 @@ __device__ __forceinline__ int agent_of(const int32_t* __restrict__ off, int na,
 }
 
 // transformed xyz of row i (fp64 products and sums in the reference's matmul order, one rounding to fp32) and its mask
+__device__ __forceinline__ const float* fuse_src(const FuseArgs& A, int64_t i, int a) {
+  return A.ptrs ? A.ptrs[a] + (i - A.agent_off[a]) * A.in_stride : A.points + i * A.in_stride;
+}
+
 __device__ __forceinline__ bool fuse_row(const FuseArgs& A, int64_t i, float& x, float& y, float& z) {
-  const float* row = A.points + i * A.in_stride;
+  const int a = agent_of(A.agent_off, A.num_agents, i);
+  const float* row = fuse_src(A, i, a);
   const double px = (double)__ldg(row), py = (double)__ldg(row + 1), pz = (double)__ldg(row + 2);
-  const double* T = A.se3 + 12 * agent_of(A.agent_off, A.num_agents, i);
+  const double* T = A.se3 + 12 * a;
   // numpy: (xyz @ R.T)[k] = x R[k,0] + y R[k,1] + z R[k,2] accumulated left to right, then + t[k]
   x = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, T[0]), __dmul_rn(py, T[1])), __dmul_rn(pz, T[2])), T[3]);
   y = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, T[4]), __dmul_rn(py, T[5])), __dmul_rn(pz, T[6])), T[7]);
@@ -122,7 +128,7 @@ fuse_write_kernel(const FuseArgs A, int64_t n, const int32_t* __restrict__ block
   for (int u = 0; u < kFuseItems; ++u) {
     if (!keep[u]) continue;
     const int64_t i = (int64_t)blockIdx.x * kFuseBlock + (int64_t)tid * kFuseItems + u;
-    const float* row = A.points + i * A.in_stride;
+    const float* row = fuse_src(A, i, agent_of(A.agent_off, A.num_agents, i));
     float* dst = out + (int64_t)pos * out_stride;
     if (with_batch_col) *dst++ = batch_idx;
     dst[0] = x[u]; dst[1] = y[u]; dst[2] = z[u];
@@ -356,19 +362,19 @@ extern "C" size_t pcp_fuse_scratch_bytes(int64_t n_points) {
   return sizeof(int32_t) * (size_t)((n_points + kFuseBlock - 1) / kFuseBlock + 1);
 }
 
-extern "C" int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols, int64_t n_points,
-                                     const int32_t* agent_offsets, const double* se3, int32_t num_agents,
-                                     const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
-                                     float* rows_out, int64_t out_stride, int32_t* count_out, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int fuse_launch(const float* const* cloud_ptrs, const float* points, int64_t in_stride, int32_t n_cols, int64_t n_points,
+                       const int32_t* agent_offsets, const double* se3, int32_t num_agents, const float* range6_host,
+                       int32_t with_batch_col, float batch_idx, int32_t* scratch, float* rows_out, int64_t out_stride,
+                       int32_t* count_out, cudaStream_t stream) {
   PCP_REQUIRE(count_out && scratch, PCP_E_INVALID, "pcp_fuse_agent_points: null argument");
   PCP_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - kFuseBlock, PCP_E_INVALID, "pcp_fuse_agent_points: n_points out of range");
-  PCP_REQUIRE(n_points == 0 || (points && rows_out && agent_offsets && se3), PCP_E_INVALID, "pcp_fuse_agent_points: null input");
+  PCP_REQUIRE(n_points == 0 || ((points || cloud_ptrs) && rows_out && agent_offsets && se3), PCP_E_INVALID,
+              "pcp_fuse_agent_points: null input");
   PCP_REQUIRE(n_cols >= 3 && in_stride >= n_cols && out_stride >= n_cols + (with_batch_col ? 1 : 0), PCP_E_INVALID,
               "pcp_fuse_agent_points: bad column counts / strides");
   PCP_REQUIRE(num_agents >= 1 && num_agents <= 64, PCP_E_INVALID, "pcp_fuse_agent_points: 1 <= num_agents <= 64");
   FuseArgs A{};
-  A.points = points; A.in_stride = in_stride; A.n_cols = n_cols; A.agent_off = agent_offsets; A.se3 = se3; A.num_agents = num_agents;
+  A.ptrs = cloud_ptrs; A.points = points; A.in_stride = in_stride; A.n_cols = n_cols; A.agent_off = agent_offsets; A.se3 = se3; A.num_agents = num_agents;
   A.apply_mask = range6_host != nullptr;
   if (range6_host)
     for (int k = 0; k < 3; ++k) { A.lo[k] = range6_host[k]; A.hi[k] = range6_host[3 + k]; }
@@ -384,4 +390,21 @@ extern "C" int pcp_fuse_agent_points(const float* points, int64_t in_stride, int
   fuse_write_kernel<<<nblk, kFuseThreads, 0, stream>>>(A, n_points, scratch, with_batch_col, batch_idx, rows_out, out_stride);
   PCP_LAUNCH_CHECK("fuse_write_kernel");
   return 0;
+}
+
+extern "C" int pcp_fuse_agent_points(const float* points, int64_t in_stride, int32_t n_cols, int64_t n_points,
+                                     const int32_t* agent_offsets, const double* se3, int32_t num_agents,
+                                     const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
+                                     float* rows_out, int64_t out_stride, int32_t* count_out, void* stream_) {
+  return fuse_launch(nullptr, points, in_stride, n_cols, n_points, agent_offsets, se3, num_agents, range6_host, with_batch_col,
+                     batch_idx, scratch, rows_out, out_stride, count_out, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int pcp_fuse_agent_clouds(const float* const* cloud_ptrs, int64_t in_stride, int32_t n_cols, int64_t n_points,
+                                     const int32_t* agent_offsets, const double* se3, int32_t num_agents,
+                                     const float* range6_host, int32_t with_batch_col, float batch_idx, int32_t* scratch,
+                                     float* rows_out, int64_t out_stride, int32_t* count_out, void* stream_) {
+  PCP_REQUIRE(n_points == 0 || cloud_ptrs, PCP_E_INVALID, "pcp_fuse_agent_clouds: null cloud_ptrs");
+  return fuse_launch(cloud_ptrs, nullptr, in_stride, n_cols, n_points, agent_offsets, se3, num_agents, range6_host, with_batch_col,
+                     batch_idx, scratch, rows_out, out_stride, count_out, static_cast<cudaStream_t>(stream_));
 }

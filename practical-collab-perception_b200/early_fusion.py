@@ -35,18 +35,20 @@ def fuse_agent_points(ego_points: torch.Tensor, agent_points: Sequence[torch.Ten
         _require_cuda(t, "agent_points")
         if t.shape[1] != ncols:
             raise ValueError("all clouds must have the same number of columns")
-    allp = torch.cat([t.detach().float() for t in clouds], dim=0).contiguous()      # device memory plumbing only
-    n = allp.shape[0]
+    # the clouds stay where they are: the kernels take one device pointer per agent (no concatenated copy of the inputs)
+    clouds = [t.detach() if (t.dtype == torch.float32 and t.is_contiguous()) else t.detach().float().contiguous() for t in clouds]
     offs = np.zeros(len(clouds) + 1, dtype=np.int32)
     offs[1:] = np.cumsum([t.shape[0] for t in clouds])
+    n = int(offs[-1])
     se3 = np.zeros((len(clouds), 12), dtype=np.float64)
     se3[0] = np.eye(4)[:3].reshape(-1)
     for i, tf in enumerate(target_se3_agents):
         tf = np.asarray(tf, dtype=np.float64)
         assert tf.shape == (4, 4)
         se3[i + 1] = tf[:3].reshape(-1)
-    d_offs = torch.from_numpy(offs).to(dev)
-    d_se3 = torch.from_numpy(se3).to(dev)
+    ptrs = np.asarray([t.data_ptr() if t.shape[0] else 0 for t in clouds], dtype=np.uint64)
+    from .modar import _upload
+    d_se3, d_offs, d_ptrs = _upload(dev, [se3, offs, ptrs])       # one small asynchronous H2D from pinned staging
     with_b = batch_idx is not None
     out = torch.empty((max(n, 1), ncols + (1 if with_b else 0)), dtype=torch.float32, device=dev)
     scratch = torch.empty(int(lib.pcp_fuse_scratch_bytes(n)) // 4 + 1, dtype=torch.int32, device=dev)
@@ -54,8 +56,8 @@ def fuse_agent_points(ego_points: torch.Tensor, agent_points: Sequence[torch.Ten
     rng = None
     if point_cloud_range is not None:
         rng = (C.c_float * 6)(*[float(np.float32(v)) for v in point_cloud_range])   # np.float32 range: dataset.py:25
-    rc = lib.pcp_fuse_agent_points(_ptr(allp), allp.stride(0), ncols, n, _ptr(d_offs), _ptr(d_se3), len(clouds),
+    rc = lib.pcp_fuse_agent_clouds(_ptr(d_ptrs), ncols, ncols, n, _ptr(d_offs), _ptr(d_se3), len(clouds),
                                    rng, int(with_b), C.c_float(float(batch_idx or 0)), _ptr(scratch), _ptr(out),
                                    out.stride(0), _ptr(count), _stream())
-    _lib.check(rc, "pcp_fuse_agent_points")
+    _lib.check(rc, "pcp_fuse_agent_clouds")
     return out[:int(count.item())]

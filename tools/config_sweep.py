@@ -131,5 +131,5 @@ emit({"config": "8f-2: DynamicMeanVFE, SECOND grid 1024 x 1024 x 40, 2 x 150k po
 clouds = [syn.lidar_frame(50000, 9000 + k)[:, 1:].contiguous().to(dev) for k in range(6)]
 tfs = [syn.modar_agent(9100 + k, n_boxes=1)["target_se3_agent"] for k in range(5)]
 t_fu = timed(lambda: pcp_b200.fuse_agent_points(clouds[0], clouds[1:], tfs, rng, batch_idx=0))
-emit({"config": "8f-3: early-fusion assembly, 6 clouds x 50k points", "us": {"fuse_agent_points (incl. torch.cat, pose H2D, count read-back)": t_fu},
+emit({"config": "8f-3: early-fusion assembly, 6 clouds x 50k points", "us": {"fuse_agent_points (per-agent pointers, one small H2D, count read-back)": t_fu},
       "mpts_per_s": 300000 / t_fu})
