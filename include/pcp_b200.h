@@ -109,7 +109,7 @@ int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int3
 
 /*
  * pcp_voxelize() with the compaction algorithm chosen by the caller (pillars, maps, counts identical bit for bit; means
- * identical for pillars of up to 4096 points):
+ * identical too - sequential sums in ascending row order for pillars of any length):
  *   PCP_VOXELIZE_HISTOGRAM  dense per-cell histogram with one L2 atomic per point + cell scan + counting-sort placement + an
  *                           ordering pass per pillar (csrc/voxelize.cu); any size.  The faster one on the B200 at every size
  *                           measured (profiles/r02_voxelize_time_*.json), hence:
@@ -117,8 +117,7 @@ int pcp_voxelize(const float* points, int64_t row_stride, int64_t n_points, int3
  *   PCP_VOXELIZE_RADIX      stable two-digit MSD radix sort on the linear key: partition into bins of 512 / 1024 consecutive
  *                           cells, then a counting sort + run-length per bin in shared memory (csrc/voxelize_radix.cu).  No
  *                           global atomics, no gathers; rows ascend inside every pillar by construction, so the per-pillar
- *                           mean is the sequential sum in row order for pillars of ANY length (the histogram path falls back
- *                           to arrival order above 4096 points).  Covers key spaces of at most 4 M cells (16 frames of
+ *                           mean is the sequential sum in row order for pillars of ANY length.  Covers key spaces of at most 4 M cells (16 frames of
  *                           512 x 512) and 1 .. 16.6 M rows; PCP_E_UNSUPPORTED outside.
  *   PCP_VOXELIZE_BINNED     one coarse partition pass into bins of 2048 consecutive cells ({x, y, z, row} records, unordered
  *                           inside a bin), then one CTA per bin: rows per cell, scan, placement, pillars of up to 8 rows put in

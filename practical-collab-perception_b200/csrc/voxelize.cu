@@ -734,9 +734,13 @@ __global__ void __launch_bounds__(kPrepThreads, 4)
 pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float4* __restrict__ srec, int32_t* __restrict__ hdr,
                    unsigned long long* __restrict__ lists, const ListOffsets lo, const int4* __restrict__ long_table,
                    const int32_t* __restrict__ big_list, int32_t* __restrict__ sorted_idx, float4* __restrict__ mean,
-                   float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, const pcp_grid g, int phase_mask) {
+                   float4* __restrict__ long_mean, unsigned* __restrict__ long_acc, const pcp_grid g, int phase_mask,
+                   int32_t* __restrict__ tmp) {
   __shared__ __align__(16) PrepSmem sm;
   __shared__ float s_red[3][8];
+  __shared__ int s_red_i[kPrepWarps];
+  __shared__ int s_flag;
+  __shared__ int32_t s_bucket[kBigSegMax + 1];       // giant pillars: first position of every 4096-row bucket
   __shared__ int s_chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   STAGE_BEGIN(g_stage_vox, 3);
@@ -762,15 +766,14 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
       lists[lo.off[kSegList] + sb + i] = pack_entry(li, off + i * kSegRows, min(kSegRows, n - i * kSegRows));
     for (int i = tid; i < 96; i += kPrepThreads) long_acc[(int64_t)li * 96 + i] = kAccInit;
     int32_t* s = sm.cta.s;
-    float mx, my, mz;
-    if (n <= kBigSegMax) {
-      if (n <= kCountSortMax) {
+    // sort `cnt` (<= kBigSegMax) row numbers, fetched by `src(i)`, ascending in s[]
+    auto sort_rows = [&](int cnt, auto src) {
+      if (cnt <= kCountSortMax) {
         int32_t* s2 = sm.cta.scratch;
-        const int n4 = (n + 3) & ~3;
-        for (int i = tid; i < n4; i += kPrepThreads)
-          s[i] = (i < n) ? (kRec ? __float_as_int(__ldcg(srec + off + i).w) : sorted_idx[off + i]) : 0x7fffffff;
+        const int n4 = (cnt + 3) & ~3;
+        for (int i = tid; i < n4; i += kPrepThreads) s[i] = (i < cnt) ? src(i) : 0x7fffffff;
         __syncthreads();
-        for (int i = tid; i < n; i += kPrepThreads) {
+        for (int i = tid; i < cnt; i += kPrepThreads) {
           const int32_t v = s[i];
           int rank = 0;
           for (int j = 0; j < n4; j += 4) {
@@ -780,88 +783,164 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
           s2[rank] = v;
         }
         __syncthreads();
-        for (int i = tid; i < n; i += kPrepThreads) s[i] = s2[i];
+        for (int i = tid; i < cnt; i += kPrepThreads) s[i] = s2[i];
         __syncthreads();
       } else {
         int m = 2048;
-        while (m < n) m <<= 1;
-        for (int i = tid; i < m; i += kPrepThreads)
-          s[i] = (i < n) ? (kRec ? __float_as_int(__ldcg(srec + off + i).w) : sorted_idx[off + i]) : 0x7fffffff;
+        while (m < cnt) m <<= 1;
+        for (int i = tid; i < m; i += kPrepThreads) s[i] = (i < cnt) ? src(i) : 0x7fffffff;
         __syncthreads();
         for (int k = 2; k <= m; k <<= 1) {
           for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < m; i += kPrepThreads) {
-              const int p = i ^ j;
-              if (p > i) {
-                const int32_t a = s[i], b = s[p];
+              const int p2 = i ^ j;
+              if (p2 > i) {
+                const int32_t va = s[i], vb = s[p2];
                 const bool up = (i & k) == 0;
-                if ((a > b) == up) { s[i] = b; s[p] = a; }
+                if ((va > vb) == up) { s[i] = vb; s[p2] = va; }
               }
             }
             __syncthreads();
           }
         }
       }
-      // sequential sums in ascending row order, rows staged kSumChunk at a time (double buffered: one barrier per chunk)
+    };
+    // the sorted rows s[0 .. cnt) go to sorted_idx[out_off ..); their x, y, z are added to the running sums IN ORDER (warps 0, 1, 2
+    // lane 0 own the three accumulators), rows staged kSumChunk at a time (double buffered: one barrier per chunk)
+    float acc = 0.f;
+    float cellw = 0.f;
+    auto sum_rows = [&](int cnt, int out_off, bool first) {
       float* ch = reinterpret_cast<float*>(sm.cta.scratch);      // [2][3][kSumChunk]
-      float acc = 0.f;
-      float cellw = 0.f;
-      for (int c0 = 0; c0 < n; c0 += kSumChunk) {
+      for (int c0 = 0; c0 < cnt; c0 += kSumChunk) {
         float* buf = ch + ((c0 / kSumChunk) & 1) * (3 * kSumChunk);
         const int i = c0 + tid;
-        if (i < n) {
+        if (i < cnt) {
           const int32_t idx = s[i];
-          sorted_idx[off + i] = idx;
+          sorted_idx[out_off + i] = idx;
           float x, y, z;
           load_xyz<kVec4>(points, stride, idx, x, y, z);
-          if (i == 0) cellw = pack_cell(x, y, g);
+          if (first && i == 0) cellw = pack_cell(x, y, g);
           buf[tid] = x; buf[kSumChunk + tid] = y; buf[2 * kSumChunk + tid] = z;
         }
         __syncthreads();
         if (warp < 3 && lane == 0) {
-          const float* src = buf + warp * kSumChunk;
-          const int m = min(kSumChunk, n - c0);
-          for (int q = 0; q < m; ++q) acc = __fadd_rn(acc, src[q]);
+          const float* srcv = buf + warp * kSumChunk;
+          const int m = min(kSumChunk, cnt - c0);
+          for (int q = 0; q < m; ++q) acc = __fadd_rn(acc, srcv[q]);
         }
       }
+      __syncthreads();                                           // s[] and the staging buffers are free again
+    };
+    auto row_at = [&](int i) { return kRec ? __float_as_int(__ldcg(srec + off + i).w) : sorted_idx[off + i]; };
+    bool exact = true;
+    if (n <= kBigSegMax) {
+      sort_rows(n, row_at);
+      sum_rows(n, off, true);
+    } else {
+      // Giant pillar.  Row numbers are distinct integers, so a bucket of 4096 consecutive row numbers holds at most 4096 of the
+      // pillar's rows: counting sort by bucket (row >> 12) into the scratch array `tmp`, then consecutive buckets are taken
+      // together while they fit, ordered in shared memory like a <= 4096-row pillar, and summed - one running sum over
+      // the whole pillar, in ascending row order, as the reference's CPU scatter_mean does.  Covers row numbers below
+      // 4096 * 4096 = 16.7 M; above that the sum falls back to arrival order (tolerance, flagged nowhere else).
+      for (int i = tid; i <= kBigSegMax; i += kPrepThreads) s_bucket[i] = 0;
+      if (tid == 0) s_flag = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kPrepThreads) {
+        const int bkt = row_at(i) >> 12;
+        if (bkt < kBigSegMax) atomicAdd(&s_bucket[bkt + 1], 1); else s_flag = 1;
+      }
+      __syncthreads();
+      exact = (s_flag == 0) && (tmp != nullptr);
+      if (exact) {
+        // exclusive scan of the 4096 bucket counts (16 per thread): s_bucket[b] = first position of bucket b, [4096] = n
+        {
+          int v[16], run = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = s_bucket[1 + tid * 16 + j]; run += v[j]; }
+          int incl = run;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+          }
+          if (lane == 31) s_red_i[warp] = incl;
+          __syncthreads();
+          int base = incl - run;
+          for (int w = 0; w < warp; ++w) base += s_red_i[w];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { base += v[j]; v[j] = base; }           // inclusive
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s_bucket[1 + tid * 16 + j] = v[j];
+        }
+        __syncthreads();
+        for (int i = tid; i < kBigSegMax; i += kPrepThreads) s[i] = s_bucket[i];      // running cursors
+        __syncthreads();
+        for (int i = tid; i < n; i += kPrepThreads) {
+          const int32_t row = row_at(i);
+          tmp[off + atomicAdd(&s[row >> 12], 1)] = row;
+        }
+        __syncthreads();
+        int g_lo = 0;
+        bool first = true;
+        while (g_lo < kBigSegMax) {
+          if (tid == 0) {
+            int hi = g_lo + 1;
+            while (hi < kBigSegMax && s_bucket[hi + 1] - s_bucket[g_lo] <= kBigSegMax) ++hi;
+            s_flag = hi;
+          }
+          __syncthreads();
+          const int g_hi = s_flag;
+          const int p0 = s_bucket[g_lo], cnt = s_bucket[g_hi] - p0;
+          __syncthreads();
+          if (cnt > 0) {
+            sort_rows(cnt, [&](int i) { return __ldcg(tmp + off + p0 + i); });
+            sum_rows(cnt, off + p0, first);
+            first = false;
+          }
+          g_lo = g_hi;
+        }
+      } else {
+        // arrival order, strided partial sums + tree (within tolerance, not order-canonical)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int i = tid; i < n; i += kPrepThreads) {
+          float x, y, z;
+          if (kRec) {
+            const float4 rc = __ldcg(srec + off + i);
+            x = rc.x; y = rc.y; z = rc.z;
+            sorted_idx[off + i] = __float_as_int(rc.w);
+          } else {
+            load_xyz<kVec4>(points, stride, sorted_idx[off + i], x, y, z);
+          }
+          a0 += x; a1 += y; a2 += z;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d); a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+        }
+        if (lane == 0) { s_red[0][warp] = a0; s_red[1][warp] = a1; s_red[2][warp] = a2; }
+        __syncthreads();
+        if (tid < 3) {
+          float t = 0.f;
+          for (int w = 0; w < kPrepWarps; ++w) t += s_red[tid][w];
+          s_red[tid][0] = __fdiv_rn(t, (float)n);
+        }
+        if (tid == 0) {
+          float x, y, z;
+          if (kRec) { const float4 rc = __ldcg(srec + off); x = rc.x; y = rc.y; }
+          else load_xyz<kVec4>(points, stride, sorted_idx[off], x, y, z);
+          s_red[0][1] = pack_cell(x, y, g);
+        }
+        __syncthreads();
+      }
+    }
+    float mx, my, mz;
+    if (exact) {
       if (warp < 3 && lane == 0) s_red[warp][0] = __fdiv_rn(acc, (float)n);
       if (tid == 0) s_red[0][1] = cellw;
       __syncthreads();
-      mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
-    } else {
-      // giant pillar: arrival order, strided partial sums + tree (within tolerance, not order-canonical)
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-      for (int i = tid; i < n; i += kPrepThreads) {
-        float x, y, z;
-        if (kRec) {
-          const float4 rc = __ldcg(srec + off + i);
-          x = rc.x; y = rc.y; z = rc.z;
-          sorted_idx[off + i] = __float_as_int(rc.w);
-        } else {
-          load_xyz<kVec4>(points, stride, sorted_idx[off + i], x, y, z);
-        }
-        a0 += x; a1 += y; a2 += z;
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d); a2 += __shfl_xor_sync(0xffffffffu, a2, d);
-      }
-      if (lane == 0) { s_red[0][warp] = a0; s_red[1][warp] = a1; s_red[2][warp] = a2; }
-      __syncthreads();
-      if (tid < 3) {
-        float acc = 0.f;
-        for (int w = 0; w < kPrepWarps; ++w) acc += s_red[tid][w];
-        s_red[tid][0] = __fdiv_rn(acc, (float)n);
-      }
-      __syncthreads();
-      mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
-      if (tid == 0) {
-        float x, y, z;
-        if (kRec) { const float4 rc = __ldcg(srec + off); x = rc.x; y = rc.y; }
-        else load_xyz<kVec4>(points, stride, sorted_idx[off], x, y, z);
-        s_red[0][1] = pack_cell(x, y, g);
-      }
     }
+    mx = s_red[0][0]; my = s_red[1][0]; mz = s_red[2][0];
     if (tid == 0) {
       const float cw = s_red[0][1];
       long_mean[li] = make_float4(mx, my, mz, cw);
@@ -1037,10 +1116,10 @@ int finish_grouping(const WsLayout& L, const WsView& W, int64_t n, int32_t nx, i
     const float4* no_rec = nullptr;
     if (vec4)
       PCP_CUDA(launch_pdl(kPdlPrep, pillar_prep_kernel<true, false>, dim3(blocks), dim3(kPrepThreads), 0, stream, points, stride, no_rec, W.hdr,
-                          W.lists, L.lo, W.long_table, W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15));
+                          W.lists, L.lo, W.long_table, W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15, W.within));
     else
       PCP_CUDA(launch_pdl(kPdlPrep, pillar_prep_kernel<false, false>, dim3(blocks), dim3(kPrepThreads), 0, stream, points, stride, no_rec, W.hdr,
-                          W.lists, L.lo, W.long_table, W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15));
+                          W.lists, L.lo, W.long_table, W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 15, W.within));
   }
   return 0;
 }
@@ -1057,10 +1136,10 @@ int launch_pillar_prep_rec(const WsLayout& L, const WsView& W, const float* poin
   const bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
   if (vec4)
     pillar_prep_kernel<true, true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.rsrec, W.hdr, W.lists, L.lo, W.long_table,
-                                                                       W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 7);
+                                                                       W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 7, W.within);
   else
     pillar_prep_kernel<false, true><<<blocks, kPrepThreads, 0, stream>>>(points, stride, W.rsrec, W.hdr, W.lists, L.lo, W.long_table,
-                                                                        W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 7);
+                                                                        W.big_list, W.sorted_idx, W.mean, W.long_mean, W.long_acc, grid, 7, W.within);
   PCP_LAUNCH_CHECK("pillar_prep_kernel(records)");
   return 0;
 }
