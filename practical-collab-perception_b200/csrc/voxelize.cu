@@ -720,7 +720,8 @@ constexpr int kPrepWarps = kPrepThreads / 32;
 constexpr int kCountSortMax = 1024;   // CTA path: ranked by counting up to this size, bitonic network above
 constexpr int kSumChunk = 256;        // CTA path: rows staged per step of the sequential sum
 
-// Shared memory of a CTA (24 KB, static): either 8 per-warp regions of 3 x 256 words (warp path), or the CTA path's
+// Shared memory of a CTA (24 KB, static; measured: 12 KB is no faster, 41 KB - which drops the L1 to its 92 KB configuration with
+// four resident CTAs - costs 16 us on the bench batch): either 8 per-warp regions of 3 x 256 words (warp path), or the CTA path's
 // row-number array [kBigSegMax] followed by 2048 words of scratch (counting-sort output / double-buffered xyz chunks).
 struct PrepSmem {
   union {
@@ -740,7 +741,6 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
   __shared__ float s_red[3][8];
   __shared__ int s_red_i[kPrepWarps];
   __shared__ int s_flag;
-  __shared__ int32_t s_bucket[kBigSegMax + 1];       // giant pillars: first position of every 4096-row bucket
   __shared__ int s_chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   STAGE_BEGIN(g_stage_vox, 3);
@@ -838,25 +838,25 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
       sum_rows(n, off, true);
     } else {
       // Giant pillar.  Row numbers are distinct integers, so a bucket of 4096 consecutive row numbers holds at most 4096 of the
-      // pillar's rows: counting sort by bucket (row >> 12) into the scratch array `tmp`, then consecutive buckets are taken
+      // pillar's rows: counting sort by bucket (row >> 12) into the scratch array `tmp`, then whole buckets are taken
       // together while they fit, ordered in shared memory like a <= 4096-row pillar, and summed - one running sum over
       // the whole pillar, in ascending row order, as the reference's CPU scatter_mean does.  Covers row numbers below
-      // 4096 * 4096 = 16.7 M; above that the sum falls back to arrival order (tolerance, flagged nowhere else).
-      for (int i = tid; i <= kBigSegMax; i += kPrepThreads) s_bucket[i] = 0;
+      // 4096 * 4096 = 16.7 M; above that the sum falls back to arrival order (tolerance).
+      for (int i = tid; i < kBigSegMax; i += kPrepThreads) s[i] = 0;
       if (tid == 0) s_flag = 0;
       __syncthreads();
       for (int i = tid; i < n; i += kPrepThreads) {
         const int bkt = row_at(i) >> 12;
-        if (bkt < kBigSegMax) atomicAdd(&s_bucket[bkt + 1], 1); else s_flag = 1;
+        if (bkt < kBigSegMax) atomicAdd(&s[bkt], 1); else s_flag = 1;
       }
       __syncthreads();
       exact = (s_flag == 0) && (tmp != nullptr);
       if (exact) {
-        // exclusive scan of the 4096 bucket counts (16 per thread): s_bucket[b] = first position of bucket b, [4096] = n
+        // in-place exclusive scan of the 4096 bucket counts (16 per thread): s[b] = first position of bucket b = its cursor
         {
           int v[16], run = 0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { v[j] = s_bucket[1 + tid * 16 + j]; run += v[j]; }
+          for (int j = 0; j < 16; ++j) { v[j] = s[tid * 16 + j]; run += v[j]; }
           int incl = run;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -868,37 +868,35 @@ pillar_prep_kernel(const float* __restrict__ points, int64_t stride, const float
           int base = incl - run;
           for (int w = 0; w < warp; ++w) base += s_red_i[w];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { base += v[j]; v[j] = base; }           // inclusive
-          __syncthreads();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s_bucket[1 + tid * 16 + j] = v[j];
+          for (int j = 0; j < 16; ++j) { s[tid * 16 + j] = base; base += v[j]; }
         }
-        __syncthreads();
-        for (int i = tid; i < kBigSegMax; i += kPrepThreads) s[i] = s_bucket[i];      // running cursors
         __syncthreads();
         for (int i = tid; i < n; i += kPrepThreads) {
           const int32_t row = row_at(i);
           tmp[off + atomicAdd(&s[row >> 12], 1)] = row;
         }
         __syncthreads();
-        int g_lo = 0;
+        // tmp[off ..] now holds the rows grouped by bucket, buckets ascending.  Windows of up to 4096 rows, cut back to the last
+        // bucket boundary inside them (the rows of the bucket that continues behind the window wait for the next one)
         bool first = true;
-        while (g_lo < kBigSegMax) {
-          if (tid == 0) {
-            int hi = g_lo + 1;
-            while (hi < kBigSegMax && s_bucket[hi + 1] - s_bucket[g_lo] <= kBigSegMax) ++hi;
-            s_flag = hi;
+        for (int p0 = 0; p0 < n;) {
+          int cnt = min(kBigSegMax, n - p0);
+          if (p0 + cnt < n) {
+            const int next_bkt = __ldcg(tmp + off + p0 + cnt) >> 12;
+            if (tid == 0) s_flag = 0;
+            __syncthreads();
+            int mine = 0;
+            for (int i = tid; i < cnt; i += kPrepThreads) mine += ((__ldcg(tmp + off + p0 + i) >> 12) == next_bkt) ? 1 : 0;
+            mine = __reduce_add_sync(0xffffffffu, mine);
+            if (lane == 0 && mine) atomicAdd(&s_flag, mine);
+            __syncthreads();
+            cnt -= s_flag;            // > 0: a bucket holds at most 4096 rows and one of them lies behind the window
+            __syncthreads();
           }
-          __syncthreads();
-          const int g_hi = s_flag;
-          const int p0 = s_bucket[g_lo], cnt = s_bucket[g_hi] - p0;
-          __syncthreads();
-          if (cnt > 0) {
-            sort_rows(cnt, [&](int i) { return __ldcg(tmp + off + p0 + i); });
-            sum_rows(cnt, off + p0, first);
-            first = false;
-          }
-          g_lo = g_hi;
+          sort_rows(cnt, [&](int i) { return __ldcg(tmp + off + p0 + i); });
+          sum_rows(cnt, off + p0, first);
+          first = false;
+          p0 += cnt;
         }
       } else {
         // arrival order, strided partial sums + tree (within tolerance, not order-canonical)
