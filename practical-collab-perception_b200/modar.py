@@ -58,35 +58,54 @@ _staging = {}   # (device, stream, thread) -> [pinned uint8 buffer, event of the
 _staging_lock = threading.Lock()
 
 
+class _DevPtr:
+    """A device address inside a staging upload (what ``frontend._ptr`` returns for a tensor); ``keep`` pins the buffer."""
+    __slots__ = ("ptr", "keep")
+
+    def __init__(self, ptr, keep):
+        self.ptr, self.keep = ptr, keep
+
+    def data_ptr(self):
+        return self.ptr
+
+
+_RING = 4     # staging buffers per (device, stream, thread): a call only waits for the copy issued four calls earlier
+
+
 def _upload(dev, arrays):
     """One asynchronous H2D copy for all the small host-side arrays of a call (poses, offsets, pointers): they are packed
-    into a pinned staging buffer (8-byte aligned pieces) and come back as typed views of one device buffer.  One staging
-    buffer per (device, stream, host thread): concurrent callers never share one."""
+    into a pinned staging buffer (8-byte aligned pieces) and come back as device addresses inside one device buffer.  A small
+    ring of staging buffers per (device, stream, host thread): concurrent callers never share one, and a caller does not wait
+    for its own previous copy."""
     sizes = [(a.nbytes + 7) // 8 * 8 for a in arrays]
     total = max(sum(sizes), 8)
     key = (dev, torch.cuda.current_stream(dev).cuda_stream, threading.get_ident())
     with _staging_lock:
-        st = _staging.get(key)
+        ring = _staging.get(key)
+        if ring is None:
+            ring = {"slots": [None] * _RING, "next": 0}
+            _staging[key] = ring
+        i = ring["next"]
+        ring["next"] = (i + 1) % _RING
+        st = ring["slots"][i]
         if st is None or st[0].numel() < total:
             st = [torch.empty(max(total, 4096), dtype=torch.uint8).pin_memory(), None]
-            _staging[key] = st
+            ring["slots"][i] = st
     if st[1] is not None:
-        st[1].synchronize()                      # the previous call's copy has left the staging buffer
+        st[1].synchronize()                      # the copy issued _RING calls ago has left this staging buffer
     host = st[0].numpy()
-    o = 0
+    offs, o = [], 0
     for a, sz in zip(arrays, sizes):
-        host[o:o + a.nbytes] = np.frombuffer(a.tobytes(), dtype=np.uint8)
+        host[o:o + a.nbytes].view(a.dtype)[:] = a.reshape(-1)
+        offs.append(o)
         o += sz
     d = torch.empty(total, dtype=torch.uint8, device=dev)
     d.copy_(st[0][:total], non_blocking=True)
     ev = torch.cuda.Event()
-    ev.record(torch.cuda.current_stream())
+    ev.record(torch.cuda.current_stream(dev))
     st[1] = ev
-    views, o = [], 0
-    for a, sz in zip(arrays, sizes):
-        views.append(d[o:o + a.nbytes].view(torch.from_numpy(a[:0].copy()).dtype).reshape(a.shape))
-        o += sz
-    return views
+    base = d.data_ptr()
+    return [_DevPtr(base + off, d) for off in offs]
 
 
 def modar_exchange(detections, foreground, target_se3_agent, t_detect: float, t_query: float,
