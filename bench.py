@@ -426,10 +426,17 @@ def run_ours(args):
     if rank == 0:
         try:
             flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-            for name, npts, cfg_id in (("car_32k_points", 32768, 1), ("early_fusion_300k_points", POINTS_PER_FRAME, CONFIG_ID)):
-                fe_s = FrontEnd(gs, C_RAW)
-                fe_s.packed = pipe.stages[0].packed
-                pts_s = syn.batch_of_frames(1, npts, cfg_id).to(dev)
+            for name, npts, cfg_id, ego in (("car_32k_points", 32768, 1, False), ("ego_lately_fusion_33k_points", 32938, 2, True),
+                                            ("early_fusion_300k_points", POINTS_PER_FRAME, CONFIG_ID, False)):
+                if ego:                      # BASELINE configs[1]: 14-column ego rows (11 raw features -> PFN 17 -> 32, 64 -> 64)
+                    fe_s = FrontEnd(gs, 11)
+                    sd_e = syn.pfn_state_dict(17)
+                    bn_e = lambda i: [sd_e[f"pfn_layers.{i}.norm.{k}"].to(dev) for k in ("weight", "bias", "running_mean", "running_var")]
+                    fe_s.pack_params(sd_e["pfn_layers.0.linear.weight"].to(dev), bn_e(0), sd_e["pfn_layers.1.linear.weight"].to(dev), bn_e(1))
+                else:
+                    fe_s = FrontEnd(gs, C_RAW)
+                    fe_s.packed = pipe.stages[0].packed
+                pts_s = syn.batch_of_frames(1, npts, cfg_id, ego_columns=ego).to(dev)
                 out_s, canvas_s = {}, torch.empty((1, 64, gs.ny, gs.nx), dtype=torch.float32, device=dev)
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -451,7 +458,7 @@ def run_ours(args):
                     if i >= 3:
                         ts.append(a0.elapsed_time(a1) * 1e3)
                 c_s = fe_s.read_counts(out_s)
-                alg_s = npts * row_bytes + int(c_s[0]) * (64 * 4 + 16) + 64 * gs.ny * gs.nx * 4
+                alg_s = npts * 4 * pts_s.shape[1] + int(c_s[0]) * (64 * 4 + 16) + 64 * gs.ny * gs.nx * 4
                 us = statistics.median(ts)
                 single[name] = {"us_per_frame": us, "pillars": int(c_s[0]), "algorithmic_bytes": alg_s,
                                 "frac": alg_s / (us * 1e-6) / 1e9 / peak, "frames_per_s": 1e6 / us}
