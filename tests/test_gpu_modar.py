@@ -167,6 +167,24 @@ def test_exchange_messages_packed_on_the_gpu_feed_modar_and_nms(tmp_path):
     assert torch.equal(s1, s2) and torch.equal(sc1, sc2) and s1.numel() > 0
 
 
+def test_agents_without_boxes_or_foreground():
+    """Ragged exchange: one agent reports no boxes, one reports boxes but no foreground points - the per-agent pointer entry
+    (pcp_modar_agents) against the oracle."""
+    import pcp_b200
+    from pcp_b200 import synthetic as syn
+    ego14, agents = syn.modar_scene(2, 7, n_agents=3, n_ego_points=2048)
+    agents[1]["modar"] = agents[1]["modar"][:0]
+    agents[1]["foreground"] = agents[1]["foreground"][:0]
+    agents[2]["foreground"] = agents[2]["foreground"][:0]
+    pts = pcp_b200.modar_exchange([a["modar"] for a in agents], [a["foreground"] for a in agents],
+                                  [a["target_se3_agent"] for a in agents], 0.0, 0.2, ego14.to(DEV))
+    want = mo.modar_exchange(ego14[:, 1:].numpy(), [{k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in a.items()} for a in agents],
+                             float(ego14[:, -2].max()), 2.0)
+    got = pts.cpu().numpy()
+    assert got.shape[0] == want.shape[0] == 2048 + agents[0]["modar"].shape[0] + agents[2]["modar"].shape[0]
+    np.testing.assert_allclose(got[:, 1:], want, rtol=1e-5, atol=2e-5)
+
+
 def test_single_message_call_forms():
     """The documented one-agent forms: a bare ExchangeMessage (a NamedTuple - it must not be iterated as four agents),
     a bare detections dict and a bare (M, 9) tensor, each with a bare (4, 4) pose."""

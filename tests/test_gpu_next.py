@@ -190,6 +190,27 @@ def test_early_fusion_golden():
     _close_fp64_rounded(nomask, g["ref_fused_nomask"])
 
 
+def test_early_fusion_ragged_agents():
+    """An agent that sent nothing, an empty ego cloud, non-contiguous / float64 inputs: the per-agent pointer path
+    (pcp_fuse_agent_clouds) against the oracle."""
+    import pcp_b200
+    from pcp_b200 import synthetic as syn
+    rng = np.asarray(syn.V2X_RANGE, dtype=np.float32)
+    clouds = [syn.lidar_frame(n, 8300 + a)[:, 1:].contiguous() for a, n in enumerate((500, 0, 1234, 1))]
+    tfs = [syn.modar_agent(8400 + a, n_boxes=1)["target_se3_agent"] for a in range(3)]
+    want = no.fuse_agent_points(clouds[0].numpy(), [c.numpy() for c in clouds[1:]], tfs, rng)
+    got = pcp_b200.fuse_agent_points(clouds[0].to(DEV), [clouds[1].to(DEV), clouds[2].double().to(DEV), clouds[3].to(DEV)], tfs, rng,
+                                     batch_idx=0)
+    assert got.shape == (want.shape[0], 8)
+    _close_fp64_rounded(got.cpu().numpy()[:, 1:], want)
+    # empty ego, strided agent rows (a column slice of a wider tensor)
+    wide = torch.cat([clouds[2], torch.zeros(clouds[2].shape[0], 3)], dim=1).to(DEV)
+    want2 = no.fuse_agent_points(clouds[1].numpy(), [clouds[2].numpy()], tfs[:1], rng)
+    got2 = pcp_b200.fuse_agent_points(clouds[1].to(DEV), [wide[:, :7]], tfs[:1], rng, batch_idx=None)
+    assert got2.shape == want2.shape
+    _close_fp64_rounded(got2.cpu().numpy(), want2)
+
+
 def test_early_fusion_feeds_the_pillar_path():
     """BASELINE configs[2] shape in small: 6 clouds fused on the GPU, then DynamicPillarVFE + PointPillarScatter; checked
     against the oracle chain on the CPU-fused cloud."""
