@@ -209,12 +209,16 @@ class FrontEnd:
         out["capacity"] = cap
         out.pop("counts_host", None)
         if host_counts:
+            # a small ring of pinned blocks: the counts of a call stay readable until eight later calls have been made
             if self._counts_pinned is None:
-                self._counts_pinned = torch.empty(_lib.PCP_COUNTS_LEN, dtype=torch.int32).pin_memory()
-            self._counts_pinned.copy_(counts, non_blocking=True)
+                self._counts_pinned = torch.empty((8, _lib.PCP_COUNTS_LEN), dtype=torch.int32).pin_memory()
+                self._counts_slot = 0
+            pinned = self._counts_pinned[self._counts_slot]
+            self._counts_slot = (self._counts_slot + 1) % 8
+            pinned.copy_(counts, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
-            out["counts_host"] = (self._counts_pinned, ev)
+            out["counts_host"] = (pinned, ev)
         return out
 
     @device_guard
