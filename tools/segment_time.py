@@ -1,3 +1,6 @@
+"""Device time of the stand-alone segment reductions (pcp_segment_reduce: scatter_mean / scatter_max over the pillars) on the
+bench batch and the stress clouds; PCP_LIB=... times an alternative build.
+    python tools/segment_time.py"""
 import os, sys, json, statistics
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
