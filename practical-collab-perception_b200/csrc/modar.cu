@@ -73,8 +73,12 @@ modar_membership_kernel(const float* __restrict__ boxes_cat, const float* const*
 }
 
 // 3 + 4. one warp per box: grid (box chunks, agents).  The agent's membership array is staged in shared memory in panels, so
-// the scan over the foreground points never waits on global memory; only the flow of the box's own points is gathered.
-constexpr int kIdxPanel = 8192;
+// the scan over the foreground points never waits on global memory.  The box's own points are first COLLECTED (their numbers,
+// in ascending order, kMemberCap at a time), then their flow vectors are gathered with every lane's loads in flight at once,
+// then summed sequentially in point order by lanes 0 / 1 / 2 - the scan never stalls on a gather (it did: one exposed global
+// round trip per 32-point step that held a member made this the longest kernel of the exchange, 79 us for 170 boxes).
+constexpr int kIdxPanel = 4096;
+constexpr int kMemberCap = 192;
 
 __global__ void __launch_bounds__(256)
 modar_rows_kernel(const float* __restrict__ boxes_cat, const float* const* __restrict__ box_ptrs,
@@ -96,8 +100,22 @@ modar_rows_kernel(const float* __restrict__ boxes_cat, const float* const* __res
   const double* T = se3 + 12 * a;
   const double yaw_T = atan2(T[4], T[0]);  // rotation_matrix_to_yaw: arctan2(R10, R00), nuscenes_temporal_utils.py:28-29
   const int k = blockIdx.x * nwarp + warp;
-  float sx = 0.f, sy = 0.f, sz = 0.f;
-  int cnt = 0;
+  __shared__ int32_t s_mem[8][kMemberCap];            // per warp: point numbers of the box's members, ascending
+  __shared__ float s_flow[8][3][kMemberCap];          // per warp: their flow vectors
+  float acc = 0.f;                                    // lanes 0 / 1 / 2: running sums of flow x / y / z
+  int cnt = 0, nm = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  auto flush = [&](int n_m) {
+    __syncwarp();
+    for (int j = lane; j < n_m; j += 32) {
+      const float* p = fg + (int64_t)s_mem[warp][j] * 13;
+      s_flow[warp][0][j] = p[10]; s_flow[warp][1][j] = p[11]; s_flow[warp][2][j] = p[12];   // flow3 = last three columns (:213)
+    }
+    __syncwarp();
+    if (lane < 3)
+      for (int j = 0; j < n_m; ++j) acc = __fadd_rn(acc, s_flow[warp][lane][j]);           // sequential, ascending point order
+    __syncwarp();
+  };
   for (int p0 = 0; p0 < F; p0 += kIdxPanel) {
     const int pc = min(kIdxPanel, F - p0);
     __syncthreads();
@@ -107,24 +125,17 @@ modar_rows_kernel(const float* __restrict__ boxes_cat, const float* const* __res
       for (int i0 = 0; i0 < pc; i0 += 32) {
         const int i = i0 + lane;
         const bool mine = (i < pc) && (s_idx[i] == k);
-        unsigned m = __ballot_sync(0xffffffffu, mine);
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
         if (m == 0) continue;
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        if (mine) {
-          const float* p = fg + (int64_t)(p0 + i) * 13;
-          fx = p[10]; fy = p[11]; fz = p[12];     // flow3 = last three columns (v2x_sim_dataset_ego.py:213)
-        }
-        cnt += __popc(m);
-        while (m) {                                // sequential fp32 adds in ascending point order
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          sx = __fadd_rn(sx, __shfl_sync(0xffffffffu, fx, l));
-          sy = __fadd_rn(sy, __shfl_sync(0xffffffffu, fy, l));
-          sz = __fadd_rn(sz, __shfl_sync(0xffffffffu, fz, l));
-        }
+        if (mine) s_mem[warp][nm + __popc(m & lt)] = p0 + i;
+        const int c = __popc(m);
+        nm += c; cnt += c;
+        if (nm > kMemberCap - 32) { flush(nm); nm = 0; }
       }
     }
   }
+  if (k < M && nm) flush(nm);
+  const float sx = __shfl_sync(0xffffffffu, acc, 0), sy = __shfl_sync(0xffffffffu, acc, 1), sz = __shfl_sync(0xffffffffu, acc, 2);
   if (k >= M) return;
   const float* bx = boxes + (int64_t)k * 9;
   float ox = 0.f, oy = 0.f, oz = 0.f;
